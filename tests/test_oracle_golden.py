@@ -1,0 +1,65 @@
+"""Pin the CPU oracle (oracle/vae_oracle.py) to outputs of the UNMODIFIED reference
+(tests/golden/*.npz, produced by oracle/make_golden.py from /root/reference)."""
+import pytest
+import torch
+
+from oracle import vae_oracle as O
+from oracle import weights as W
+
+from conftest import load_golden
+
+TOL = 2e-5  # fp32 CPU vs fp32 CPU; only summation order differs
+
+
+def _check(ref, out, tol=TOL):
+    assert ref.shape == out.shape
+    assert O.rel_err(ref, out) < tol
+
+
+def test_ops_conv_stride_variants():
+    _, a = load_golden("ops")
+    for tag, s in (("s111", (1, 1, 1)), ("s122", (1, 2, 2)), ("s222", (2, 2, 2)), ("s422", (4, 2, 2))):
+        _check(a[f"conv_{tag}_y"], O.causal_conv3d(a["x"], a["conv_w"], a["conv_b"], s))
+    _check(a["conv1_y"], O.causal_conv3d(a["x"], a["conv1_w"], None))
+
+
+def test_ops_upsample_first_frame_rule():
+    _, a = load_golden("ops")
+    assert torch.equal(a["up_u222_y"], O.upsample_nearest_causal(a["x"], (2, 2, 2)))
+    assert torch.equal(a["up_u122_y"], O.upsample_nearest_causal(a["x"], (1, 2, 2)))
+    assert torch.equal(a["up_u222_T1_y"], O.upsample_nearest_causal(a["x"][:, :, :1], (2, 2, 2)))
+
+
+def test_ops_mask():
+    _, a = load_golden("ops")
+    assert torch.equal(a["mask_3_4"], O.frame_causal_mask(3, 4))
+
+
+def test_ops_resnet_and_midblock():
+    _, a = load_golden("ops")
+    rsd = {k[len("res_sd."):]: v for k, v in a.items() if k.startswith("res_sd.")}
+    _check(a["res_y"], O.resnet_block(rsd, "", a["x"], 32))
+    msd = {k[len("mid_sd."):]: v for k, v in a.items() if k.startswith("mid_sd.")}
+    _check(a["mid_y"], O.mid_block(msd, "", a["mid_x"], 32))
+
+
+@pytest.mark.parametrize("name", ["small_untiled", "small_untiled_b2", "small_spatial", "small_temporal",
+                                  "small_tiled", "hy_untiled", "small_tops_pool_interp", "small_tops_stride4"])
+def test_model_cases(name):
+    meta, a = load_golden(name)
+    cfg = getattr(W, meta["cfg"])
+    sd = W.make_state_dict(cfg, meta["weight_seed"])
+    tl = O.Tiling.from_cfg(cfg, meta["spatial"], meta["temporal"])
+    x = W.make_video(tuple(meta["shape"]), meta["video_seed"])
+    mom = O.encode_moments(sd, cfg, x, tl, meta["t_ops"])
+    _check(a["moments"], mom)
+    mean, _ = O.posterior_mean_logvar(a["moments"])
+    dec = O.decode(sd, cfg, mean.clone(), tl, meta["t_ops"])
+    _check(a["dec"], dec)
+    assert O.psnr(a["dec"], dec) > 80
+
+
+def test_spec_has_248_keys():
+    assert len(W.state_dict_spec(W.HY_VAE_CONFIG)) == 248
+    n = sum(torch.Size(s).numel() for s in W.state_dict_spec(W.HY_VAE_CONFIG).values())
+    assert n == 246_478_803  # SURVEY.md §8c [measured]
