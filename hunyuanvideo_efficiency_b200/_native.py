@@ -1,0 +1,227 @@
+"""ctypes binding of libhyvae.so (include/hyvae.h) and the channels-last volume container.
+
+There is NO CPU fallback: every op below enqueues a hand-written sm_100a kernel on the current CUDA
+stream, and loading fails loudly when the shared library has not been built
+(`make -C hunyuanvideo_efficiency_b200/csrc`, or `python -c "import __graft_entry__ as g; g.build()"`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhyvae.so")
+
+BF16, F32, F16 = 0, 1, 2
+_DT = {torch.bfloat16: BF16, torch.float32: F32, torch.float16: F16}
+
+
+class HyvaeError(RuntimeError):
+    pass
+
+
+class _CVol(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("dtype", C.c_int32), ("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32),
+                ("W", C.c_int32), ("C", C.c_int32), ("pt", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32)]
+
+
+_VP = C.POINTER(_CVol)
+_i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+# name -> argtypes; every entry returns int status (include/hyvae.h)
+_SIGNATURES = {
+    "hyvae_ncthw_to_vol": [_vp, _i32, C.POINTER(_i64), _VP, _vp],
+    "hyvae_vol_to_ncthw": [_VP, _vp, _i32, _vp],
+    "hyvae_conv3d_causal_direct": [_VP, _vp, _vp, _VP, _VP, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "hyvae_conv3d_causal_tc": [_VP, _vp, _vp, _VP, _VP, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "hyvae_groupnorm_stats": [_VP, _i32, _vp, _vp],
+    "hyvae_groupnorm_apply": [_VP, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _VP, _vp],
+    "hyvae_pad_upsample": [_VP, _VP, _i32, _i32, _i32, _vp],
+    "hyvae_softmax_frame_causal": [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp],
+    "hyvae_avgpool_t": [_VP, _VP, _i32, _i32, _vp],
+    "hyvae_interp_t_nearest": [_VP, _VP, _f32, _vp],
+    "hyvae_blend_crop_scatter": [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32,
+                                 _i32, _i32, _i32, _i32, C.POINTER(_i64), _vp],
+}
+EXPORTS = sorted(list(_SIGNATURES) + ["hyvae_version", "hyvae_last_error", "hyvae_device_supports_tc", "hyvae_launch_count"])
+
+_lib = None
+
+
+def lib():
+    """Load libhyvae.so once.  Raises HyvaeError if it is missing — the product has no other path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HyvaeError(f"{LIB_PATH} not found: build the CUDA extension first "
+                             f"(make -C {os.path.join(_HERE, 'csrc')}); there is no CPU fallback")
+        l = C.CDLL(LIB_PATH)
+        for name, args in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        l.hyvae_version.restype = C.c_int
+        l.hyvae_last_error.restype = C.c_char_p
+        l.hyvae_device_supports_tc.restype = C.c_int
+        l.hyvae_launch_count.restype = C.c_int64
+        _lib = l
+    return _lib
+
+
+def _check(status: int, what: str):
+    if status != 0:
+        raise HyvaeError(f"{what} failed ({status}): {lib().hyvae_last_error().decode()}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().hyvae_launch_count())
+
+
+_tc_ok: Optional[bool] = None
+
+
+def device_supports_tc() -> bool:
+    global _tc_ok
+    if _tc_ok is None:
+        _tc_ok = bool(lib().hyvae_device_supports_tc())
+    return _tc_ok
+
+
+class Vol:
+    """Channels-last activation volume [B][T+pt][H+2ph][W+2pw][C] in HBM (see hyvae_vol)."""
+
+    __slots__ = ("t", "B", "T", "H", "W", "C", "pad", "_c")
+
+    def __init__(self, B, T, H, W, Cn, dtype, device, pad: Tuple[int, int, int] = (0, 0, 0), tensor=None):
+        pt, ph, pw = pad
+        shape = (B, T + pt, H + 2 * ph, W + 2 * pw, Cn)
+        if tensor is None:
+            tensor = torch.empty(shape, dtype=dtype, device=device)
+        else:
+            assert tuple(tensor.shape) == shape and tensor.is_contiguous()
+        if tensor.device.type != "cuda":
+            raise HyvaeError("hyvae volumes live in CUDA memory; there is no CPU execution path")
+        self.t, self.B, self.T, self.H, self.W, self.C, self.pad = tensor, B, T, H, W, Cn, tuple(pad)
+        self._c = _CVol(tensor.data_ptr(), _DT[tensor.dtype], B, T, H, W, Cn, pt, ph, pw)
+
+    @property
+    def dtype(self):
+        return self.t.dtype
+
+    @property
+    def device(self):
+        return self.t.device
+
+    @property
+    def dims(self):
+        return (self.B, self.T, self.H, self.W, self.C)
+
+    def ref(self):
+        return C.byref(self._c)
+
+    def like(self, C_=None, pad=(0, 0, 0), dtype=None, T=None, H=None, W=None) -> "Vol":
+        return Vol(self.B, T or self.T, H or self.H, W or self.W, C_ or self.C, dtype or self.dtype, self.device, pad)
+
+    def interior(self) -> torch.Tensor:
+        """Logical [B,T,H,W,C] view (no halo)."""
+        pt, ph, pw = self.pad
+        return self.t[:, pt:, ph:ph + self.H, pw:pw + self.W, :]
+
+    # ---- NCTHW <-> volume -------------------------------------------------------------------
+    @staticmethod
+    def from_ncthw(x: torch.Tensor, dtype=None, pad=(0, 0, 0)) -> "Vol":
+        assert x.ndim == 5
+        B, Cn, T, H, W = x.shape
+        v = Vol(B, T, H, W, Cn, dtype or x.dtype, x.device, pad)
+        strides = (_i64 * 5)(*x.stride())
+        _check(lib().hyvae_ncthw_to_vol(x.data_ptr(), _DT[x.dtype], strides, v.ref(), _stream()), "ncthw_to_vol")
+        return v
+
+    def to_ncthw(self, dtype=None) -> torch.Tensor:
+        out = torch.empty((self.B, self.C, self.T, self.H, self.W), dtype=dtype or self.dtype, device=self.device)
+        _check(lib().hyvae_vol_to_ncthw(self.ref(), out.data_ptr(), _DT[out.dtype], _stream()), "vol_to_ncthw")
+        return out
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------ ops
+def conv_out_dims(T, H, W, stride, up=(1, 1, 1)):
+    Tl = 1 + 2 * (T - 1) if up[0] == 2 else T
+    Hl, Wl = H * up[1], W * up[2]
+    return (Tl - 1) // stride[0] + 1, (Hl - 1) // stride[1] + 1, (Wl - 1) // stride[2] + 1
+
+
+def conv3d_direct(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, residual: Optional[Vol] = None,
+                  up=(1, 1, 1), out_dtype=None, round_like_ref=True, out: Optional[Vol] = None) -> Vol:
+    To, Ho, Wo = conv_out_dims(x.T, x.H, x.W, stride, up)
+    y = out if out is not None else Vol(x.B, To, Ho, Wo, cout, out_dtype or x.dtype, x.device)
+    _check(lib().hyvae_conv3d_causal_direct(x.ref(), w.data_ptr(), _ptr(bias), residual.ref() if residual else None, y.ref(),
+                                            k, stride[0], stride[1], stride[2], up[0], up[1], up[2],
+                                            int(round_like_ref), _stream()), "conv3d_causal_direct")
+    return y
+
+
+def conv3d_tc(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, residual: Optional[Vol] = None,
+              out_dtype=None, round_like_ref=True, variant=0, out: Optional[Vol] = None) -> Vol:
+    To, Ho, Wo = conv_out_dims(x.T, x.H, x.W, stride)
+    y = out if out is not None else Vol(x.B, To, Ho, Wo, cout, out_dtype or x.dtype, x.device)
+    _check(lib().hyvae_conv3d_causal_tc(x.ref(), w.data_ptr(), _ptr(bias), residual.ref() if residual else None, y.ref(),
+                                        k, stride[0], stride[1], stride[2], int(round_like_ref), variant, _stream()),
+           "conv3d_causal_tc")
+    return y
+
+
+def groupnorm(x: Vol, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
+              pad=(0, 0, 0), round_like_ref=True) -> Vol:
+    sums = torch.empty((x.B, groups, 2), dtype=torch.float64, device=x.device)
+    _check(lib().hyvae_groupnorm_stats(x.ref(), groups, sums.data_ptr(), _stream()), "groupnorm_stats")
+    y = x.like(pad=pad)
+    _check(lib().hyvae_groupnorm_apply(x.ref(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), groups, eps, int(silu),
+                                       int(round_like_ref), y.ref(), _stream()), "groupnorm_apply")
+    return y
+
+
+def pad_upsample(x: Vol, up=(1, 1, 1), pad=(0, 0, 0)) -> Vol:
+    T = 1 + 2 * (x.T - 1) if up[0] == 2 else x.T
+    y = Vol(x.B, T, x.H * up[1], x.W * up[2], x.C, x.dtype, x.device, pad)
+    _check(lib().hyvae_pad_upsample(x.ref(), y.ref(), up[0], up[1], up[2], _stream()), "pad_upsample")
+    return y
+
+
+def softmax_frame_causal(S: torch.Tensor, n_hw: int, scale: float, p_dtype) -> torch.Tensor:
+    B, L, L2 = S.shape
+    assert L == L2 and S.dtype == torch.float32 and S.is_contiguous()
+    P = torch.empty((B, L, L), dtype=p_dtype, device=S.device)
+    _check(lib().hyvae_softmax_frame_causal(S.data_ptr(), P.data_ptr(), _DT[p_dtype], B, L, n_hw, scale, _stream()),
+           "softmax_frame_causal")
+    return P
+
+
+def avgpool_t(x: Vol, k: int, s: int) -> Vol:
+    y = x.like(T=(x.T - 1) // s + 1)
+    _check(lib().hyvae_avgpool_t(x.ref(), y.ref(), k, s, _stream()), "avgpool_t")
+    return y
+
+
+def interp_t_nearest(x: Vol, scale: float) -> Vol:
+    import math
+    y = x.like(T=int(math.floor(x.T * scale)))
+    _check(lib().hyvae_interp_t_nearest(x.ref(), y.ref(), float(1.0 / scale), _stream()), "interp_t_nearest")
+    return y
+
+
+def blend_crop_scatter(cur: torch.Tensor, above, left, N: int, Yc: int, Xc: int, Ya: int, Xl: int, ev: int, eh: int,
+                       out, Yo: int, Xo: int, y0: int, x0: int, crop_y: int, crop_x: int, n_strides=None):
+    ns = (_i64 * 4)(*n_strides) if n_strides is not None else None
+    _check(lib().hyvae_blend_crop_scatter(cur.data_ptr(), _ptr(above), _ptr(left), _DT[cur.dtype], N, Yc, Xc, Ya, Xl, ev, eh,
+                                          _ptr(out), Yo, Xo, y0, x0, crop_y, crop_x, ns, _stream()), "blend_crop_scatter")

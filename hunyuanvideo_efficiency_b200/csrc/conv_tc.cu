@@ -1,0 +1,427 @@
+// CausalConv3d as an implicit GEMM on the sm_100a tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+// Reference semantics: F.pad(replicate) + nn.Conv3d, unet_causal_3d_blocks.py:73-75 (+ residual :415).
+//
+// GEMM view (NT):  D[m][n] = sum_{tap, c} A_tap[m][c] * W[tap][n][c]
+//   m  = one output voxel of a TH x TW spatial patch of one output frame (TH*TW = 128 = UMMA M)
+//   n  = output channel (BN per CTA tile, UMMA N)
+//   k  = (tap, 64-channel chunk): one TMA box each for A and B per pipeline stage
+// A operand: the input volume already carries the causal replicate halo (hyvae_vol pt/ph/pw), so the
+//   A tile of tap (kt,kh,kw) is the plain 5-D TMA box {64 ch, TW, TH, 1, 1} at
+//   (c0, w0*sw+kw, h0*sh+kh, t*st+kt, b): 128 rows of 128 bytes, SWIZZLE_128B — exactly the K-major
+//   UMMA shared-memory layout.  Strided convs use the tensor map's elementStrides; rows / columns
+//   beyond the volume and channels beyond Cin are zero-filled by TMA.
+// B operand: weights repacked to [tap][Cout][Cin]; 3-D box {64, BN, 1}.
+// D: fp32 accumulators in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps
+//   the main loop of tile i+1.  Epilogue: tcgen05.ld -> +bias (+residual) -> bf16/fp16 -> global.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+//   warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Persistent CTAs, static tile schedule
+//   with the n-tile fastest so concurrent CTAs share the A halo in L2.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace hyvae {
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("hyvae conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) | [32,46) SBO >> 4 = 1024 B
+//   between 8-row core-matrix groups | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::f16 instruction descriptor: fp32 accumulate, A/B both K-major, M = 128.
+//   [4,6) D fmt (1 = f32) | [7,10) A fmt | [10,13) B fmt (0 = f16, 1 = bf16) | [17,23) N >> 3 | [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc(int n, int ab_fmt) {
+  return (1u << 4) | ((uint32_t)ab_fmt << 7) | ((uint32_t)ab_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------- kernel
+struct TcArgs {
+  void* y;
+  const void* res;
+  const float* bias;
+  int64_t ysB, ysT, ysH, ysW, yoff;  // element strides / offset of logical (0,0,0,0) in y
+  int64_t rsB, rsT, rsH, rsW, roff;
+  int B, To, Ho, Wo, Cin, Cout;
+  int k, st, sh, sw;
+  int TH, TW, tiles_h, tiles_w, n_tiles;
+  int64_t total_tiles;
+  int round_like_ref;
+};
+
+constexpr int TC_THREADS = 192;
+constexpr int A_STAGE_BYTES = 128 * 64 * 2;
+
+template <int BN> struct TcCfg {
+  static constexpr int B_STAGE_BYTES = BN * 64 * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <typename T> struct TcFmt;
+template <> struct TcFmt<__nv_bfloat16> { static constexpr int fmt = 1; };
+template <> struct TcFmt<__half> { static constexpr int fmt = 0; };
+
+template <typename T, typename OT, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t bars = sB + STAGES * Cfg::B_STAGE_BYTES;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
+  const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
+  const uint32_t tmem_slot = tempty_bar + 16;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 128); }
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int taps = a.k * a.k * a.k;
+  const int kchunks = (a.Cin + 63) / 64;
+  const int num_kb = taps * kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer =================
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int nt = (int)(tile % a.n_tiles);
+        int64_t mt = tile / a.n_tiles;
+        const int tw = (int)(mt % a.tiles_w); mt /= a.tiles_w;
+        const int th = (int)(mt % a.tiles_h); mt /= a.tiles_h;
+        const int t = (int)(mt % a.To); const int b = (int)(mt / a.To);
+        const int w0 = tw * a.TW * a.sw, h0 = th * a.TH * a.sh, t0 = t * a.st, n0 = nt * BN;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int kt = tap / (a.k * a.k), kh = (tap / a.k) % a.k, kw = tap % a.k;
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+            mbar_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
+            tma_load_5d(sA + stage * A_STAGE_BYTES, &tmA, full_bar + 8 * stage, kc * 64, w0 + kw, h0 + kh, t0 + kt, b);
+            tma_load_3d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, full_bar + 8 * stage, kc * 64, n0, tap);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer =================
+      constexpr uint32_t idesc = make_idesc(BN, TcFmt<T>::fmt);
+      int stage = 0; uint32_t phase = 0;
+      int iter = 0;
+      for (int64_t tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t adesc = make_kmajor_sw128_desc(sA + stage * A_STAGE_BYTES);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sB + stage * Cfg::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 4 x (K = 16) per 64-channel chunk: +32 B along K inside the swizzle atom
+            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    OT* yd = reinterpret_cast<OT*>(a.y);
+    const T* rs = reinterpret_cast<const T*>(a.res);
+    int iter = 0;
+    for (int64_t tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++iter) {
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      const int nt = (int)(tile % a.n_tiles);
+      int64_t mt = tile / a.n_tiles;
+      const int tw = (int)(mt % a.tiles_w); mt /= a.tiles_w;
+      const int th = (int)(mt % a.tiles_h); mt /= a.tiles_h;
+      const int t = (int)(mt % a.To); const int b = (int)(mt / a.To);
+      const int h = th * a.TH + row / a.TW, w = tw * a.TW + row % a.TW;
+      const bool valid = (h < a.Ho) && (w < a.Wo);
+      const int n0 = nt * BN;
+      const int64_t yo = a.yoff + (int64_t)b * a.ysB + (int64_t)t * a.ysT + (int64_t)h * a.ysH + (int64_t)w * a.ysW;
+      const int64_t ro = a.roff + (int64_t)b * a.rsB + (int64_t)t * a.rsT + (int64_t)h * a.rsH + (int64_t)w * a.rsW;
+
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + j * 32), v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + j * 32 + g * 8;
+            if (n < a.Cout) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
+              if (a.bias) {
+                const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n);
+                const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n + 4);
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (rs) {
+                Vec8<T> r; r.load(rs + ro + n);
+                float rf[8]; r.get(rf);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = (a.round_like_ref ? rnd<T>(f[i]) : f[i]) + rf[i];
+              }
+              Vec8<OT> o; o.set(f);
+              o.store(yd + yo + n);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+template <typename T, typename OT, int BN>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<T, OT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+      return fail(HYVAE_ECUDA, "conv_tc: cannot opt in to %d bytes of shared memory", Cfg::SMEM_BYTES);
+    attr_set = true;
+  }
+  int64_t grid = a.total_tiles < num_sms() ? a.total_tiles : num_sms();
+  conv_tc_kernel<T, OT, BN><<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, a);
+  return check_launch("conv3d_causal_tc");
+}
+
+}  // namespace hyvae
+
+using namespace hyvae;
+
+extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
+                                      const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
+                                      int32_t round_like_ref, int32_t variant, void* stream) {
+  if (int e = check_vol(x, "x")) return e;
+  if (int e = check_vol(y, "y")) return e;
+  HYVAE_CHECK_ARG(w != nullptr, "w is null");
+  HYVAE_CHECK_ARG(k == 1 || k == 3, "kernel size %d not supported", k);
+  HYVAE_CHECK_ARG(x->dtype == HYVAE_BF16 || x->dtype == HYVAE_F16, "tensor-core conv needs bf16/f16 activations");
+  HYVAE_CHECK_ARG((x->dtype == y->dtype || y->dtype == HYVAE_F32) && x->B == y->B, "x / y dtype or batch mismatch");
+  HYVAE_CHECK_ARG(x->dtype == y->dtype || residual == nullptr, "residual needs y in x's dtype");
+  HYVAE_CHECK_ARG(x->pt == k - 1 && x->ph == k / 2 && x->pw == k / 2, "x must carry the halo (%d,%d,%d), has (%d,%d,%d)", k - 1, k / 2, k / 2, x->pt, x->ph, x->pw);
+  HYVAE_CHECK_ARG(x->C % 8 == 0 && y->C % 8 == 0, "Cin and Cout must be multiples of 8 (Cin=%d Cout=%d)", x->C, y->C);
+  HYVAE_CHECK_ARG(st >= 1 && sh >= 1 && sw >= 1 && sh <= 2 && sw <= 2, "stride (%d,%d,%d) not supported by the tensor-core path", st, sh, sw);
+  HYVAE_CHECK_ARG(y->T == (x->T - 1) / st + 1 && y->H == (x->H - 1) / sh + 1 && y->W == (x->W - 1) / sw + 1, "y dims do not match the conv output");
+  HYVAE_CHECK_ARG(((uintptr_t)x->data & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)y->data & 15) == 0, "pointers must be 16-byte aligned");
+  (void)variant;
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+
+  Vol vx = make_vol(x), vy = make_vol(y);
+  TcArgs a;
+  a.y = y->data; a.bias = bias;
+  a.ysB = vy.sB; a.ysT = vy.sT; a.ysH = vy.sH; a.ysW = vy.sW; a.yoff = vy.at(0, 0, 0, 0);
+  if (residual) {
+    if (int e = check_vol(residual, "residual")) return e;
+    HYVAE_CHECK_ARG(residual->dtype == y->dtype && residual->B == y->B && residual->T == y->T && residual->H == y->H &&
+                    residual->W == y->W && residual->C == y->C, "residual shape mismatch");
+    Vol vr = make_vol(residual);
+    a.res = residual->data; a.rsB = vr.sB; a.rsT = vr.sT; a.rsH = vr.sH; a.rsW = vr.sW; a.roff = vr.at(0, 0, 0, 0);
+  } else {
+    a.res = nullptr; a.rsB = a.rsT = a.rsH = a.rsW = a.roff = 0;
+  }
+  a.B = y->B; a.To = y->T; a.Ho = y->H; a.Wo = y->W; a.Cin = x->C; a.Cout = y->C;
+  a.k = k; a.st = st; a.sh = sh; a.sw = sw; a.round_like_ref = round_like_ref;
+
+  // tile shape: TH x TW = 128 output voxels of one frame, chosen to minimise padded area
+  int best_tw = 16; int64_t best_area = -1;
+  for (int tw = 8; tw <= 128; tw <<= 1) {
+    int th = 128 / tw;
+    if (tw * sw > 256 || th * sh > 256) continue;
+    int64_t area = (int64_t)((y->H + th - 1) / th) * th * ((y->W + tw - 1) / tw) * tw;
+    if (best_area < 0 || area < best_area || (area == best_area && tw == 16)) { best_area = area; best_tw = tw; }
+  }
+  a.TW = best_tw; a.TH = 128 / best_tw;
+  a.tiles_h = (y->H + a.TH - 1) / a.TH; a.tiles_w = (y->W + a.TW - 1) / a.TW;
+  const int BN = y->C > 128 ? 256 : (y->C > 64 ? 128 : (y->C > 32 ? 64 : 32));
+  a.n_tiles = (y->C + BN - 1) / BN;
+  a.total_tiles = (int64_t)y->B * y->T * a.tiles_h * a.tiles_w * a.n_tiles;
+
+  const CUtensorMapDataType dt = x->dtype == HYVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)x->C, (cuuint64_t)vx.Wp(), (cuuint64_t)vx.Hp(), (cuuint64_t)vx.Tp(), (cuuint64_t)x->B};
+    cuuint64_t strides[4] = {(cuuint64_t)vx.sW * 2, (cuuint64_t)vx.sH * 2, (cuuint64_t)vx.sT * 2, (cuuint64_t)vx.sB * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)(a.TW * sw), (cuuint32_t)(a.TH * sh), 1, 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1, 1};
+    CUresult r = encode(&tmA, dt, 5, x->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)x->C, (cuuint64_t)y->C, (cuuint64_t)(k * k * k)};
+    cuuint64_t strides[2] = {(cuuint64_t)x->C * 2, (cuuint64_t)x->C * y->C * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&tmB, dt, 3, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+#define HYVAE_TC_LAUNCH(T, OT)                                    \
+  switch (BN) {                                                   \
+    case 256: return launch_tc<T, OT, 256>(tmA, tmB, a, s);       \
+    case 128: return launch_tc<T, OT, 128>(tmA, tmB, a, s);       \
+    case 64: return launch_tc<T, OT, 64>(tmA, tmB, a, s);         \
+    default: return launch_tc<T, OT, 32>(tmA, tmB, a, s);         \
+  }
+  const bool f32out = (y->dtype == HYVAE_F32);
+  if (x->dtype == HYVAE_BF16) {
+    if (f32out) { HYVAE_TC_LAUNCH(__nv_bfloat16, float) } else { HYVAE_TC_LAUNCH(__nv_bfloat16, __nv_bfloat16) }
+  } else {
+    if (f32out) { HYVAE_TC_LAUNCH(__half, float) } else { HYVAE_TC_LAUNCH(__half, __half) }
+  }
+#undef HYVAE_TC_LAUNCH
+}

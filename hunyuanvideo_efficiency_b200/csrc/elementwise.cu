@@ -1,0 +1,431 @@
+// HBM-bound passes of the causal 3D VAE: layout conversion, GroupNorm(+SiLU), replicate-pad /
+// nearest-upsample, frame-causal softmax, temporal pool / interp, tile blend+crop+scatter.
+// All are coalesced, 16-byte vectorised along the channel (or W) axis, and written in the "gather"
+// form: one thread per DESTINATION element, source index by clamping — which is what turns the
+// reference's F.pad(replicate) copies (unet_causal_3d_blocks.py:74) into index arithmetic.
+#include "common.cuh"
+
+namespace hyvae {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+static inline int grid_for(int64_t n, int block, int cap_mult = 32) {
+  int64_t g = (n + block - 1) / block;
+  int64_t cap = (int64_t)num_sms() * cap_mult;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCTHW <-> channels-last volume
+// ------------------------------------------------------------------------------------------------
+template <typename S, typename D>
+__global__ void ncthw_to_vol_kernel(const S* __restrict__ src, Vol d, int64_t sb, int64_t sc, int64_t st, int64_t sh, int64_t sw) {
+  const int64_t nvox = (int64_t)d.B * d.Tp() * d.Hp() * d.Wp();
+  D* dst = reinterpret_cast<D*>(d.p);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvox; i += (int64_t)gridDim.x * blockDim.x) {
+    int wp = (int)(i % d.Wp());
+    int64_t r = i / d.Wp();
+    int hp = (int)(r % d.Hp()); r /= d.Hp();
+    int tp = (int)(r % d.Tp());
+    int b = (int)(r / d.Tp());
+    int t = max(tp - d.pt, 0);
+    int h = min(max(hp - d.ph, 0), d.H - 1);
+    int w = min(max(wp - d.pw, 0), d.W - 1);
+    const S* s = src + b * sb + t * st + h * sh + w * sw;
+    D* o = dst + i * d.C;
+    for (int c = 0; c < d.C; ++c) o[c] = from_f<D>(to_f<S>(s[c * sc]));
+  }
+}
+
+template <typename S, typename D>
+__global__ void vol_to_ncthw_kernel(Vol s, D* __restrict__ dst) {
+  const int64_t thw = (int64_t)s.T * s.H * s.W;
+  const int64_t nvox = (int64_t)s.B * thw;
+  const S* src = reinterpret_cast<const S*>(s.p);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvox; i += (int64_t)gridDim.x * blockDim.x) {
+    int w = (int)(i % s.W);
+    int64_t r = i / s.W;
+    int h = (int)(r % s.H); r /= s.H;
+    int t = (int)(r % s.T);
+    int b = (int)(r / s.T);
+    const S* p = src + s.at(b, t, h, w);
+    D* o = dst + (int64_t)b * s.C * thw + ((int64_t)t * s.H + h) * s.W + w;
+    for (int c = 0; c < s.C; ++c) o[c * thw] = from_f<D>(to_f<S>(p[c]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics: per (b, group) sum and sum of squares.
+// grid = (chunks, B); a thread owns one 8-channel vector position and strides over voxels, so its 16
+// partial sums stay in registers; block partials go through shared memory, then one fp64 atomic per
+// (group, moment) per block.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gn_stats_kernel(Vol x, int groups, int vox_per_block, double* __restrict__ sums) {
+  extern __shared__ float sh[];  // [2][C]
+  const int C = x.C, CV = C / 8;
+  const int b = blockIdx.y;
+  const int64_t nvox = (int64_t)x.T * x.H * x.W;
+  const int64_t v0 = (int64_t)blockIdx.x * vox_per_block;
+  const int64_t v1 = min(v0 + vox_per_block, nvox);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int lanes = blockDim.x / CV;
+  const int cv = threadIdx.x % CV, vl = threadIdx.x / CV;
+  if (vl < lanes) {
+    float s[8], ss[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+    const T* base = reinterpret_cast<const T*>(x.p);
+    const bool dense = (x.pt | x.ph | x.pw) == 0;
+    for (int64_t v = v0 + vl; v < v1; v += lanes) {
+      int64_t off;
+      if (dense) off = ((int64_t)b * nvox + v) * C;
+      else {
+        int w = (int)(v % x.W); int64_t r = v / x.W; int h = (int)(r % x.H); int t = (int)(r / x.H);
+        off = x.at(b, t, h, w);
+      }
+      Vec8<T> q; q.load(base + off + cv * 8);
+      float f[8]; q.get(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { atomicAdd(&sh[cv * 8 + j], s[j]); atomicAdd(&sh[C + cv * 8 + j], ss[j]); }
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double a = 0.0, q = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += (double)sh[c]; q += (double)sh[C + c]; }
+    atomicAdd(&sums[((int64_t)b * groups + g) * 2 + 0], a);
+    atomicAdd(&sums[((int64_t)b * groups + g) * 2 + 1], q);
+  }
+}
+
+// GroupNorm apply (+SiLU) into a possibly padded destination.  grid = (chunks, B).
+template <typename T>
+__global__ void gn_apply_kernel(Vol x, Vol y, const double* __restrict__ sums, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int groups, float eps, int silu, int round_like_ref) {
+  extern __shared__ float sh[];  // scale[C], shift[C]
+  const int C = x.C, CV = C / 8, b = blockIdx.y;
+  const int cpg = C / groups;
+  const double n = (double)x.T * x.H * x.W * cpg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int g = c / cpg;
+    double mean = sums[((int64_t)b * groups + g) * 2] / n;
+    double var = sums[((int64_t)b * groups + g) * 2 + 1] / n - mean * mean;
+    if (var < 0) var = 0;
+    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float sc = gamma[c] * rstd;
+    sh[c] = sc;
+    sh[C + c] = beta[c] - (float)mean * sc;
+  }
+  __syncthreads();
+  const int64_t nvp = (int64_t)y.Tp() * y.Hp() * y.Wp();
+  const int64_t total = nvp * CV;
+  const T* xs = reinterpret_cast<const T*>(x.p);
+  T* yd = reinterpret_cast<T*>(y.p) + (int64_t)b * y.sB;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    int64_t v = i / CV;
+    int wp = (int)(v % y.Wp()); int64_t r = v / y.Wp();
+    int hp = (int)(r % y.Hp()); int tp = (int)(r / y.Hp());
+    int t = max(tp - y.pt, 0);
+    int h = min(max(hp - y.ph, 0), y.H - 1);
+    int w = min(max(wp - y.pw, 0), y.W - 1);
+    Vec8<T> q; q.load(xs + x.at(b, t, h, w) + cv * 8);
+    float f[8]; q.get(f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int c = cv * 8 + j;
+      float u = fmaf(f[j], sh[c], sh[C + c]);
+      if (round_like_ref) u = rnd<T>(u);
+      if (silu) u = u / (1.f + expf(-u));
+      f[j] = u;
+    }
+    q.set(f);
+    q.store(yd + v * C + cv * 8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// replicate pad / nearest upsample (first frame not upsampled in T)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void pad_upsample_kernel(Vol x, Vol y, int up_t, int up_h, int up_w) {
+  const int CV = x.C / VEC;
+  const int64_t nvp = (int64_t)y.B * y.Tp() * y.Hp() * y.Wp();
+  const int64_t total = nvp * CV;
+  const T* xs = reinterpret_cast<const T*>(x.p);
+  T* yd = reinterpret_cast<T*>(y.p);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    int64_t v = i / CV;
+    int wp = (int)(v % y.Wp()); int64_t r = v / y.Wp();
+    int hp = (int)(r % y.Hp()); r /= y.Hp();
+    int tp = (int)(r % y.Tp()); int b = (int)(r / y.Tp());
+    int t = max(tp - y.pt, 0);
+    int h = min(max(hp - y.ph, 0), y.H - 1);
+    int w = min(max(wp - y.pw, 0), y.W - 1);
+    int ts = (up_t == 2) ? (t == 0 ? 0 : 1 + ((t - 1) >> 1)) : t;
+    int hs = (up_h == 2) ? (h >> 1) : h;
+    int ws = (up_w == 2) ? (w >> 1) : w;
+    const T* s = xs + x.at(b, ts, hs, ws) + cv * VEC;
+    T* o = yd + v * y.C + cv * VEC;
+    if (VEC == 8) { Vec8<T> q; q.load(s); q.store(o); }
+    else { o[0] = s[0]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame-causal softmax: one block per row.  Row i attends to keys j < (i / n_hw + 1) * n_hw.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, u) : v + u;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  v = (lane < nw) ? sh[lane] : (is_max ? -INFINITY : 0.f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, u) : v + u;
+  }
+  return v;
+}
+
+template <typename T>
+__global__ void softmax_frame_causal_kernel(const float* __restrict__ S, T* __restrict__ P, int L, int n_hw, float scale) {
+  __shared__ float sh[32];
+  const int64_t row = blockIdx.x;  // b*L + i
+  const int i = (int)(row % L);
+  const int lim = min((i / n_hw + 1) * n_hw, L);
+  const float* s = S + row * L;
+  T* p = P + row * L;
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < lim; j += blockDim.x) m = fmaxf(m, s[j]);
+  m = block_reduce(m, sh, true);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < lim; j += blockDim.x) sum += expf((s[j] - m) * scale);
+  sum = block_reduce(sum, sh, false);
+  const float inv = 1.f / sum;
+  for (int j = threadIdx.x; j < L; j += blockDim.x)
+    p[j] = from_f<T>(j < lim ? expf((s[j] - m) * scale) * inv : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// temporal avg-pool (front-replicated) and nearest temporal interpolation
+// ------------------------------------------------------------------------------------------------
+template <typename T, int MODE>  // MODE 0: avgpool (k, s);  MODE 1: nearest interp (inv_scale)
+__global__ void temporal_kernel(Vol x, Vol y, int k, int s, float inv_scale) {
+  const int C = x.C;
+  const int64_t total = (int64_t)y.B * y.T * y.H * y.W * C;
+  const T* xs = reinterpret_cast<const T*>(x.p);
+  T* yd = reinterpret_cast<T*>(y.p);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); int64_t v = i / C;
+    int w = (int)(v % y.W); int64_t r = v / y.W;
+    int h = (int)(r % y.H); r /= y.H;
+    int t = (int)(r % y.T); int b = (int)(r / y.T);
+    float o;
+    if (MODE == 0) {
+      float acc = 0.f;
+      for (int j = 0; j < k; ++j) acc += to_f<T>(xs[x.at(b, max(t * s + j - (k - 1), 0), h, w) + c]);
+      o = acc / (float)k;
+    } else {
+      int ts = min((int)floorf((float)t * inv_scale), x.T - 1);
+      o = to_f<T>(xs[x.at(b, ts, h, w) + c]);
+    }
+    yd[y.at(b, t, h, w) + c] = from_f<T>(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// blend (in place, raster order is the caller's) + crop + scatter
+// Products and the sum are rounded separately, in the tensor dtype, exactly like the reference's
+// `a * (1 - y / e) + b * (y / e)` on tensors (autoencoder_kl_causal_3d.py:347,353,359).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float blend2(float a, float b, int y, int e) {
+  const float wa = (float)(1.0 - (double)y / (double)e), wb = (float)((double)y / (double)e);
+  return rnd<T>(__fadd_rn(rnd<T>(__fmul_rn(a, wa)), rnd<T>(__fmul_rn(b, wb))));
+}
+
+template <typename T>
+__global__ void blend_crop_scatter_kernel(T* __restrict__ cur, const T* __restrict__ above, const T* __restrict__ left,
+                                          int64_t N, int Yc, int Xc, int Ya, int Xl, int ev, int eh,
+                                          T* __restrict__ out, int Yo, int Xo, int y0, int x0, int crop_y, int crop_x,
+                                          int64_t cur_ns, int64_t above_ns, int64_t left_ns, int64_t out_ns) {
+  const int64_t total = N * Yc * Xc;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % Xc); int64_t r = i / Xc;
+    int y = (int)(r % Yc); int64_t n = r / Yc;
+    const int64_t ci = n * cur_ns + (int64_t)y * Xc + x;
+    float v = to_f<T>(cur[ci]);
+    bool mod = false;
+    if (above != nullptr && y < ev) {
+      v = blend2<T>(to_f<T>(above[n * above_ns + (int64_t)(Ya - ev + y) * Xc + x]), v, y, ev);
+      mod = true;
+    }
+    if (left != nullptr && x < eh) {
+      v = blend2<T>(to_f<T>(left[n * left_ns + (int64_t)y * Xl + (Xl - eh + x)]), v, x, eh);
+      mod = true;
+    }
+    if (mod) cur[ci] = from_f<T>(v);
+    if (out != nullptr && y < crop_y && x < crop_x) out[n * out_ns + (int64_t)(y0 + y) * Xo + (x0 + x)] = from_f<T>(v);
+  }
+}
+
+}  // namespace hyvae
+
+using namespace hyvae;
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int hyvae_version(void) { return HYVAE_VERSION; }
+const char* hyvae_last_error(void) { return g_err; }
+int64_t hyvae_launch_count(void) { return g_launches.load(); }
+
+int hyvae_device_supports_tc(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  return major == 10;
+}
+
+int hyvae_ncthw_to_vol(const void* src, int32_t src_dtype, const int64_t* ss, const hyvae_vol* dst, void* stream) {
+  if (int e = check_vol(dst, "dst")) return e;
+  HYVAE_CHECK_ARG(src != nullptr && ss != nullptr, "src is null");
+  Vol d = make_vol(dst);
+  int64_t n = (int64_t)d.B * d.Tp() * d.Hp() * d.Wp();
+  HYVAE_DISPATCH_DTYPE(src_dtype, S, HYVAE_DISPATCH_DTYPE(dst->dtype, D,
+      (ncthw_to_vol_kernel<S, D><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const S*)src, d, ss[0], ss[1], ss[2], ss[3], ss[4]))));
+  return check_launch("ncthw_to_vol");
+}
+
+int hyvae_vol_to_ncthw(const hyvae_vol* src, void* dst, int32_t dst_dtype, void* stream) {
+  if (int e = check_vol(src, "src")) return e;
+  HYVAE_CHECK_ARG(dst != nullptr, "dst is null");
+  Vol s = make_vol(src);
+  int64_t n = (int64_t)s.B * s.T * s.H * s.W;
+  HYVAE_DISPATCH_DTYPE(src->dtype, S, HYVAE_DISPATCH_DTYPE(dst_dtype, D,
+      (vol_to_ncthw_kernel<S, D><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s, (D*)dst))));
+  return check_launch("vol_to_ncthw");
+}
+
+int hyvae_groupnorm_stats(const hyvae_vol* x, int32_t groups, double* sums, void* stream) {
+  if (int e = check_vol(x, "x")) return e;
+  HYVAE_CHECK_ARG(sums != nullptr, "sums is null");
+  HYVAE_CHECK_ARG(groups > 0 && x->C % groups == 0, "C=%d not divisible by groups=%d", x->C, groups);
+  HYVAE_CHECK_ARG(x->C % 8 == 0 && x->C / 8 <= 256, "GroupNorm needs C%%8==0 and C<=2048 (C=%d)", x->C);
+  Vol v = make_vol(x);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups * x->B, st) != cudaSuccess)
+    return fail(HYVAE_ECUDA, "memset sums failed");
+  const int block = 256, lanes = block / (x->C / 8);
+  const int64_t nvox = (int64_t)x->T * x->H * x->W;
+  int vpb = lanes * 64;
+  // keep at least ~4 blocks per SM when the tensor is large enough
+  while (vpb > lanes * 8 && (nvox + vpb - 1) / vpb * x->B < 4 * num_sms()) vpb >>= 1;
+  dim3 grid((unsigned)((nvox + vpb - 1) / vpb), (unsigned)x->B);
+  size_t smem = sizeof(float) * 2 * x->C;
+  HYVAE_DISPATCH_DTYPE(x->dtype, T, (gn_stats_kernel<T><<<grid, block, smem, st>>>(v, groups, vpb, sums)));
+  return check_launch("groupnorm_stats");
+}
+
+int hyvae_groupnorm_apply(const hyvae_vol* x, const double* sums, const float* gamma, const float* beta,
+                          int32_t groups, float eps, int32_t silu, int32_t round_like_ref, const hyvae_vol* y,
+                          void* stream) {
+  if (int e = check_vol(x, "x")) return e;
+  if (int e = check_vol(y, "y")) return e;
+  HYVAE_CHECK_ARG(sums && gamma && beta, "null parameter");
+  HYVAE_CHECK_ARG(x->dtype == y->dtype, "dtype mismatch");
+  HYVAE_CHECK_ARG(x->B == y->B && x->T == y->T && x->H == y->H && x->W == y->W && x->C == y->C, "shape mismatch");
+  HYVAE_CHECK_ARG(groups > 0 && x->C % groups == 0 && x->C % 8 == 0, "bad C=%d / groups=%d", x->C, groups);
+  Vol vx = make_vol(x), vy = make_vol(y);
+  int64_t total = (int64_t)vy.Tp() * vy.Hp() * vy.Wp() * (x->C / 8);
+  dim3 grid((unsigned)grid_for(total, 256, 16), (unsigned)x->B);
+  size_t smem = sizeof(float) * 2 * x->C;
+  HYVAE_DISPATCH_DTYPE(x->dtype, T, (gn_apply_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
+      vx, vy, sums, gamma, beta, groups, eps, silu, round_like_ref)));
+  return check_launch("groupnorm_apply");
+}
+
+int hyvae_pad_upsample(const hyvae_vol* x, const hyvae_vol* y, int32_t up_t, int32_t up_h, int32_t up_w, void* stream) {
+  if (int e = check_vol(x, "x")) return e;
+  if (int e = check_vol(y, "y")) return e;
+  HYVAE_CHECK_ARG(x->dtype == y->dtype && x->C == y->C && x->B == y->B, "dtype/C/B mismatch");
+  HYVAE_CHECK_ARG((up_t == 1 || up_t == 2) && (up_h == 1 || up_h == 2) && (up_w == 1 || up_w == 2), "up factors must be 1 or 2");
+  int Te = up_t == 2 ? 1 + 2 * (x->T - 1) : x->T;
+  HYVAE_CHECK_ARG(y->T == Te && y->H == x->H * up_h && y->W == x->W * up_w, "y dims %dx%dx%d do not match upsampled x", y->T, y->H, y->W);
+  Vol vx = make_vol(x), vy = make_vol(y);
+  int64_t nvp = (int64_t)vy.B * vy.Tp() * vy.Hp() * vy.Wp();
+  if (x->C % 8 == 0) {
+    HYVAE_DISPATCH_DTYPE(x->dtype, T, (pad_upsample_kernel<T, 8><<<grid_for(nvp * (x->C / 8), 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, up_t, up_h, up_w)));
+  } else {
+    HYVAE_DISPATCH_DTYPE(x->dtype, T, (pad_upsample_kernel<T, 1><<<grid_for(nvp * x->C, 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, up_t, up_h, up_w)));
+  }
+  return check_launch("pad_upsample");
+}
+
+int hyvae_softmax_frame_causal(const float* S, void* P, int32_t p_dtype, int32_t B, int32_t L, int32_t n_hw,
+                               float scale, void* stream) {
+  HYVAE_CHECK_ARG(S && P && B > 0 && L > 0 && n_hw > 0 && L % n_hw == 0, "bad softmax arguments (L=%d n_hw=%d)", L, n_hw);
+  HYVAE_DISPATCH_DTYPE(p_dtype, T, (softmax_frame_causal_kernel<T><<<(unsigned)((int64_t)B * L), 256, 0, (cudaStream_t)stream>>>(
+      S, (T*)P, L, n_hw, scale)));
+  return check_launch("softmax_frame_causal");
+}
+
+int hyvae_avgpool_t(const hyvae_vol* x, const hyvae_vol* y, int32_t k, int32_t s, void* stream) {
+  if (int e = check_vol(x, "x")) return e;
+  if (int e = check_vol(y, "y")) return e;
+  HYVAE_CHECK_ARG(k >= 1 && s >= 1, "bad pool k=%d s=%d", k, s);
+  HYVAE_CHECK_ARG(y->T == (x->T - 1) / s + 1 && y->H == x->H && y->W == x->W && y->C == x->C && y->B == x->B && x->dtype == y->dtype,
+                  "avgpool_t: y shape mismatch");
+  Vol vx = make_vol(x), vy = make_vol(y);
+  int64_t total = (int64_t)y->B * y->T * y->H * y->W * y->C;
+  HYVAE_DISPATCH_DTYPE(x->dtype, T, (temporal_kernel<T, 0><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, k, s, 0.f)));
+  return check_launch("avgpool_t");
+}
+
+int hyvae_interp_t_nearest(const hyvae_vol* x, const hyvae_vol* y, float inv_scale, void* stream) {
+  if (int e = check_vol(x, "x")) return e;
+  if (int e = check_vol(y, "y")) return e;
+  HYVAE_CHECK_ARG(y->H == x->H && y->W == x->W && y->C == x->C && y->B == x->B && x->dtype == y->dtype, "interp_t: y shape mismatch");
+  Vol vx = make_vol(x), vy = make_vol(y);
+  int64_t total = (int64_t)y->B * y->T * y->H * y->W * y->C;
+  HYVAE_DISPATCH_DTYPE(x->dtype, T, (temporal_kernel<T, 1><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, 0, 0, inv_scale)));
+  return check_launch("interp_t_nearest");
+}
+
+int hyvae_blend_crop_scatter(void* cur, const void* above, const void* left, int32_t dtype, int64_t N,
+                             int32_t Yc, int32_t Xc, int32_t Ya, int32_t Xl, int32_t ev, int32_t eh,
+                             void* out, int32_t Yo, int32_t Xo, int32_t y0, int32_t x0, int32_t crop_y,
+                             int32_t crop_x, const int64_t* ns, void* stream) {
+  const int64_t cur_ns = ns ? ns[0] : (int64_t)Yc * Xc, above_ns = ns ? ns[1] : (int64_t)Ya * Xc;
+  const int64_t left_ns = ns ? ns[2] : (int64_t)Yc * Xl, out_ns = ns ? ns[3] : (int64_t)Yo * Xo;
+  HYVAE_CHECK_ARG(cur != nullptr && N > 0 && Yc > 0 && Xc > 0, "bad blend arguments");
+  HYVAE_CHECK_ARG(above == nullptr || (ev > 0 && ev <= Ya && ev <= Yc), "bad vertical extent %d", ev);
+  HYVAE_CHECK_ARG(left == nullptr || (eh > 0 && eh <= Xl && eh <= Xc), "bad horizontal extent %d", eh);
+  HYVAE_CHECK_ARG(out == nullptr || (crop_y <= Yc && crop_x <= Xc && y0 + crop_y <= Yo && x0 + crop_x <= Xo && y0 >= 0 && x0 >= 0),
+                  "crop window does not fit");
+  int64_t total = N * Yc * Xc;
+  HYVAE_DISPATCH_DTYPE(dtype, T, (blend_crop_scatter_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (T*)cur, (const T*)above, (const T*)left, N, Yc, Xc, Ya, Xl, ev, eh, (T*)out, Yo, Xo, y0, x0, crop_y, crop_x,
+      cur_ns, above_ns, left_ns, out_ns)));
+  return check_launch("blend_crop_scatter");
+}
+
+}  // extern "C"

@@ -1,0 +1,494 @@
+"""Building blocks of the causal 3D VAE, scheduled onto libhyvae.so kernels.
+
+Same class names, constructor arguments, sub-module / parameter names (hence the same 248 state-dict
+keys) and t-ops hooks as /root/reference/hyvideo/vae/unet_causal_3d_blocks.py, so callers and
+checkpoints are interchangeable.  What differs is everything underneath: activations travel between
+blocks as channels-last `Vol`s in HBM, each `forward_vol` is a fixed schedule of C-ABI kernel calls
+(include/hyvae.h), and nothing here computes with torch ops.  Public `forward(tensor)` wrappers take
+and return NCTHW tensors like the reference modules do.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from .. import _native as N
+from .._native import Vol
+
+_16BIT = (torch.bfloat16, torch.float16)
+
+
+def _triple(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v, v)
+
+
+def tc_eligible(dtype, cin: int, cout: int, stride, k: int) -> bool:
+    """Tensor-core (tcgen05) path iff the shape fits it; everything else runs the CUDA-core kernel."""
+    if os.environ.get("HYVAE_FORCE_DIRECT", "0") == "1":
+        return False
+    return (N.device_supports_tc() and dtype in _16BIT and cin % 8 == 0 and cin >= 64 and cout % 8 == 0
+            and cout >= 32 and stride[1] <= 2 and stride[2] <= 2)
+
+
+def prepare_causal_attention_mask(n_frame: int, n_hw: int, dtype, device, batch_size: int = None):
+    """API parity with unet_causal_3d_blocks.py:38-46.  The CUDA attention path never builds this
+    mask (hyvae_softmax_frame_causal derives it from indices); kept for callers that import it."""
+    f = torch.arange(n_frame * n_hw, device=device) // n_hw
+    mask = torch.zeros((n_frame * n_hw, n_frame * n_hw), dtype=dtype, device=device)
+    mask.masked_fill_(f[None, :] > f[:, None], float("-inf"))
+    if batch_size is not None:
+        mask = mask.unsqueeze(0).expand(batch_size, -1, -1)
+    return mask
+
+
+class _Conv3dParams(nn.Module):
+    """Parameter holder standing where the reference keeps an nn.Conv3d (`CausalConv3d.conv`):
+    same `weight` [Cout,Cin,k,k,k] / `bias` names and a mutable `stride` (unet_causal_3d_blocks.py:741)."""
+
+    def __init__(self, cin, cout, k, stride=1, bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels = cin, cout
+        self.kernel_size, self.stride = _triple(k), _triple(stride)
+        self.weight = nn.Parameter(torch.empty(cout, cin, *self.kernel_size))
+        self.bias = nn.Parameter(torch.empty(cout)) if bias else None
+        bound = 1.0 / math.sqrt(cin * self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2])
+        nn.init.uniform_(self.weight, -bound, bound)
+        if bias:
+            nn.init.uniform_(self.bias, -bound, bound)
+        self._packed = None
+
+    def packed(self, dtype):
+        """[taps][Cout][Cin] weights in the activation dtype + fp32 bias (kernel layout), cached."""
+        w = self.weight
+        key = (w._version, w.data_ptr(), dtype, w.device, None if self.bias is None else self.bias._version)
+        if self._packed is None or self._packed[0] != key:
+            k = self.kernel_size[0]
+            pw = w.detach().permute(2, 3, 4, 0, 1).reshape(k * k * k, self.out_channels, self.in_channels).to(dtype).contiguous()
+            pb = None if self.bias is None else self.bias.detach().float().contiguous()
+            self._packed = (key, pw, pb)
+        return self._packed[1], self._packed[2]
+
+
+class CausalConv3d(nn.Module):
+    """unet_causal_3d_blocks.py:49-75.  `time_causal_padding` is kept as an attribute; the padding
+    itself is a halo of the input volume (tensor-core path) or index clamping (CUDA-core path)."""
+
+    def __init__(self, chan_in, chan_out, kernel_size, stride=1, dilation=1, pad_mode="replicate", **kwargs):
+        super().__init__()
+        if _triple(dilation) != (1, 1, 1):
+            raise NotImplementedError("dilation != 1")
+        if pad_mode != "replicate":
+            raise NotImplementedError(f"pad_mode {pad_mode}")
+        if not isinstance(kernel_size, int) or kernel_size not in (1, 3):
+            raise NotImplementedError(f"kernel_size {kernel_size}")
+        self.pad_mode = pad_mode
+        k = kernel_size
+        self.time_causal_padding = (k // 2, k // 2, k // 2, k // 2, k - 1, 0)
+        self.conv = _Conv3dParams(chan_in, chan_out, k, stride, bias=kwargs.get("bias", True))
+
+    @property
+    def halo(self) -> Tuple[int, int, int]:
+        k = self.conv.kernel_size[0]
+        return (k - 1, k // 2, k // 2)
+
+    def wants_halo(self, dtype) -> Tuple[int, int, int]:
+        """Halo the producer should write so this conv can read its input through TMA."""
+        c = self.conv
+        return self.halo if tc_eligible(dtype, c.in_channels, c.out_channels, c.stride, c.kernel_size[0]) else (0, 0, 0)
+
+    def forward_vol(self, x: Vol, residual: Optional[Vol] = None, up=(1, 1, 1), out_dtype=None) -> Vol:
+        c = self.conv
+        k, stride = c.kernel_size[0], tuple(int(s) for s in c.stride)
+        w, b = c.packed(x.dtype)
+        rl = x.dtype in _16BIT
+        if tc_eligible(x.dtype, c.in_channels, c.out_channels, stride, k):
+            if x.pad != self.halo or up != (1, 1, 1):
+                x = N.pad_upsample(x, up, self.halo)
+            return N.conv3d_tc(x, w, b, k, stride, c.out_channels, residual, out_dtype, rl)
+        return N.conv3d_direct(x, w, b, k, stride, c.out_channels, residual, up, out_dtype, rl)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.forward_vol(Vol.from_ncthw(x)).to_ncthw()
+
+
+class _GroupNorm(nn.Module):
+    """nn.GroupNorm-compatible parameters (`weight`, `bias`); the compute is hyvae_groupnorm_*."""
+
+    def __init__(self, num_groups, num_channels, eps=1e-6):
+        super().__init__()
+        self.num_groups, self.num_channels, self.eps = num_groups, num_channels, eps
+        self.weight = nn.Parameter(torch.ones(num_channels))
+        self.bias = nn.Parameter(torch.zeros(num_channels))
+        self._f32 = None
+
+    def _params(self):
+        key = (self.weight._version, self.bias._version, self.weight.data_ptr(), self.weight.device)
+        if self._f32 is None or self._f32[0] != key:
+            self._f32 = (key, self.weight.detach().float().contiguous(), self.bias.detach().float().contiguous())
+        return self._f32[1], self._f32[2]
+
+    def forward_vol(self, x: Vol, silu: bool, pad=(0, 0, 0)) -> Vol:
+        g, b = self._params()
+        return N.groupnorm(x, g, b, self.num_groups, self.eps, silu, pad, x.dtype in _16BIT)
+
+
+class UpsampleCausal3D(nn.Module):
+    """unet_causal_3d_blocks.py:78-183: nearest upsample (frame 0 spatial only) + CausalConv3d.  The
+    upsample is folded into the conv's gather (CUDA-core path) or into the pad pass that builds the
+    TMA halo (tensor-core path); no fp32 round trip is needed because nothing is interpolated."""
+
+    def __init__(self, channels, use_conv=False, use_conv_transpose=False, out_channels=None, name="conv",
+                 kernel_size=None, padding=1, norm_type=None, eps=None, elementwise_affine=None, bias=True,
+                 interpolate=True, upsample_factor=(2, 2, 2)):
+        super().__init__()
+        if use_conv_transpose or norm_type is not None:
+            raise NotImplementedError
+        self.channels, self.out_channels = channels, out_channels or channels
+        self.use_conv, self.name, self.interpolate = use_conv, name, interpolate
+        self.upsample_factor = tuple(upsample_factor)
+        if any(f not in (1, 2) for f in self.upsample_factor):
+            raise NotImplementedError(f"upsample_factor {upsample_factor}")
+        conv = CausalConv3d(self.channels, self.out_channels, kernel_size=kernel_size or 3, bias=bias) if use_conv else None
+        if name == "conv":
+            self.conv = conv
+        else:
+            self.Conv2d_0 = conv
+
+    def forward_vol(self, x: Vol) -> Vol:
+        assert x.C == self.channels
+        up = self.upsample_factor if self.interpolate else (1, 1, 1)
+        conv = self.conv if self.name == "conv" else self.Conv2d_0
+        if conv is None:
+            return N.pad_upsample(x, up)
+        return conv.forward_vol(x, up=up)
+
+    def forward(self, hidden_states, output_size=None, scale: float = 1.0):
+        if output_size is not None:
+            raise NotImplementedError
+        return self.forward_vol(Vol.from_ncthw(hidden_states)).to_ncthw()
+
+
+class DownsampleCausal3D(nn.Module):
+    """unet_causal_3d_blocks.py:186-247: one strided CausalConv3d."""
+
+    def __init__(self, channels, use_conv=False, out_channels=None, padding=1, name="conv", kernel_size=3,
+                 norm_type=None, eps=None, elementwise_affine=None, bias=True, stride=2):
+        super().__init__()
+        if not use_conv or norm_type is not None:
+            raise NotImplementedError
+        self.channels, self.out_channels = channels, out_channels or channels
+        self.use_conv, self.padding, self.name = use_conv, padding, name
+        self.conv = CausalConv3d(self.channels, self.out_channels, kernel_size=kernel_size, stride=stride, bias=bias)
+        if name == "conv":
+            self.Conv2d_0 = self.conv
+
+    def forward_vol(self, x: Vol) -> Vol:
+        assert x.C == self.channels
+        return self.conv.forward_vol(x)
+
+    def forward(self, hidden_states, scale: float = 1.0):
+        return self.forward_vol(Vol.from_ncthw(hidden_states)).to_ncthw()
+
+
+class ResnetBlockCausal3D(nn.Module):
+    """unet_causal_3d_blocks.py:250-417 for the configuration the VAE uses (no temb, GroupNorm, swish).
+    Schedule: GN-stats, GN+SiLU (writes conv1's halo), conv1, GN-stats, GN+SiLU, [1x1x1 shortcut],
+    conv2 with the residual add fused into its epilogue."""
+
+    def __init__(self, *, in_channels, out_channels=None, conv_shortcut=False, dropout=0.0, temb_channels=512,
+                 groups=32, groups_out=None, pre_norm=True, eps=1e-6, non_linearity="swish", skip_time_act=False,
+                 time_embedding_norm="default", kernel=None, output_scale_factor=1.0, use_in_shortcut=None,
+                 up=False, down=False, conv_shortcut_bias=True, conv_3d_out_channels=None):
+        super().__init__()
+        if temb_channels is not None or time_embedding_norm != "default" or up or down:
+            raise NotImplementedError("only the temb-free GroupNorm resnet of the VAE is implemented")
+        if non_linearity not in ("swish", "silu"):
+            raise NotImplementedError(non_linearity)
+        if dropout != 0.0:
+            raise NotImplementedError("dropout")
+        out_channels = in_channels if out_channels is None else out_channels
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.output_scale_factor = output_scale_factor
+        self.norm1 = _GroupNorm(groups, in_channels, eps)
+        self.conv1 = CausalConv3d(in_channels, out_channels, kernel_size=3, stride=1)
+        self.norm2 = _GroupNorm(groups_out or groups, out_channels, eps)
+        c3 = conv_3d_out_channels or out_channels
+        self.conv2 = CausalConv3d(out_channels, c3, kernel_size=3, stride=1)
+        self.use_in_shortcut = (in_channels != c3) if use_in_shortcut is None else use_in_shortcut
+        self.conv_shortcut = (CausalConv3d(in_channels, c3, kernel_size=1, stride=1, bias=conv_shortcut_bias)
+                              if self.use_in_shortcut else None)
+
+    def forward_vol(self, x: Vol) -> Vol:
+        if self.output_scale_factor != 1.0:
+            raise NotImplementedError("output_scale_factor != 1")
+        h = self.norm1.forward_vol(x, True, self.conv1.wants_halo(x.dtype))
+        h = self.conv1.forward_vol(h)
+        h = self.norm2.forward_vol(h, True, self.conv2.wants_halo(x.dtype))
+        skip = x if self.conv_shortcut is None else self.conv_shortcut.forward_vol(x)
+        return self.conv2.forward_vol(h, residual=skip)
+
+    def forward(self, input_tensor, temb=None, scale: float = 1.0):
+        return self.forward_vol(Vol.from_ncthw(input_tensor)).to_ncthw()
+
+
+class _Linear(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.in_features, self.out_features = cin, cout
+        self.weight = nn.Parameter(torch.empty(cout, cin))
+        self.bias = nn.Parameter(torch.empty(cout))
+        bound = 1.0 / math.sqrt(cin)
+        nn.init.uniform_(self.weight, -bound, bound)
+        nn.init.uniform_(self.bias, -bound, bound)
+        self._packed = None
+
+    def packed(self, dtype):
+        key = (self.weight._version, self.bias._version, self.weight.data_ptr(), dtype)
+        if self._packed is None or self._packed[0] != key:
+            self._packed = (key, self.weight.detach().to(dtype).contiguous(), self.bias.detach().float().contiguous())
+        return self._packed[1], self._packed[2]
+
+
+def _gemm_nt(x: Vol, w: torch.Tensor, bias, cout: int, residual: Optional[Vol] = None, out_dtype=None,
+             out: Optional[Vol] = None) -> Vol:
+    """y[m][n] = sum_k x[m][k] * w[n][k] (+bias[n]) (+residual): a 1x1x1 'conv' on either kernel."""
+    rl = x.dtype in _16BIT
+    if tc_eligible(x.dtype, x.C, cout, (1, 1, 1), 1) and x.pad == (0, 0, 0):
+        return N.conv3d_tc(x, w, bias, 1, (1, 1, 1), cout, residual, out_dtype, rl, out=out)
+    return N.conv3d_direct(x, w, bias, 1, (1, 1, 1), cout, residual, (1, 1, 1), out_dtype, rl, out=out)
+
+
+class Attention(nn.Module):
+    """The diffusers==0.31.0 `Attention` the reference instantiates at unet_causal_3d_blocks.py:580-592
+    (one head of width C, GroupNorm(32), biased q/k/v/out projections, residual), with the frame-causal
+    mask of :38-46 computed from indices.  Parameter names match diffusers' so checkpoints load.
+    Schedule per batch item: GN -> Q,K = X Wq^T, X Wk^T -> V^T = Wv X^T -> S = Q K^T (fp32) ->
+    masked softmax -> O = P V + bv -> out-proj (+bias +residual in the epilogue)."""
+
+    def __init__(self, query_dim, heads=1, dim_head=None, rescale_output_factor=1.0, eps=1e-6, norm_num_groups=32,
+                 spatial_norm_dim=None, residual_connection=True, bias=True, upcast_softmax=True,
+                 _from_deprecated_attn_block=True, **unused):
+        super().__init__()
+        dim_head = dim_head or query_dim
+        if heads != 1 or dim_head != query_dim or spatial_norm_dim is not None or not bias or rescale_output_factor != 1.0:
+            raise NotImplementedError("only the single-head VAE attention block is implemented")
+        self.heads, self.inner_dim, self.scale = heads, dim_head, dim_head ** -0.5
+        self.residual_connection, self.rescale_output_factor = residual_connection, rescale_output_factor
+        self.group_norm = _GroupNorm(norm_num_groups, query_dim, eps)
+        self.to_q, self.to_k, self.to_v = _Linear(query_dim, dim_head), _Linear(query_dim, dim_head), _Linear(query_dim, dim_head)
+        self.to_out = nn.ModuleList([_Linear(dim_head, query_dim), nn.Identity()])
+
+    def forward_vol(self, x: Vol) -> Vol:
+        B, T, H, W, Cn = x.dims
+        L, n_hw = T * H * W, H * W
+        hn = self.group_norm.forward_vol(x, False)
+        out = x.like()
+        wq, bq = self.to_q.packed(x.dtype)
+        wk, bk = self.to_k.packed(x.dtype)
+        wv, bv = self.to_v.packed(x.dtype)
+        wo, bo = self.to_out[0].packed(x.dtype)
+        for b in range(B):
+            xb = Vol(1, 1, 1, L, Cn, x.dtype, x.device, tensor=hn.t[b].reshape(1, 1, 1, L, Cn))
+            q = _gemm_nt(xb, wq, bq, Cn)
+            k = _gemm_nt(xb, wk, bk, Cn)
+            wv_rows = Vol(1, 1, 1, Cn, Cn, x.dtype, x.device, tensor=wv.reshape(1, 1, 1, Cn, Cn))
+            vt = _gemm_nt(wv_rows, xb.t.reshape(L, Cn), None, L)                      # V^T [C][L], bias folded below
+            s = _gemm_nt(q, k.t.reshape(L, Cn), None, L, out_dtype=torch.float32)     # S [L][L] fp32
+            p = N.softmax_frame_causal(s.t.reshape(1, L, L), n_hw, self.scale, x.dtype)
+            pv = Vol(1, 1, 1, L, L, x.dtype, x.device, tensor=p.reshape(1, 1, 1, L, L))
+            o = _gemm_nt(pv, vt.t.reshape(Cn, L), bv, Cn)                             # rows of P sum to 1 => + bv
+            res = Vol(1, 1, 1, L, Cn, x.dtype, x.device, tensor=x.t[b].reshape(1, 1, 1, L, Cn)) if self.residual_connection else None
+            ob = Vol(1, 1, 1, L, Cn, x.dtype, x.device, tensor=out.t[b].reshape(1, 1, 1, L, Cn))
+            _gemm_nt(o, wo, bo, Cn, residual=res, out=ob)
+        return out
+
+
+class UNetMidBlockCausal3D(nn.Module):
+    """unet_causal_3d_blocks.py:525-678: resnet, then (attention, resnet) x num_layers, with the
+    optional per-resnet temporal avg-pool hooks of the stride/pool experiments."""
+
+    def __init__(self, in_channels, temb_channels, dropout=0.0, num_layers=1, resnet_eps=1e-6,
+                 resnet_time_scale_shift="default", resnet_act_fn="swish", resnet_groups=32, attn_groups=None,
+                 resnet_pre_norm=True, add_attention=True, attention_head_dim=1, output_scale_factor=1.0):
+        super().__init__()
+        self.add_attention = add_attention
+        resnet_groups = resnet_groups if resnet_groups is not None else min(in_channels // 4, 32)
+        if attn_groups is None:
+            attn_groups = resnet_groups if resnet_time_scale_shift == "default" else None
+        if attention_head_dim is None:
+            attention_head_dim = in_channels
+
+        def res():
+            return ResnetBlockCausal3D(in_channels=in_channels, out_channels=in_channels, temb_channels=temb_channels,
+                                       eps=resnet_eps, groups=resnet_groups, dropout=dropout,
+                                       time_embedding_norm=resnet_time_scale_shift, non_linearity=resnet_act_fn,
+                                       output_scale_factor=output_scale_factor, pre_norm=resnet_pre_norm)
+
+        resnets, attentions = [res()], []
+        for _ in range(num_layers):
+            attentions.append(Attention(in_channels, heads=in_channels // attention_head_dim, dim_head=attention_head_dim,
+                                        rescale_output_factor=output_scale_factor, eps=resnet_eps,
+                                        norm_num_groups=attn_groups, residual_connection=True, bias=True)
+                              if add_attention else None)
+            resnets.append(res())
+        self.attentions = nn.ModuleList(attentions)
+        self.resnets = nn.ModuleList(resnets)
+        self.num_resblocks = num_layers + 1
+        self.resnet_pool_configs = [None] * self.num_resblocks
+        self.resnet_pad_configs = [None] * self.num_resblocks
+
+    def apply_t_ops_config_midblock(self, config: dict):
+        if not isinstance(config, dict):
+            return
+        epb = config.get("enable_t_pool_before_block", [])
+        epa = config.get("enable_t_pool_after_block", [])
+        if any(len(lst) != self.num_resblocks for lst in (epb, epa)):
+            raise ValueError(f"[UNetMidBlockCausal3D] T-ops config mismatch: we have {self.num_resblocks} ResnetBlock(s), "
+                             f"but got list lengths: {list(map(len, [epb, epa]))}")
+        k, s = config.get("pool_t_kernel", 2), config.get("pool_t_stride", 2)
+        for i in range(self.num_resblocks):
+            self.resnet_pool_configs[i] = {"enable_before": epb[i], "enable_after": epa[i], "kernel": k, "stride": s}
+
+    def forward_vol(self, x: Vol) -> Vol:
+        for i in range(self.num_resblocks):
+            if i > 0 and self.attentions[i - 1] is not None:
+                x = self.attentions[i - 1].forward_vol(x)
+            pc = self.resnet_pool_configs[i] or {}
+            if pc.get("enable_before", False):
+                x = N.avgpool_t(x, pc["kernel"], pc["stride"])
+            x = self.resnets[i].forward_vol(x)
+            if pc.get("enable_after", False):
+                x = N.avgpool_t(x, pc["kernel"], pc["stride"])
+        return x
+
+    def forward(self, hidden_states, temb=None):
+        return self.forward_vol(Vol.from_ncthw(hidden_states)).to_ncthw()
+
+
+class DownEncoderBlockCausal3D(nn.Module):
+    """unet_causal_3d_blocks.py:680-790."""
+
+    def __init__(self, in_channels, out_channels, dropout=0.0, num_layers=1, resnet_eps=1e-6,
+                 resnet_time_scale_shift="default", resnet_act_fn="swish", resnet_groups=32, resnet_pre_norm=True,
+                 output_scale_factor=1.0, add_downsample=True, downsample_stride=2, downsample_padding=1):
+        super().__init__()
+        self.resnets = nn.ModuleList([
+            ResnetBlockCausal3D(in_channels=in_channels if i == 0 else out_channels, out_channels=out_channels,
+                                temb_channels=None, eps=resnet_eps, groups=resnet_groups, dropout=dropout,
+                                time_embedding_norm=resnet_time_scale_shift, non_linearity=resnet_act_fn,
+                                output_scale_factor=output_scale_factor, pre_norm=resnet_pre_norm)
+            for i in range(num_layers)])
+        self.downsamplers = (nn.ModuleList([DownsampleCausal3D(out_channels, use_conv=True, out_channels=out_channels,
+                                                               padding=downsample_padding, name="op", stride=downsample_stride)])
+                             if add_downsample else None)
+        self.resnet_pool_configs = [None] * num_layers
+
+    def apply_t_ops_config(self, block_config: dict):
+        if "downsample_stride" in block_config and self.downsamplers is not None:
+            for ds in self.downsamplers:
+                ds.conv.conv.stride = tuple(block_config["downsample_stride"])
+        n = len(self.resnets)
+        epb = block_config.get("enable_t_pool_before_block", [])
+        epa = block_config.get("enable_t_pool_after_block", [])
+        if any(len(x) != n for x in (epb, epa)):
+            raise ValueError(f"[DownEncoderBlockCausal3D] config mismatch: expecting {n} bools in each list.")
+        k, s = block_config.get("pool_t_kernel", 2), block_config.get("pool_t_stride", 2)
+        for i in range(n):
+            self.resnet_pool_configs[i] = {"enable_before": epb[i], "enable_after": epa[i], "kernel": k, "stride": s}
+
+    def forward_vol(self, x: Vol) -> Vol:
+        for i, resnet in enumerate(self.resnets):
+            pc = self.resnet_pool_configs[i] or {}
+            if pc.get("enable_before", False):
+                x = N.avgpool_t(x, pc["kernel"], pc["stride"])
+            x = resnet.forward_vol(x)
+            if pc.get("enable_after", False):
+                x = N.avgpool_t(x, pc["kernel"], pc["stride"])
+        if self.downsamplers is not None:
+            for ds in self.downsamplers:
+                x = ds.forward_vol(x)
+        return x
+
+    def forward(self, hidden_states, scale: float = 1.0, index: int = None):
+        return self.forward_vol(Vol.from_ncthw(hidden_states)).to_ncthw()
+
+
+class UpDecoderBlockCausal3D(nn.Module):
+    """unet_causal_3d_blocks.py:792-917."""
+
+    def __init__(self, in_channels, out_channels, resolution_idx=None, dropout=0.0, num_layers=1, resnet_eps=1e-6,
+                 resnet_time_scale_shift="default", resnet_act_fn="swish", resnet_groups=32, resnet_pre_norm=True,
+                 output_scale_factor=1.0, add_upsample=True, upsample_scale_factor=(2, 2, 2), temb_channels=None):
+        super().__init__()
+        self.resnets = nn.ModuleList([
+            ResnetBlockCausal3D(in_channels=in_channels if i == 0 else out_channels, out_channels=out_channels,
+                                temb_channels=temb_channels, eps=resnet_eps, groups=resnet_groups, dropout=dropout,
+                                time_embedding_norm=resnet_time_scale_shift, non_linearity=resnet_act_fn,
+                                output_scale_factor=output_scale_factor, pre_norm=resnet_pre_norm)
+            for i in range(num_layers)])
+        self.upsamplers = (nn.ModuleList([UpsampleCausal3D(out_channels, use_conv=True, out_channels=out_channels,
+                                                           upsample_factor=upsample_scale_factor)])
+                           if add_upsample else None)
+        self.resolution_idx, self.num_layers = resolution_idx, num_layers
+        self.resnet_interp_configs = [None] * num_layers
+
+    def apply_t_ops_config(self, block_config: dict):
+        n = len(self.resnets)
+        eib = block_config.get("enable_t_interp_before_block", [])
+        eia = block_config.get("enable_t_interp_after_block", [])
+        if any(len(x) != n for x in (eib, eia)):
+            raise ValueError(f"[UpDecoderBlockCausal3D] config mismatch: expecting {n} bools in each list.")
+        sc, mode = block_config.get("interp_t_scale_factor", 2), block_config.get("interp_mode", "nearest")
+        for i in range(n):
+            self.resnet_interp_configs[i] = {"enable_before": eib[i], "enable_after": eia[i], "scale_factor": sc, "mode": mode}
+
+    @staticmethod
+    def _interp(x: Vol, conf) -> Vol:
+        if conf["mode"] != "nearest":
+            raise NotImplementedError(f"interp_mode {conf['mode']!r}: only 'nearest' has a CUDA kernel")
+        return N.interp_t_nearest(x, conf["scale_factor"]) if x.T > 0 else x
+
+    def forward_vol(self, x: Vol) -> Vol:
+        for i, resnet in enumerate(self.resnets):
+            ic = self.resnet_interp_configs[i] or {}
+            if ic.get("enable_before", False):
+                x = self._interp(x, ic)
+            x = resnet.forward_vol(x)
+            if ic.get("enable_after", False):
+                x = self._interp(x, ic)
+        if self.upsamplers is not None:
+            for up in self.upsamplers:
+                x = up.forward_vol(x)
+        return x
+
+    def forward(self, hidden_states, temb=None, scale: float = 1.0):
+        return self.forward_vol(Vol.from_ncthw(hidden_states)).to_ncthw()
+
+
+def get_down_block3d(down_block_type, num_layers, in_channels, out_channels, temb_channels, add_downsample,
+                     downsample_stride, resnet_eps, resnet_act_fn, resnet_groups=None, downsample_padding=None,
+                     resnet_time_scale_shift="default", dropout=0.0, **unused):
+    t = down_block_type[7:] if down_block_type.startswith("UNetRes") else down_block_type
+    if t == "DownEncoderBlockCausal3D":
+        return DownEncoderBlockCausal3D(num_layers=num_layers, in_channels=in_channels, out_channels=out_channels,
+                                        dropout=dropout, add_downsample=add_downsample, downsample_stride=downsample_stride,
+                                        resnet_eps=resnet_eps, resnet_act_fn=resnet_act_fn, resnet_groups=resnet_groups,
+                                        downsample_padding=downsample_padding, resnet_time_scale_shift=resnet_time_scale_shift)
+    raise ValueError(f"{down_block_type} does not exist.")
+
+
+def get_up_block3d(up_block_type, num_layers, in_channels, out_channels, prev_output_channel, temb_channels,
+                   add_upsample, upsample_scale_factor, resnet_eps, resnet_act_fn, resolution_idx=None,
+                   resnet_groups=None, resnet_time_scale_shift="default", dropout=0.0, **unused):
+    t = up_block_type[7:] if up_block_type.startswith("UNetRes") else up_block_type
+    if t == "UpDecoderBlockCausal3D":
+        return UpDecoderBlockCausal3D(num_layers=num_layers, in_channels=in_channels, out_channels=out_channels,
+                                      resolution_idx=resolution_idx, dropout=dropout, add_upsample=add_upsample,
+                                      upsample_scale_factor=upsample_scale_factor, resnet_eps=resnet_eps,
+                                      resnet_act_fn=resnet_act_fn, resnet_groups=resnet_groups,
+                                      resnet_time_scale_shift=resnet_time_scale_shift, temb_channels=temb_channels)
+    raise ValueError(f"{up_block_type} does not exist.")

@@ -1,0 +1,517 @@
+"""AutoencoderKLCausal3D on libhyvae.so: the reference's module API over a CUDA tile schedule.
+
+Surface kept from /root/reference/hyvideo/vae/autoencoder_kl_causal_3d.py and vae.py:
+constructor/config keys, `encode / decode / forward`, the tiling and slicing switches and public tiling
+attributes, `spatial_tiled_* / temporal_tiled_*`, `blend_v/h/t`, `DiagonalGaussianDistribution`,
+`DecoderOutput`, the sub-module tree and its 248 state-dict keys.  `tiled_decode()` (named by the
+north-star, absent from the reference) is provided as decode-with-tiling.
+
+Underneath, a sub-model call is: NCTHW slice -> channels-last volume -> kernel schedule (blocks.py) ->
+NCTHW tile; tile assembly is the fused blend+crop+scatter kernel applied in the reference's raster
+order (the blend chain is in place and order dependent, autoencoder_kl_causal_3d.py:403-409,457-462).
+"""
+from __future__ import annotations
+
+import inspect
+import json
+import math
+import os
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _native as N
+from .._native import Vol
+from .blocks import CausalConv3d, UNetMidBlockCausal3D, _GroupNorm, get_down_block3d, get_up_block3d
+
+
+# --------------------------------------------------------------------------------------- outputs
+class _Output(dict):
+    """Attribute + index access like diffusers' BaseOutput (`.sample`, `["sample"]`, `[0]`)."""
+
+    def __init__(self, **kw):
+        super().__init__({k: v for k, v in kw.items() if v is not None})
+        self.__dict__.update(kw)
+
+    def __getitem__(self, k):
+        return super().__getitem__(k) if isinstance(k, str) else self.to_tuple()[k]
+
+    def to_tuple(self):
+        return tuple(self.values())
+
+
+class DecoderOutput(_Output):
+    def __init__(self, sample):
+        super().__init__(sample=sample)
+
+
+class DecoderOutput2(_Output):
+    def __init__(self, sample, posterior=None):
+        super().__init__(sample=sample, posterior=posterior)
+
+
+class AutoencoderKLOutput(_Output):
+    def __init__(self, latent_dist, tiles_ci=None):  # `tiles_ci` is passed at autoencoder_kl_causal_3d.py:296
+        super().__init__(latent_dist=latent_dist)
+        self.tiles_ci = tiles_ci
+
+
+class DiagonalGaussianDistribution(object):
+    """vae.py:297-358.  A handful of tiny elementwise torch ops on the moments."""
+
+    def __init__(self, parameters: torch.Tensor, deterministic: bool = False):
+        if parameters.ndim == 3:
+            dim = 2
+        elif parameters.ndim in (4, 5):
+            dim = 1
+        else:
+            raise NotImplementedError
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=dim)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        if deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        dev = self.parameters.device
+        gdev = generator.device if generator is not None else dev
+        noise = torch.randn(self.mean.shape, generator=generator, device=gdev, dtype=self.parameters.dtype).to(dev)
+        return self.mean + self.std * noise
+
+    def kl(self, other: "DiagonalGaussianDistribution" = None) -> torch.Tensor:
+        if self.deterministic:
+            return torch.Tensor([0.0])
+        dims = list(range(1, self.mean.ndim))
+        if other is None:
+            return 0.5 * torch.sum(torch.pow(self.mean, 2) + self.var - 1.0 - self.logvar, dim=dims)
+        return 0.5 * torch.sum(torch.pow(self.mean - other.mean, 2) / other.var + self.var / other.var - 1.0
+                               - self.logvar + other.logvar, dim=dims)
+
+    def nll(self, sample: torch.Tensor, dims=(1, 2, 3)) -> torch.Tensor:
+        if self.deterministic:
+            return torch.Tensor([0.0])
+        return 0.5 * torch.sum(np.log(2.0 * np.pi) + self.logvar + torch.pow(sample - self.mean, 2) / self.var, dim=list(dims))
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+
+# --------------------------------------------------------------------------------------- sub-models
+def _sampler_plan(n_blocks: int, spatial_ratio: int, time_ratio: int):
+    """Per block (has_sampler, (t, h, w) factor) — vae.py:58-81 (encoder) and :176-201 (decoder)."""
+    if time_ratio != 4:
+        raise ValueError(f"Unsupported time_compression_ratio: {time_ratio}.")
+    ns, nt = int(np.log2(spatial_ratio)), int(np.log2(time_ratio))
+    plan = []
+    for i in range(n_blocks):
+        sp = i < ns
+        tm = (i >= n_blocks - 1 - nt) and i != n_blocks - 1
+        plan.append((sp or tm, ((2 if tm else 1), (2 if sp else 1), (2 if sp else 1))))
+    return plan
+
+
+class EncoderCausal3D(nn.Module):
+    """vae.py:32-136."""
+
+    def __init__(self, in_channels=3, out_channels=3, down_block_types=("DownEncoderBlockCausal3D",),
+                 block_out_channels=(64,), layers_per_block=2, norm_num_groups=32, act_fn="silu", double_z=True,
+                 mid_block_add_attention=True, time_compression_ratio=4, spatial_compression_ratio=8):
+        super().__init__()
+        self.layers_per_block = layers_per_block
+        self.conv_in = CausalConv3d(in_channels, block_out_channels[0], kernel_size=3, stride=1)
+        self.down_blocks = nn.ModuleList([])
+        plan = _sampler_plan(len(block_out_channels), spatial_compression_ratio, time_compression_ratio)
+        oc = block_out_channels[0]
+        for i, t in enumerate(down_block_types):
+            ic, oc = oc, block_out_channels[i]
+            self.down_blocks.append(get_down_block3d(
+                t, num_layers=layers_per_block, in_channels=ic, out_channels=oc, add_downsample=plan[i][0],
+                downsample_stride=plan[i][1], resnet_eps=1e-6, downsample_padding=0, resnet_act_fn=act_fn,
+                resnet_groups=norm_num_groups, attention_head_dim=oc, temb_channels=None))
+        self.mid_block = UNetMidBlockCausal3D(
+            in_channels=block_out_channels[-1], resnet_eps=1e-6, resnet_act_fn=act_fn, output_scale_factor=1,
+            resnet_time_scale_shift="default", attention_head_dim=block_out_channels[-1], resnet_groups=norm_num_groups,
+            temb_channels=None, add_attention=mid_block_add_attention)
+        self.conv_norm_out = _GroupNorm(norm_num_groups, block_out_channels[-1], 1e-6)
+        self.conv_out = CausalConv3d(block_out_channels[-1], 2 * out_channels if double_z else out_channels, kernel_size=3)
+
+    def forward_vol(self, x: Vol) -> Vol:
+        x = self.conv_in.forward_vol(x)
+        for blk in self.down_blocks:
+            x = blk.forward_vol(x)
+        x = self.mid_block.forward_vol(x)
+        x = self.conv_norm_out.forward_vol(x, True, self.conv_out.wants_halo(x.dtype))
+        return self.conv_out.forward_vol(x)
+
+    def forward(self, sample: torch.Tensor) -> torch.Tensor:
+        assert len(sample.shape) == 5, "The input tensor should have 5 dimensions"
+        return self.forward_vol(Vol.from_ncthw(sample)).to_ncthw()
+
+
+class DecoderCausal3D(nn.Module):
+    """vae.py:139-294."""
+
+    def __init__(self, in_channels=3, out_channels=3, up_block_types=("UpDecoderBlockCausal3D",),
+                 block_out_channels=(64,), layers_per_block=2, norm_num_groups=32, act_fn="silu", norm_type="group",
+                 mid_block_add_attention=True, time_compression_ratio=4, spatial_compression_ratio=8):
+        super().__init__()
+        if norm_type != "group":
+            raise NotImplementedError("norm_type 'spatial'")
+        self.layers_per_block = layers_per_block
+        self.conv_in = CausalConv3d(in_channels, block_out_channels[-1], kernel_size=3, stride=1)
+        self.mid_block = UNetMidBlockCausal3D(
+            in_channels=block_out_channels[-1], resnet_eps=1e-6, resnet_act_fn=act_fn, output_scale_factor=1,
+            resnet_time_scale_shift="default", attention_head_dim=block_out_channels[-1], resnet_groups=norm_num_groups,
+            temb_channels=None, add_attention=mid_block_add_attention)
+        self.up_blocks = nn.ModuleList([])
+        rev = list(reversed(block_out_channels))
+        plan = _sampler_plan(len(block_out_channels), spatial_compression_ratio, time_compression_ratio)
+        oc = rev[0]
+        for i, t in enumerate(up_block_types):
+            pc, oc = oc, rev[i]
+            self.up_blocks.append(get_up_block3d(
+                t, num_layers=layers_per_block + 1, in_channels=pc, out_channels=oc, prev_output_channel=None,
+                add_upsample=plan[i][0], upsample_scale_factor=plan[i][1], resnet_eps=1e-6, resnet_act_fn=act_fn,
+                resnet_groups=norm_num_groups, attention_head_dim=oc, temb_channels=None,
+                resnet_time_scale_shift="default"))
+        self.conv_norm_out = _GroupNorm(norm_num_groups, block_out_channels[0], 1e-6)
+        self.conv_out = CausalConv3d(block_out_channels[0], out_channels, kernel_size=3)
+        self.gradient_checkpointing = False
+
+    def forward_vol(self, x: Vol) -> Vol:
+        x = self.conv_in.forward_vol(x)
+        x = self.mid_block.forward_vol(x)
+        for blk in self.up_blocks:
+            x = blk.forward_vol(x)
+        x = self.conv_norm_out.forward_vol(x, True, self.conv_out.wants_halo(x.dtype))
+        return self.conv_out.forward_vol(x)
+
+    def forward(self, sample: torch.Tensor, latent_embeds=None) -> torch.Tensor:
+        assert len(sample.shape) == 5, "The input tensor should have 5 dimensions."
+        if latent_embeds is not None:
+            raise NotImplementedError("latent_embeds")
+        return self.forward_vol(Vol.from_ncthw(sample)).to_ncthw()
+
+
+# --------------------------------------------------------------------------------------- config
+class FrozenConfig(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+class _ConvParamsOnly(nn.Module):
+    """quant_conv / post_quant_conv: an nn.Conv3d(k=1) in the reference (:114-115); here weights + a
+    1x1x1 launch of the conv kernel."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(c, c, 1, 1, 1))
+        self.bias = nn.Parameter(torch.empty(c))
+        b = 1.0 / math.sqrt(c)
+        nn.init.uniform_(self.weight, -b, b)
+        nn.init.uniform_(self.bias, -b, b)
+        self._packed = None
+
+    def forward_vol(self, x: Vol) -> Vol:
+        key = (self.weight._version, self.bias._version, self.weight.data_ptr(), x.dtype)
+        if self._packed is None or self._packed[0] != key:
+            c = self.weight.shape[0]
+            self._packed = (key, self.weight.detach().reshape(1, c, c).to(x.dtype).contiguous(), self.bias.detach().float().contiguous())
+        return N.conv3d_direct(x, self._packed[1], self._packed[2], 1, (1, 1, 1), self.weight.shape[0],
+                               round_like_ref=x.dtype != torch.float32)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.forward_vol(Vol.from_ncthw(x)).to_ncthw()
+
+
+class AutoencoderKLCausal3D(nn.Module):
+    """autoencoder_kl_causal_3d.py:53-616 (the parts callers use)."""
+
+    config_name = "config.json"
+    _supports_gradient_checkpointing = False
+
+    def __init__(self, in_channels: int = 3, out_channels: int = 3,
+                 down_block_types: Tuple[str] = ("DownEncoderBlockCausal3D",),
+                 up_block_types: Tuple[str] = ("UpDecoderBlockCausal3D",), block_out_channels: Tuple[int] = (64,),
+                 layers_per_block: int = 1, act_fn: str = "silu", latent_channels: int = 4, norm_num_groups: int = 32,
+                 sample_size: int = 32, sample_tsize: int = 64, scaling_factor: float = 0.18215,
+                 force_upcast: float = True, spatial_compression_ratio: int = 8, time_compression_ratio: int = 4,
+                 mid_block_add_attention: bool = True):
+        super().__init__()
+        sig = inspect.signature(AutoencoderKLCausal3D.__init__)
+        loc = locals()
+        self._internal_dict = FrozenConfig({k: loc[k] for k in list(sig.parameters)[1:]})
+        self.time_compression_ratio = time_compression_ratio
+        self.encoder = EncoderCausal3D(
+            in_channels=in_channels, out_channels=latent_channels, down_block_types=down_block_types,
+            block_out_channels=block_out_channels, layers_per_block=layers_per_block, act_fn=act_fn,
+            norm_num_groups=norm_num_groups, double_z=True, time_compression_ratio=time_compression_ratio,
+            spatial_compression_ratio=spatial_compression_ratio, mid_block_add_attention=mid_block_add_attention)
+        self.decoder = DecoderCausal3D(
+            in_channels=latent_channels, out_channels=out_channels, up_block_types=up_block_types,
+            block_out_channels=block_out_channels, layers_per_block=layers_per_block, norm_num_groups=norm_num_groups,
+            act_fn=act_fn, time_compression_ratio=time_compression_ratio,
+            spatial_compression_ratio=spatial_compression_ratio, mid_block_add_attention=mid_block_add_attention)
+        self.quant_conv = _ConvParamsOnly(2 * latent_channels)
+        self.post_quant_conv = _ConvParamsOnly(latent_channels)
+        self.use_slicing = self.use_spatial_tiling = self.use_temporal_tiling = False
+        self.tile_sample_min_tsize = sample_tsize
+        self.tile_latent_min_tsize = sample_tsize // time_compression_ratio
+        self.tile_sample_min_size = sample_size
+        ss = sample_size[0] if isinstance(sample_size, (list, tuple)) else sample_size
+        self.tile_latent_min_size = int(ss / (2 ** (len(block_out_channels) - 1)))
+        self.tile_overlap_factor = 0.25
+
+    # ---- diffusers-style config / nn.Module conveniences
+    @property
+    def config(self):
+        return self._internal_dict
+
+    @classmethod
+    def load_config(cls, path, **kw):
+        p = path if str(path).endswith(".json") else os.path.join(path, cls.config_name)
+        with open(p) as f:
+            return json.load(f)
+
+    @classmethod
+    def from_config(cls, config, **kwargs):
+        sig = inspect.signature(cls.__init__)
+        cfg = {k: v for k, v in dict(config).items() if k in sig.parameters}
+        cfg.update(kwargs)
+        return cls(**cfg)
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    # ---- switches (:138-179)
+    def enable_temporal_tiling(self, use_tiling: bool = True):
+        self.use_temporal_tiling = use_tiling
+
+    def disable_temporal_tiling(self):
+        self.enable_temporal_tiling(False)
+
+    def enable_spatial_tiling(self, use_tiling: bool = True):
+        self.use_spatial_tiling = use_tiling
+
+    def disable_spatial_tiling(self):
+        self.enable_spatial_tiling(False)
+
+    def enable_tiling(self, use_tiling: bool = True):
+        self.enable_spatial_tiling(use_tiling)
+        self.enable_temporal_tiling(use_tiling)
+
+    def disable_tiling(self):
+        self.disable_spatial_tiling()
+        self.disable_temporal_tiling()
+
+    def enable_slicing(self):
+        self.use_slicing = True
+
+    def disable_slicing(self):
+        self.use_slicing = False
+
+    # ---- one sub-model call on one tile (NCTHW in, NCTHW out)
+    def _act_dtype(self):
+        return self.dtype
+
+    def _encode_tile(self, x: torch.Tensor) -> torch.Tensor:
+        v = Vol.from_ncthw(x, dtype=self._act_dtype())
+        return self.quant_conv.forward_vol(self.encoder.forward_vol(v)).to_ncthw()
+
+    def _decode_tile(self, z: torch.Tensor) -> torch.Tensor:
+        v = Vol.from_ncthw(z, dtype=self._act_dtype())
+        return self.decoder.forward_vol(self.post_quant_conv.forward_vol(v)).to_ncthw()
+
+    # ---- encode / decode (:259-342)
+    def encode(self, x: torch.Tensor, return_dict: bool = True):
+        assert len(x.shape) == 5, "The input tensor should have 5 dimensions."
+        if self.use_temporal_tiling and x.shape[2] > self.tile_sample_min_tsize:
+            return self.temporal_tiled_encode(x, return_dict=return_dict)
+        if self.use_spatial_tiling and (x.shape[-1] > self.tile_sample_min_size or x.shape[-2] > self.tile_sample_min_size):
+            return self.spatial_tiled_encode(x, return_dict=return_dict)
+        if self.use_slicing and x.shape[0] > 1:
+            moments = torch.cat([self._encode_tile(s) for s in x.split(1)])
+        else:
+            moments = self._encode_tile(x)
+        posterior = DiagonalGaussianDistribution(moments)
+        if not return_dict:
+            return (posterior,)
+        return AutoencoderKLOutput(latent_dist=posterior, tiles_ci=None)
+
+    def _decode(self, z: torch.Tensor, return_dict: bool = True):
+        assert len(z.shape) == 5, "The input tensor should have 5 dimensions."
+        if self.use_temporal_tiling and z.shape[2] > self.tile_latent_min_tsize:
+            return self.temporal_tiled_decode(z, return_dict=return_dict)
+        if self.use_spatial_tiling and (z.shape[-1] > self.tile_latent_min_size or z.shape[-2] > self.tile_latent_min_size):
+            return self.spatial_tiled_decode(z, return_dict=return_dict)
+        dec = self._decode_tile(z)
+        if not return_dict:
+            return (dec,)
+        return DecoderOutput(sample=dec)
+
+    def decode(self, z: torch.Tensor, return_dict: bool = True, generator=None):
+        if self.use_slicing and z.shape[0] > 1:
+            decoded = torch.cat([self._decode(s).sample for s in z.split(1)])
+        else:
+            decoded = self._decode(z).sample
+        if not return_dict:
+            return (decoded,)
+        return DecoderOutput(sample=decoded)
+
+    def tiled_decode(self, z: torch.Tensor, return_dict: bool = True):
+        """decode() with spatial + temporal tiling switched on for this call."""
+        saved = (self.use_spatial_tiling, self.use_temporal_tiling)
+        self.enable_tiling(True)
+        try:
+            return self.decode(z, return_dict=return_dict)
+        finally:
+            self.use_spatial_tiling, self.use_temporal_tiling = saved
+
+    # ---- blends (:344-360), public like the reference's; in place on b, one kernel each
+    @staticmethod
+    def _blend(a: torch.Tensor, b: torch.Tensor, extent: int, axis: int) -> torch.Tensor:
+        e = min(a.shape[axis], b.shape[axis], extent)
+        if e <= 0:
+            return b
+        assert a.is_contiguous() and b.is_contiguous(), "blend_* operate on contiguous tile tensors"
+        B, C, T, H, W = b.shape
+        if axis == -2:
+            N.blend_crop_scatter(b, a, None, B * C * T, H, W, a.shape[-2], 0, e, 0, None, 0, 0, 0, 0, 0, 0)
+        elif axis == -1:
+            N.blend_crop_scatter(b, None, a, B * C * T, H, W, 0, a.shape[-1], 0, e, None, 0, 0, 0, 0, 0, 0)
+        else:
+            N.blend_crop_scatter(b, a, None, B * C, T, H * W, a.shape[-3], 0, e, 0, None, 0, 0, 0, 0, 0, 0)
+        return b
+
+    def blend_v(self, a, b, blend_extent):
+        return self._blend(a, b, blend_extent, -2)
+
+    def blend_h(self, a, b, blend_extent):
+        return self._blend(a, b, blend_extent, -1)
+
+    def blend_t(self, a, b, blend_extent):
+        return self._blend(a, b, blend_extent, -3)
+
+    # ---- spatial tiling (:362-469)
+    def _spatial_tiled(self, x: torch.Tensor, fn, tile: int, stride: int, extent: int, limit: int) -> torch.Tensor:
+        rows = []
+        for i in range(0, x.shape[-2], stride):
+            rows.append([fn(x[:, :, :, i:i + tile, j:j + tile]) for j in range(0, x.shape[-1], stride)])
+        hs = [min(r[0].shape[-2], limit) for r in rows]
+        ws = [min(t.shape[-1], limit) for t in rows[0]]
+        B, C, T = rows[0][0].shape[:3]
+        out = torch.empty((B, C, T, sum(hs), sum(ws)), dtype=rows[0][0].dtype, device=x.device)
+        Yo, Xo, n = out.shape[-2], out.shape[-1], B * C * T
+        y0 = 0
+        for i, row in enumerate(rows):
+            x0 = 0
+            for j, t in enumerate(row):
+                above = rows[i - 1][j] if i > 0 else None
+                left = row[j - 1] if j > 0 else None
+                ev = min(above.shape[-2], t.shape[-2], extent) if above is not None else 0
+                eh = min(left.shape[-1], t.shape[-1], extent) if left is not None else 0
+                if ev <= 0:
+                    above = None
+                if eh <= 0:
+                    left = None
+                N.blend_crop_scatter(t, above, left, n, t.shape[-2], t.shape[-1],
+                                     above.shape[-2] if above is not None else 0, left.shape[-1] if left is not None else 0,
+                                     ev, eh, out, Yo, Xo, y0, x0, hs[i], ws[j])
+                x0 += ws[j]
+            y0 += hs[i]
+        return out
+
+    def spatial_tiled_encode(self, x: torch.Tensor, return_dict: bool = True, return_moments: bool = False):
+        stride = int(self.tile_sample_min_size * (1 - self.tile_overlap_factor))
+        extent = int(self.tile_latent_min_size * self.tile_overlap_factor)
+        moments = self._spatial_tiled(x, self._encode_tile, self.tile_sample_min_size, stride, extent,
+                                      self.tile_latent_min_size - extent)
+        if return_moments:
+            return moments
+        posterior = DiagonalGaussianDistribution(moments)
+        if not return_dict:
+            return (posterior,)
+        return AutoencoderKLOutput(latent_dist=posterior)
+
+    def spatial_tiled_decode(self, z: torch.Tensor, return_dict: bool = True):
+        stride = int(self.tile_latent_min_size * (1 - self.tile_overlap_factor))
+        extent = int(self.tile_sample_min_size * self.tile_overlap_factor)
+        dec = self._spatial_tiled(z, self._decode_tile, self.tile_latent_min_size, stride, extent,
+                                  self.tile_sample_min_size - extent)
+        if not return_dict:
+            return (dec,)
+        return DecoderOutput(sample=dec)
+
+    # ---- temporal tiling (:471-541)
+    def _temporal_tiled(self, x, fn_plain, fn_spatial, tile_t, stride, extent, limit, min_size) -> torch.Tensor:
+        row = []  # (tensor, first_frame_offset): tiles i>0 drop their first output frame (:491,527)
+        for i in range(0, x.shape[2], stride):
+            t = x[:, :, i:i + tile_t + 1]
+            if self.use_spatial_tiling and (t.shape[-1] > min_size or t.shape[-2] > min_size):
+                t = fn_spatial(t)
+            else:
+                t = fn_plain(t)
+            row.append((t, 1 if i > 0 else 0))
+        lens = [t.shape[2] - off for t, off in row]
+        keep = [min(lens[i], limit + 1 if i == 0 else limit) for i in range(len(row))]
+        B, C, _, H, W = row[0][0].shape
+        hw = H * W
+        out = torch.empty((B, C, sum(keep), H, W), dtype=row[0][0].dtype, device=x.device)
+        y0 = 0
+        for i, (t, off) in enumerate(row):
+            cur = t[:, :, off:]
+            if i > 0:
+                pt, poff = row[i - 1]
+                e = min(lens[i - 1], lens[i], extent)
+            else:
+                pt, poff, e = None, 0, 0
+            above = pt[:, :, poff:] if (pt is not None and e > 0) else None
+            ns = (t.shape[2] * hw, (pt.shape[2] * hw) if pt is not None else 0, 0, out.shape[2] * hw)
+            N.blend_crop_scatter(cur, above, None, B * C, lens[i], hw, lens[i - 1] if above is not None else 0, 0,
+                                 e if above is not None else 0, 0, out, out.shape[2], hw, y0, 0, keep[i], hw, n_strides=ns)
+            y0 += keep[i]
+        return out
+
+    def temporal_tiled_encode(self, x: torch.Tensor, return_dict: bool = True):
+        stride = int(self.tile_sample_min_tsize * (1 - self.tile_overlap_factor))
+        extent = int(self.tile_latent_min_tsize * self.tile_overlap_factor)
+        moments = self._temporal_tiled(x, self._encode_tile, lambda t: self.spatial_tiled_encode(t, return_moments=True),
+                                       self.tile_sample_min_tsize, stride, extent, self.tile_latent_min_tsize - extent,
+                                       self.tile_sample_min_size)
+        posterior = DiagonalGaussianDistribution(moments)
+        if not return_dict:
+            return (posterior,)
+        return AutoencoderKLOutput(latent_dist=posterior)
+
+    def temporal_tiled_decode(self, z: torch.Tensor, return_dict: bool = True):
+        stride = int(self.tile_latent_min_tsize * (1 - self.tile_overlap_factor))
+        extent = int(self.tile_sample_min_tsize * self.tile_overlap_factor)
+        dec = self._temporal_tiled(z, self._decode_tile, lambda t: self.spatial_tiled_decode(t, return_dict=True).sample,
+                                   self.tile_latent_min_tsize, stride, extent, self.tile_sample_min_tsize - extent,
+                                   self.tile_latent_min_size)
+        if not return_dict:
+            return (dec,)
+        return DecoderOutput(sample=dec)
+
+    # ---- forward (:543-578)
+    def forward(self, sample: torch.Tensor, sample_posterior: bool = False, return_dict: bool = True,
+                return_posterior: bool = False, generator: Optional[torch.Generator] = None):
+        posterior = self.encode(sample).latent_dist
+        z = posterior.sample(generator=generator) if sample_posterior else posterior.mode()
+        dec = self.decode(z).sample
+        if not return_dict:
+            return (dec, posterior) if return_posterior else (dec,)
+        return DecoderOutput2(sample=dec, posterior=posterior if return_posterior else None)

@@ -1,0 +1,126 @@
+/* hyvae.h — C ABI of the B200-native HunyuanVideo 3D causal VAE kernels (libhyvae.so).
+ *
+ * The reference (c976237222/HunyuanVideo_efficiency) is pure Python: its VAE has NO native / FFI
+ * boundary — every device op is reached through torch.nn.functional.  This header
+ * therefore defines the boundary a maintainer would bind; each entry point names the reference call
+ * site (file:line under /root/reference) whose ATen/cuDNN call chain it replaces.  The binding is
+ * ctypes (hunyuanvideo_efficiency_b200/_native.py); INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types; every function returns 0 on success or a
+ *    negative hyvae_status, and hyvae_last_error() returns a thread-local message.
+ *  - no allocation inside: the caller owns every buffer, including workspaces.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
+ *  - activations are CHANNELS-LAST volumes described by hyvae_vol (below).
+ */
+#ifndef HYVAE_H_
+#define HYVAE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HYVAE_VERSION 100 /* 0.1.0 */
+
+typedef enum { HYVAE_OK = 0, HYVAE_EINVAL = -1, HYVAE_ECUDA = -2, HYVAE_EUNSUPPORTED = -3 } hyvae_status;
+typedef enum { HYVAE_BF16 = 0, HYVAE_F32 = 1, HYVAE_F16 = 2 } hyvae_dtype;
+
+/* A channels-last activation volume in HBM: element (b,t,h,w,c) of the LOGICAL tensor lives at
+ *   data[(((b*(T+pt) + t+pt)*(H+2*ph) + h+ph)*(W+2*pw) + w+pw)*C + c].
+ * pt/ph/pw is a physical halo holding the reference's replicate padding already materialised
+ * (F.pad(x,(pw,pw,ph,ph,pt,0),'replicate'), unet_causal_3d_blocks.py:68,74): pt frames IN FRONT of T
+ * only (causal), ph rows / pw columns on both sides.  Producers that are given a padded destination
+ * fill the halo; the tensor-core conv reads it through TMA. */
+typedef struct {
+  void* data;
+  int32_t dtype; /* hyvae_dtype */
+  int32_t B, T, H, W, C;
+  int32_t pt, ph, pw;
+} hyvae_vol;
+
+int hyvae_version(void);
+const char* hyvae_last_error(void);
+/* 1 if the current device can run the tcgen05 path (compute capability 10.x). */
+int hyvae_device_supports_tc(void);
+
+/* ---- layout: torch NCTHW <-> channels-last volume ---------------------------------------------
+ * Replaces the implicit NCDHW layout of every reference tensor; `dst` halo is filled by replication. */
+/* src_strides: element strides of the (possibly sliced) source view in (B,C,T,H,W) order. */
+int hyvae_ncthw_to_vol(const void* src, int32_t src_dtype, const int64_t* src_strides, const hyvae_vol* dst, void* stream);
+int hyvae_vol_to_ncthw(const hyvae_vol* src, void* dst, int32_t dst_dtype, void* stream);
+
+/* ---- CausalConv3d ------------------------------------------------------------------------------
+ * Replaces F.pad(replicate)+nn.Conv3d, unet_causal_3d_blocks.py:73-75 (k=3 or k=1; stride from
+ * DownsampleCausal3D :223-225, mutable at run time :741), with the residual add of
+ * ResnetBlockCausal3D.forward :415 and the nearest upsample of UpsampleCausal3D.forward :152-171
+ * optionally folded in.
+ *   w:        [k*k*k][Cout][Cin] in x's dtype (tap-major, Cin contiguous); tap = (kt*k+kh)*k+kw.
+ *   bias:     Cout fp32 or NULL.   residual: volume shaped like y, or NULL (y = conv + bias + residual).
+ *   up_*:     1 or 2 — the conv input is the nearest-upsampled x (first frame not upsampled in T).
+ *   round_like_ref: 1 = round conv+bias to the activation dtype before adding the residual (what
+ *             the reference's two separate kernels do in bf16/fp16).
+ *   y:        same dtype as x, or HYVAE_F32 (used for the attention scores S = Q K^T).
+ * _direct: CUDA-core implicit GEMM, any shape/dtype; replicate padding by index clamping.
+ * _tc:     tcgen05/TMEM implicit GEMM fed by TMA; needs bf16/f16, Cin%64==0, Cout%16==0, up_*==1 and
+ *          x carrying the halo (pt,ph,pw) = (k-1,k/2,k/2). */
+int hyvae_conv3d_causal_direct(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
+                               const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
+                               int32_t up_t, int32_t up_h, int32_t up_w, int32_t round_like_ref, void* stream);
+int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
+                           const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
+                           int32_t round_like_ref, int32_t variant, void* stream);
+
+/* ---- GroupNorm (+SiLU) -------------------------------------------------------------------------
+ * Replaces nn.GroupNorm(32,C,eps=1e-6) + SiLU, unet_causal_3d_blocks.py:359-363,401-405 and
+ * vae.py:131-133,287-291.  Two launches: statistics (fp32/fp64 accumulation) then apply.
+ *   sums: [B][groups][2] float64 workspace (sum, sum of squares); zeroed by _stats.
+ *   y may carry a halo: it is filled with the replicated normalised values. */
+int hyvae_groupnorm_stats(const hyvae_vol* x, int32_t groups, double* sums, void* stream);
+int hyvae_groupnorm_apply(const hyvae_vol* x, const double* sums, const float* gamma, const float* beta,
+                          int32_t groups, float eps, int32_t silu, int32_t round_like_ref, const hyvae_vol* y,
+                          void* stream);
+
+/* ---- pad / nearest upsample --------------------------------------------------------------------
+ * Replaces F.pad(replicate) :74 and F.interpolate(nearest)+cat of UpsampleCausal3D.forward :152-171:
+ * y (T' = 1+up_t*(T-1) if up_t==2, H*up_h, W*up_w, with any halo) <- x. */
+int hyvae_pad_upsample(const hyvae_vol* x, const hyvae_vol* y, int32_t up_t, int32_t up_h, int32_t up_w, void* stream);
+
+/* ---- mid-block attention softmax ---------------------------------------------------------------
+ * Replaces prepare_causal_attention_mask :38-46 + the softmax inside F.scaled_dot_product_attention
+ * (diffusers Attention, call site :661): P[i][j] = softmax_j(scale*S[i][j]) over j < (i/n_hw+1)*n_hw,
+ * 0 elsewhere.  S: [B][L][L] fp32, P: [B][L][L] in `p_dtype`.  The mask is never materialised. */
+int hyvae_softmax_frame_causal(const float* S, void* P, int32_t p_dtype, int32_t B, int32_t L, int32_t n_hw,
+                               float scale, void* stream);
+
+/* ---- temporal ops of the stride/pool/bucket experiments ---------------------------------------
+ * avgpool_t replaces F.pad((0,0,0,0,k-1,0),'replicate')+F.avg_pool3d((k,1,1),(s,1,1)) :665-668,767-772;
+ * interp_t replaces F.interpolate(scale_factor=(sc,1,1), mode='nearest') :893-897,906-910
+ * (y.T = floor(x.T*scale); src = min(floor(dst*inv_scale), x.T-1) with inv_scale = (float)(1/scale), which is
+ * ATen's nearest source-index rule). */
+int hyvae_avgpool_t(const hyvae_vol* x, const hyvae_vol* y, int32_t k, int32_t s, void* stream);
+int hyvae_interp_t_nearest(const hyvae_vol* x, const hyvae_vol* y, float inv_scale, void* stream);
+
+/* ---- tile blend + crop + scatter ---------------------------------------------------------------
+ * Replaces blend_v / blend_h / blend_t (autoencoder_kl_causal_3d.py:344-360), the [:limit] crops and
+ * torch.cat (:410-412,463-465,501,537) with one pass.  All tensors are dense [N][Y][X]:
+ *   cur   [N][Yc][Xc]  blended IN PLACE (first ev rows from `above`, then first eh columns from `left`)
+ *   above [N][Ya][Xc]  or NULL: cur[y] = above[Ya-ev+y]*(1-y/ev) + cur[y]*(y/ev)
+ *   left  [N][Yc][Xl]  or NULL: cur[x] = left[Xl-eh+x]*(1-x/eh) + cur[x]*(x/eh)
+ *   out   rows [y0, y0+crop_y) x cols [x0, x0+crop_x) of a dense [N][Yo][Xo] tensor <- cur[:crop_y,:crop_x]
+ * Spatial tiles use N=(b,c,t), Y=h, X=w; temporal tiles use N=(b,c), Y=t, X=(h,w).
+ * n_strides: NULL for dense tensors, else the element stride between consecutive n of {cur, above, left, out}
+ * (lets a caller blend a view that dropped leading rows, e.g. tile[:, :, 1:] at :491,527). */
+int hyvae_blend_crop_scatter(void* cur, const void* above, const void* left, int32_t dtype, int64_t N,
+                             int32_t Yc, int32_t Xc, int32_t Ya, int32_t Xl, int32_t ev, int32_t eh,
+                             void* out, int32_t Yo, int32_t Xo, int32_t y0, int32_t x0, int32_t crop_y,
+                             int32_t crop_x, const int64_t* n_strides, void* stream);
+
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+int64_t hyvae_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYVAE_H_ */

@@ -1,0 +1,287 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed golden
+fixtures of the unmodified reference.  Tolerances are BASELINE.json's: fp32 <= 1e-4 relative,
+bf16 <= 2e-2 relative, decode PSNR >= 45 dB."""
+import os
+
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import vae_oracle as O
+from oracle import weights as W
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+PSNR_MIN = 45.0
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _N():
+    from hunyuanvideo_efficiency_b200 import _native as N
+    return N
+
+
+def _vol(x, dtype=None, pad=(0, 0, 0)):
+    return _N().Vol.from_ncthw(x.to(_dev()), dtype=dtype, pad=pad)
+
+
+def _pack(w, dtype):
+    co, ci, k = w.shape[0], w.shape[1], w.shape[2]
+    return w.permute(2, 3, 4, 0, 1).reshape(k ** 3, co, ci).to(_dev(), dtype).contiguous()
+
+
+# ----------------------------------------------------------------------------------------- kernels
+def test_layout_roundtrip_and_halo():
+    N = _N()
+    x = torch.randn(2, 5, 3, 6, 7)
+    v = _vol(x, pad=(2, 1, 1))
+    assert torch.equal(v.to_ncthw().cpu(), x)
+    ref = torch.nn.functional.pad(x, (1, 1, 1, 1, 2, 0), mode="replicate").permute(0, 2, 3, 4, 1)
+    assert torch.equal(v.t.cpu(), ref)
+    sl = x[:, :, 1:, 2:5, ::2]  # strided source view
+    assert torch.equal(N.Vol.from_ncthw(sl.to(_dev())[:, :, :, :, :]).to_ncthw().cpu(), sl)
+
+
+@pytest.mark.parametrize("tag,stride", [("s111", (1, 1, 1)), ("s122", (1, 2, 2)), ("s222", (2, 2, 2)), ("s422", (4, 2, 2))])
+def test_direct_conv_fp32_vs_reference(tag, stride):
+    N = _N()
+    _, a = load_golden("ops")
+    y = N.conv3d_direct(_vol(a["x"]), _pack(a["conv_w"], torch.float32), a["conv_b"].to(_dev()), 3, stride, 64)
+    assert O.rel_err(a[f"conv_{tag}_y"], y.to_ncthw().cpu()) < 1e-5
+
+
+def test_direct_conv_k1_nobias_and_upsample_fold():
+    N = _N()
+    _, a = load_golden("ops")
+    y = N.conv3d_direct(_vol(a["x"]), _pack(a["conv1_w"], torch.float32), None, 1, (1, 1, 1), 48)
+    assert O.rel_err(a["conv1_y"], y.to_ncthw().cpu()) < 1e-5
+    for up in ((2, 2, 2), (1, 2, 2)):
+        ref = O.causal_conv3d(O.upsample_nearest_causal(a["x"], up), a["conv_w"], a["conv_b"])
+        y = N.conv3d_direct(_vol(a["x"]), _pack(a["conv_w"], torch.float32), a["conv_b"].to(_dev()), 3, (1, 1, 1), 64, up=up)
+        assert O.rel_err(ref, y.to_ncthw().cpu()) < 1e-5
+
+
+def test_pad_upsample_matches_reference():
+    N = _N()
+    _, a = load_golden("ops")
+    for key, up, x in (("up_u222_y", (2, 2, 2), a["x"]), ("up_u122_y", (1, 2, 2), a["x"]), ("up_u222_T1_y", (2, 2, 2), a["x"][:, :, :1])):
+        y = N.pad_upsample(_vol(x), up, pad=(2, 1, 1))
+        assert torch.equal(y.to_ncthw().cpu(), a[key])
+        ref = torch.nn.functional.pad(a[key], (1, 1, 1, 1, 2, 0), mode="replicate").permute(0, 2, 3, 4, 1)
+        assert torch.equal(y.t.cpu(), ref)
+
+
+def test_groupnorm_silu_fp32_and_halo():
+    N = _N()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 64, 3, 9, 7, generator=g) * 3 + 1.5
+    gamma, beta = torch.randn(64, generator=g), torch.randn(64, generator=g)
+    ref = torch.nn.functional.silu(O.group_norm(x, gamma, beta, 32))
+    y = N.groupnorm(_vol(x), gamma.to(_dev()), beta.to(_dev()), 32, 1e-6, True, pad=(2, 1, 1), round_like_ref=False)
+    assert O.rel_err(ref, y.to_ncthw().cpu()) < 1e-5
+    refp = torch.nn.functional.pad(y.to_ncthw().cpu(), (1, 1, 1, 1, 2, 0), mode="replicate").permute(0, 2, 3, 4, 1)
+    assert torch.equal(y.t.cpu(), refp)
+
+
+def test_softmax_frame_causal():
+    N = _N()
+    T, hw = 3, 20
+    L = T * hw
+    S = torch.randn(2, L, L)
+    ref = torch.softmax(S * 0.125 + O.frame_causal_mask(T, hw)[None], dim=-1)
+    P = N.softmax_frame_causal(S.to(_dev()).contiguous(), hw, 0.125, torch.float32)
+    assert torch.allclose(P.cpu(), ref, atol=1e-6, rtol=1e-5)
+    assert torch.count_nonzero(P.cpu()[0, 0, hw:]) == 0
+
+
+def test_temporal_pool_and_interp():
+    N = _N()
+    x = torch.randn(1, 16, 7, 4, 5)
+    for k, s in ((3, 2), (2, 2), (2, 1)):
+        assert torch.allclose(N.avgpool_t(_vol(x), k, s).to_ncthw().cpu(), O.t_avg_pool(x, k, s), atol=1e-6)
+    for sc in (2, 3, 1.5):
+        assert torch.equal(N.interp_t_nearest(_vol(x), sc).to_ncthw().cpu(), O.t_interp(x, sc, "nearest"))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_blend_bit_exact(dtype):
+    from hunyuanvideo_efficiency_b200.vae import AutoencoderKLCausal3D
+    m = AutoencoderKLCausal3D.from_config(W.SMALL_CONFIG)
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(1, 3, 4, 10, 12, generator=g).to(dtype)
+    for fn, ofn, b_shape in ((m.blend_v, O.blend_v, (1, 3, 4, 6, 12)), (m.blend_h, O.blend_h, (1, 3, 4, 10, 5)),
+                             (m.blend_t, O.blend_t, (1, 3, 7, 10, 12))):
+        b = torch.randn(b_shape, generator=g).to(dtype)
+        ref = ofn(a.clone(), b.clone(), 4)
+        out = fn(a.to(_dev()), b.to(_dev()).clone(), 4)
+        assert torch.equal(out.cpu(), ref)
+
+
+# ----------------------------------------------------------------------------------------- tcgen05 conv
+def _rand_case(B, Cin, Cout, T, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Cin, T, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) / (27 * Cin) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    return x, w, b
+
+
+@pytest.mark.parametrize("B,Cin,Cout,T,H,W,stride", [
+    (1, 64, 64, 3, 8, 16, (1, 1, 1)),      # exactly one 8x16 tile, BN=64
+    (1, 128, 128, 4, 16, 32, (1, 1, 1)),   # BN=128
+    (2, 128, 256, 3, 18, 20, (1, 1, 1)),   # ragged H/W, batch 2, BN=256
+    (1, 512, 512, 2, 8, 16, (1, 1, 1)),    # two n-tiles, deep K
+    (1, 192, 96, 2, 9, 33, (1, 1, 1)),     # Cin/Cout not multiples of 64 -> TMA zero fill on both operands
+    (1, 128, 128, 5, 16, 32, (1, 2, 2)),   # DownsampleCausal3D strides
+    (1, 128, 128, 5, 16, 32, (2, 2, 2)),
+    (1, 64, 32, 9, 12, 10, (4, 2, 2)),     # run-time T-stride 4 (t-ops), BN=32
+])
+def test_tc_conv_matches_direct_bf16(B, Cin, Cout, T, H, W, stride):
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    x, w, b = _rand_case(B, Cin, Cout, T, H, W, 11)
+    xb, wb = x.bfloat16(), w.bfloat16()
+    ref = O.causal_conv3d(xb.float(), wb.float(), b, stride)  # same bf16-rounded operands, fp32 math
+    xv = _vol(xb, pad=(2, 1, 1))
+    y = N.conv3d_tc(xv, _pack(wb, torch.bfloat16), b.to(_dev()), 3, stride, Cout, out_dtype=torch.float32)
+    assert O.rel_err(ref, y.to_ncthw().cpu()) < 2e-5   # fp32 accumulation of exact bf16 products
+    y16 = N.conv3d_tc(xv, _pack(wb, torch.bfloat16), b.to(_dev()), 3, stride, Cout)
+    assert torch.equal(y16.to_ncthw().cpu(), y.to_ncthw().cpu().bfloat16()) or O.rel_err(ref, y16.to_ncthw().float().cpu()) < 4e-3
+
+
+def test_tc_gemm_k1_residual_and_fp16():
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    g = torch.Generator().manual_seed(2)
+    for dt in (torch.bfloat16, torch.float16):
+        x = torch.randn(1, 256, 2, 10, 12, generator=g).to(dt)
+        w = (torch.randn(128, 256, 1, 1, 1, generator=g) / 16).to(dt)
+        b = torch.randn(128, generator=g)
+        r = torch.randn(1, 128, 2, 10, 12, generator=g).to(dt)
+        conv = (O.causal_conv3d(x.float(), w.float(), b)).to(dt).float()   # reference rounds before the add
+        ref = (conv + r.float()).to(dt)
+        y = N.conv3d_tc(_vol(x), _pack(w, dt), b.to(_dev()), 1, (1, 1, 1), 128, residual=_vol(r))
+        d = (y.to_ncthw().cpu().float() - ref.float()).abs().max().item()
+        assert d <= 0.0625, d   # at most one 16-bit ulp at |v| ~ 8
+
+
+def test_tc_big_gemm_matrix_mode():
+    """Attention-shaped GEMM: S = Q K^T with L rows, fp32 out, tile = 1 x 128 rows."""
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    g = torch.Generator().manual_seed(4)
+    L, Cn = 1000, 128   # L not a multiple of 128 or 64
+    q = torch.randn(L, Cn, generator=g).bfloat16()
+    k = torch.randn(L, Cn, generator=g).bfloat16()
+    qv = N.Vol(1, 1, 1, L, Cn, torch.bfloat16, _dev(), tensor=q.to(_dev()).reshape(1, 1, 1, L, Cn).contiguous())
+    s = N.conv3d_tc(qv, k.to(_dev()).contiguous(), None, 1, (1, 1, 1), L, out_dtype=torch.float32)
+    ref = q.float() @ k.float().T
+    assert O.rel_err(ref, s.t.reshape(L, L).cpu()) < 2e-5
+
+
+# ----------------------------------------------------------------------------------------- blocks vs reference
+def test_resnet_and_midblock_fp32_vs_reference():
+    from hunyuanvideo_efficiency_b200.vae.blocks import ResnetBlockCausal3D, UNetMidBlockCausal3D
+    _, a = load_golden("ops")
+    r = ResnetBlockCausal3D(in_channels=32, out_channels=64, temb_channels=None, groups=32, eps=1e-6)
+    r.load_state_dict({k[len("res_sd."):]: v for k, v in a.items() if k.startswith("res_sd.")})
+    y = r.to(_dev())(a["x"].to(_dev()))
+    assert O.rel_err(a["res_y"], y.cpu()) < FP32_TOL
+    mb = UNetMidBlockCausal3D(in_channels=64, temb_channels=None, resnet_groups=32, attention_head_dim=64)
+    mb.load_state_dict({k[len("mid_sd."):]: v for k, v in a.items() if k.startswith("mid_sd.")})
+    y = mb.to(_dev())(a["mid_x"].to(_dev()))
+    assert O.rel_err(a["mid_y"], y.cpu()) < FP32_TOL
+
+
+# ----------------------------------------------------------------------------------------- whole model
+def _build(cfg, dtype, t_ops=None):
+    from hunyuanvideo_efficiency_b200.vae import AutoencoderKLCausal3D, _apply_t_ops_config_to_vae
+    m = AutoencoderKLCausal3D.from_config(cfg)
+    m.load_state_dict(W.make_state_dict(cfg))
+    m = m.to(dtype).to(_dev()).eval().requires_grad_(False)
+    if t_ops is not None:
+        _apply_t_ops_config_to_vae(m, t_ops)
+    return m
+
+
+MODEL_CASES = ["small_untiled", "small_untiled_b2", "small_spatial", "small_temporal", "small_tiled", "hy_untiled",
+               "small_tops_pool_interp", "small_tops_stride4"]
+
+
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_model_fp32_vs_reference_golden(name):
+    meta, a = load_golden(name)
+    m = _build(getattr(W, meta["cfg"]), torch.float32, meta["t_ops"])
+    m.enable_spatial_tiling(meta["spatial"])
+    m.enable_temporal_tiling(meta["temporal"])
+    x = W.make_video(tuple(meta["shape"]), meta["video_seed"]).to(_dev())
+    post = m.encode(x).latent_dist
+    assert post.parameters.shape == a["moments"].shape
+    assert O.rel_err(a["moments"], post.parameters.cpu()) < FP32_TOL
+    mean, _ = O.posterior_mean_logvar(a["moments"])
+    dec = m.decode(mean.to(_dev())).sample
+    assert dec.shape == a["dec"].shape
+    assert O.rel_err(a["dec"], dec.cpu()) < FP32_TOL
+    assert O.psnr(a["dec"], dec.cpu()) > 80
+
+
+@pytest.mark.parametrize("name", ["small_untiled", "small_tiled", "hy_untiled"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_model_16bit_vs_reference_golden(name, dtype):
+    meta, a = load_golden(name)
+    m = _build(getattr(W, meta["cfg"]), dtype)
+    m.enable_spatial_tiling(meta["spatial"])
+    m.enable_temporal_tiling(meta["temporal"])
+    x = W.make_video(tuple(meta["shape"]), meta["video_seed"]).to(_dev(), dtype)
+    post = m.encode(x).latent_dist
+    mean_ref, _ = O.posterior_mean_logvar(a["moments"])
+    assert O.rel_err(mean_ref, post.mode().float().cpu()) < BF16_TOL
+    dec = m.decode(mean_ref.to(_dev(), dtype)).sample
+    assert O.rel_err(a["dec"], dec.float().cpu()) < BF16_TOL
+    assert O.psnr(a["dec"], dec.float().cpu()) > PSNR_MIN
+
+
+def test_tc_model_path_matches_direct_path_bf16():
+    """Same bf16 model through the tcgen05 convs and through the CUDA-core convs (HYVAE_FORCE_DIRECT)."""
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    cfg = dict(W.SMALL_CONFIG, block_out_channels=[64, 128, 256, 256])
+    m = _build(cfg, torch.bfloat16)
+    m.enable_tiling()
+    x = W.make_video((1, 3, 21, 40, 48)).to(_dev(), torch.bfloat16)
+    sd = W.make_state_dict(cfg)
+    ref_dec, ref_mean, _ = O.forward(sd, cfg, x.float().cpu(), O.Tiling.from_cfg(cfg, True, True))
+    n0 = N.launch_count()
+    dec_tc, post_tc = m(x, return_dict=False, return_posterior=True)
+    assert N.launch_count() > n0
+    os.environ["HYVAE_FORCE_DIRECT"] = "1"
+    try:
+        dec_d, post_d = m(x, return_dict=False, return_posterior=True)
+    finally:
+        os.environ.pop("HYVAE_FORCE_DIRECT")
+    for dec, post in ((dec_tc, post_tc), (dec_d, post_d)):
+        assert O.rel_err(ref_mean, post.mode().float().cpu()) < BF16_TOL
+        assert O.psnr(ref_dec, dec.float().cpu()) > PSNR_MIN
+    assert O.rel_err(dec_d.float().cpu(), dec_tc.float().cpu()) < BF16_TOL
+
+
+def test_full_size_tile_properties_bf16():
+    """HY config at one canonical decoder tile shape (BASELINE config 2's unit): linearity-free properties
+    that do not need the oracle at full size: determinism, and tiled == untiled when one tile covers the input."""
+    N = _N()
+    m = _build(W.HY_VAE_CONFIG, torch.bfloat16)
+    z = W.make_latent((1, 16, 5, 32, 32)).to(_dev(), torch.bfloat16)
+    d1 = m.decode(z).sample
+    m.enable_tiling()
+    d2 = m.decode(z).sample
+    assert d1.shape == (1, 3, 17, 256, 256) and torch.equal(d1, d2)
+    assert torch.isfinite(d1.float()).all()
