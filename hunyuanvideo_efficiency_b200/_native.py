@@ -37,7 +37,7 @@ _SIGNATURES = {
     "hyvae_vol_to_ncthw": [_VP, _vp, _i32, _vp],
     "hyvae_conv3d_causal_direct": [_VP, _vp, _vp, _VP, _VP, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "hyvae_conv3d_causal_tc": [_VP, _vp, _vp, _VP, _VP, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
-    "hyvae_groupnorm_stats": [_VP, _i32, _vp, _vp],
+    "hyvae_groupnorm_stats": [_VP, _i32, _vp, _vp, _i64, _vp],
     "hyvae_groupnorm_apply": [_VP, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _VP, _vp],
     "hyvae_pad_upsample": [_VP, _VP, _i32, _i32, _i32, _vp],
     "hyvae_softmax_frame_causal": [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp],
@@ -46,7 +46,8 @@ _SIGNATURES = {
     "hyvae_blend_crop_scatter": [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32,
                                  _i32, _i32, _i32, _i32, C.POINTER(_i64), _vp],
 }
-EXPORTS = sorted(list(_SIGNATURES) + ["hyvae_version", "hyvae_last_error", "hyvae_device_supports_tc", "hyvae_launch_count"])
+EXPORTS = sorted(list(_SIGNATURES) + ["hyvae_version", "hyvae_last_error", "hyvae_device_supports_tc", "hyvae_launch_count",
+                                       "hyvae_groupnorm_workspace_bytes", "hyvae_profile_begin", "hyvae_profile_end"])
 
 _lib = None
 
@@ -67,6 +68,8 @@ def lib():
         l.hyvae_last_error.restype = C.c_char_p
         l.hyvae_device_supports_tc.restype = C.c_int
         l.hyvae_launch_count.restype = C.c_int64
+        l.hyvae_groupnorm_workspace_bytes.restype = C.c_int64
+        l.hyvae_groupnorm_workspace_bytes.argtypes = [_VP, _i32]
         _lib = l
     return _lib
 
@@ -78,6 +81,23 @@ def _check(status: int, what: str):
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+PROFILE_CLASSES = ("conv_tc", "conv_direct", "gn_stats", "gn_apply", "pad_upsample", "softmax", "layout", "blend", "temporal")
+
+
+def profile_begin():
+    _check(lib().hyvae_profile_begin(), "profile_begin")
+
+
+def profile_end() -> dict:
+    """{class: {"ms", "work" (flops or bytes, algorithmic), "launches"}} for the bracketed region."""
+    n = len(PROFILE_CLASSES)
+    ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
+    fn = lib().hyvae_profile_end
+    fn.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]
+    _check(fn(ms, work, cnt, n), "profile_end")
+    return {k: {"ms": ms[i], "work": work[i], "launches": int(cnt[i])} for i, k in enumerate(PROFILE_CLASSES)}
 
 
 def launch_count() -> int:
@@ -184,7 +204,11 @@ def conv3d_tc(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, residual
 def groupnorm(x: Vol, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
               pad=(0, 0, 0), round_like_ref=True) -> Vol:
     sums = torch.empty((x.B, groups, 2), dtype=torch.float64, device=x.device)
-    _check(lib().hyvae_groupnorm_stats(x.ref(), groups, sums.data_ptr(), _stream()), "groupnorm_stats")
+    nbytes = lib().hyvae_groupnorm_workspace_bytes(x.ref(), groups)
+    if nbytes < 0:
+        raise HyvaeError(f"GroupNorm: unsupported channel count C={x.C} (needs C % 8 == 0)")
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+    _check(lib().hyvae_groupnorm_stats(x.ref(), groups, sums.data_ptr(), ws.data_ptr(), nbytes, _stream()), "groupnorm_stats")
     y = x.like(pad=pad)
     _check(lib().hyvae_groupnorm_apply(x.ref(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), groups, eps, int(silu),
                                        int(round_like_ref), y.ref(), _stream()), "groupnorm_apply")

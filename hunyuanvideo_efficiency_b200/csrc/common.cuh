@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <vector>
 
 #include "../../include/hyvae.h"
 
@@ -36,6 +37,28 @@ inline int check_launch(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return HYVAE_OK;
 }
+
+// ---- optional per-kernel-class timing (CUDA events on the launching stream; bench.py's roofline leg) ----
+enum ProfClass { PC_CONV_TC = 0, PC_CONV_DIRECT, PC_GN_STATS, PC_GN_APPLY, PC_PAD_UPSAMPLE, PC_SOFTMAX, PC_LAYOUT, PC_BLEND,
+                 PC_TEMPORAL, PC_COUNT };
+struct ProfRec { cudaEvent_t a, b; int cls; double work; };
+extern bool g_prof_on;
+extern std::vector<ProfRec> g_prof;
+extern std::vector<cudaEvent_t> g_prof_pool;
+inline cudaEvent_t prof_event() {
+  cudaEvent_t e;
+  if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); }
+  else cudaEventCreate(&e);
+  return e;
+}
+// RAII: brackets the launches of one C-ABI call with two events.  `work` = algorithmic flops or bytes.
+struct ProfScope {
+  bool on; cudaStream_t st; ProfRec r;
+  ProfScope(int cls, double work, void* stream) : on(g_prof_on), st((cudaStream_t)stream) {
+    if (on) { r.cls = cls; r.work = work; r.a = prof_event(); r.b = prof_event(); cudaEventRecord(r.a, st); }
+  }
+  ~ProfScope() { if (on) { cudaEventRecord(r.b, st); g_prof.push_back(r); } }
+};
 
 inline size_t dtype_size(int dt) { return dt == HYVAE_F32 ? 4 : 2; }
 

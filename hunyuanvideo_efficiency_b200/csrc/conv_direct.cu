@@ -177,6 +177,7 @@ extern "C" int hyvae_conv3d_causal_direct(const hyvae_vol* x, const void* w, con
   a.w = w; a.bias = bias; a.k = k; a.st = st; a.sh = sh; a.sw = sw; a.up_t = up_t; a.up_h = up_h; a.up_w = up_w;
   a.Cin = x->C; a.Cout = y->C; a.M = (int64_t)y->B * y->T * y->H * y->W; a.round_like_ref = round_like_ref;
   dim3 grid((unsigned)((a.M + DM - 1) / DM), (unsigned)((a.Cout + DN - 1) / DN));
+  ProfScope prof(PC_CONV_DIRECT, 2.0 * a.M * a.Cout * a.Cin * k * k * k, stream);
   const bool vec = (a.Cin % 4 == 0);
   const bool f32out = (y->dtype == HYVAE_F32);
   HYVAE_DISPATCH_DTYPE(x->dtype, T, {

@@ -135,34 +135,52 @@ struct TcArgs {
   int B, To, Ho, Wo, Cin, Cout;
   int k, st, sh, sw;
   int TH, TW, tiles_h, tiles_w, n_tiles;
-  int64_t total_tiles;
+  int64_t m_tiles;      // B * To * tiles_h * tiles_w
+  int64_t total_tiles;  // ceil(m_tiles / MT) * n_tiles
   int round_like_ref;
 };
 
 constexpr int TC_THREADS = 192;
 constexpr int A_STAGE_BYTES = 128 * 64 * 2;
 
-template <int BN> struct TcCfg {
+// MT = number of 128-voxel m-tiles a CTA multiplies against one B (weight) tile per stage.  MT = 2 halves
+// the shared-memory fill per MMA cycle for the narrow-N layers (Cout <= 128).
+template <int BN, int MT> struct TcCfg {
+  static constexpr int A_BYTES = MT * A_STAGE_BYTES;
   static constexpr int B_STAGE_BYTES = BN * 64 * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int ACC_COLS = MT * BN;  // fp32 accumulator columns per pipeline stage
+  static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
 };
 
 template <typename T> struct TcFmt;
 template <> struct TcFmt<__nv_bfloat16> { static constexpr int fmt = 1; };
 template <> struct TcFmt<__half> { static constexpr int fmt = 0; };
 
-template <typename T, typename OT, int BN>
+struct MTile { int b, t, h0, w0; bool valid; };
+__device__ __forceinline__ MTile decode_mtile(const TcArgs& a, int64_t mt) {
+  MTile r;
+  r.valid = mt < a.m_tiles;
+  const int tw = (int)(mt % a.tiles_w); mt /= a.tiles_w;
+  const int th = (int)(mt % a.tiles_h); mt /= a.tiles_h;
+  r.t = (int)(mt % a.To); r.b = (int)(mt / a.To);  // an invalid tile gets b >= B: TMA zero-fills it
+  r.h0 = th * a.TH; r.w0 = tw * a.TW;
+  return r;
+}
+
+template <typename T, typename OT, int BN, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, MT>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
   const uint32_t sA = smem_base;
-  const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t sB = smem_base + STAGES * Cfg::A_BYTES;
   const uint32_t bars = sB + STAGES * Cfg::B_STAGE_BYTES;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
   const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
@@ -196,17 +214,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0; uint32_t phase = 0;
       for (int64_t tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int nt = (int)(tile % a.n_tiles);
-        int64_t mt = tile / a.n_tiles;
-        const int tw = (int)(mt % a.tiles_w); mt /= a.tiles_w;
-        const int th = (int)(mt % a.tiles_h); mt /= a.tiles_h;
-        const int t = (int)(mt % a.To); const int b = (int)(mt / a.To);
-        const int w0 = tw * a.TW * a.sw, h0 = th * a.TH * a.sh, t0 = t * a.st, n0 = nt * BN;
+        const int64_t mg = tile / a.n_tiles;
+        const int n0 = nt * BN;
+        MTile m[MT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) m[i] = decode_mtile(a, mg * MT + i);
         for (int tap = 0; tap < taps; ++tap) {
           const int kt = tap / (a.k * a.k), kh = (tap / a.k) % a.k, kw = tap % a.k;
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(empty_bar + 8 * stage, phase ^ 1);
             mbar_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
-            tma_load_5d(sA + stage * A_STAGE_BYTES, &tmA, full_bar + 8 * stage, kc * 64, w0 + kw, h0 + kh, t0 + kt, b);
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+              tma_load_5d(sA + stage * Cfg::A_BYTES + i * A_STAGE_BYTES, &tmA, full_bar + 8 * stage, kc * 64,
+                          m[i].w0 * a.sw + kw, m[i].h0 * a.sh + kh, m[i].t * a.st + kt, m[i].b);
             tma_load_3d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, full_bar + 8 * stage, kc * 64, n0, tap);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -224,15 +245,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t acc_phase = (iter >> 1) & 1;
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
-          const uint64_t adesc = make_kmajor_sw128_desc(sA + stage * A_STAGE_BYTES);
           const uint64_t bdesc = make_kmajor_sw128_desc(sB + stage * Cfg::B_STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x (K = 16) per 64-channel chunk: +32 B along K inside the swizzle atom
-            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          for (int i = 0; i < MT; ++i) {
+            const uint64_t adesc = make_kmajor_sw128_desc(sA + stage * Cfg::A_BYTES + i * A_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // 4 x (K = 16) per 64-channel chunk: +32 B along K inside the swizzle atom
+              umma_f16(d_tmem + i * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
           umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -250,45 +274,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       const int nt = (int)(tile % a.n_tiles);
-      int64_t mt = tile / a.n_tiles;
-      const int tw = (int)(mt % a.tiles_w); mt /= a.tiles_w;
-      const int th = (int)(mt % a.tiles_h); mt /= a.tiles_h;
-      const int t = (int)(mt % a.To); const int b = (int)(mt / a.To);
-      const int h = th * a.TH + row / a.TW, w = tw * a.TW + row % a.TW;
-      const bool valid = (h < a.Ho) && (w < a.Wo);
+      const int64_t mg = tile / a.n_tiles;
       const int n0 = nt * BN;
-      const int64_t yo = a.yoff + (int64_t)b * a.ysB + (int64_t)t * a.ysT + (int64_t)h * a.ysH + (int64_t)w * a.ysW;
-      const int64_t ro = a.roff + (int64_t)b * a.rsB + (int64_t)t * a.rsT + (int64_t)h * a.rsH + (int64_t)w * a.rsW;
-
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + j * 32), v);
-        tmem_ld_wait();
-        if (valid) {
+      for (int i = 0; i < MT; ++i) {
+        const MTile m = decode_mtile(a, mg * MT + i);
+        if (!m.valid) continue;  // warp-uniform
+        const int h = m.h0 + row / a.TW, w = m.w0 + row % a.TW;
+        const bool valid = (h < a.Ho) && (w < a.Wo);
+        const int64_t yo = a.yoff + (int64_t)m.b * a.ysB + (int64_t)m.t * a.ysT + (int64_t)h * a.ysH + (int64_t)w * a.ysW;
+        const int64_t ro = a.roff + (int64_t)m.b * a.rsB + (int64_t)m.t * a.rsT + (int64_t)h * a.rsH + (int64_t)w * a.rsW;
+#pragma unroll 1
+        for (int j = 0; j < BN / 32; ++j) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS + i * BN + j * 32), v);
+          tmem_ld_wait();
+          if (valid) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n0 + j * 32 + g * 8;
-            if (n < a.Cout) {
-              float f[8];
+            for (int g = 0; g < 4; ++g) {
+              const int n = n0 + j * 32 + g * 8;
+              if (n < a.Cout) {
+                float f[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[g * 8 + i]);
-              if (a.bias) {
-                const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n);
-                const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n + 4);
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
+                if (a.bias) {
+                  const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n);
+                  const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n + 4);
+                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                }
+                if (rs) {
+                  Vec8<T> r; r.load(rs + ro + n);
+                  float rf[8]; r.get(rf);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) f[e] = (a.round_like_ref ? rnd<T>(f[e]) : f[e]) + rf[e];
+                }
+                Vec8<OT> o; o.set(f);
+                o.store(yd + yo + n);
               }
-              if (rs) {
-                Vec8<T> r; r.load(rs + ro + n);
-                float rf[8]; r.get(rf);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = (a.round_like_ref ? rnd<T>(f[i]) : f[i]) + rf[i];
-              }
-              Vec8<OT> o; o.set(f);
-              o.store(yd + yo + n);
             }
           }
         }
@@ -322,17 +347,17 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <typename T, typename OT, int BN>
+template <typename T, typename OT, int BN, int MT>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<T, OT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_tc_kernel<T, OT, BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
       return fail(HYVAE_ECUDA, "conv_tc: cannot opt in to %d bytes of shared memory", Cfg::SMEM_BYTES);
     attr_set = true;
   }
   int64_t grid = a.total_tiles < num_sms() ? a.total_tiles : num_sms();
-  conv_tc_kernel<T, OT, BN><<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, a);
+  conv_tc_kernel<T, OT, BN, MT><<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, a);
   return check_launch("conv3d_causal_tc");
 }
 
@@ -355,7 +380,6 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
   HYVAE_CHECK_ARG(st >= 1 && sh >= 1 && sw >= 1 && sh <= 2 && sw <= 2, "stride (%d,%d,%d) not supported by the tensor-core path", st, sh, sw);
   HYVAE_CHECK_ARG(y->T == (x->T - 1) / st + 1 && y->H == (x->H - 1) / sh + 1 && y->W == (x->W - 1) / sw + 1, "y dims do not match the conv output");
   HYVAE_CHECK_ARG(((uintptr_t)x->data & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)y->data & 15) == 0, "pointers must be 16-byte aligned");
-  (void)variant;
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
 
@@ -387,7 +411,10 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
   a.tiles_h = (y->H + a.TH - 1) / a.TH; a.tiles_w = (y->W + a.TW - 1) / a.TW;
   const int BN = y->C > 128 ? 256 : (y->C > 64 ? 128 : (y->C > 32 ? 64 : 32));
   a.n_tiles = (y->C + BN - 1) / BN;
-  a.total_tiles = (int64_t)y->B * y->T * a.tiles_h * a.tiles_w * a.n_tiles;
+  a.m_tiles = (int64_t)y->B * y->T * a.tiles_h * a.tiles_w;
+  // two m-tiles per CTA tile for the narrow-N layers once there is enough work to fill the chip (variant 1 forces MT=1)
+  const int MT = (BN <= 128 && a.m_tiles >= 2 * (int64_t)num_sms() && variant != 1) ? 2 : 1;
+  a.total_tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;
 
   const CUtensorMapDataType dt = x->dtype == HYVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap tmA, tmB;
@@ -410,12 +437,13 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
     if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(B) failed with %d", (int)r);
   }
   cudaStream_t s = (cudaStream_t)stream;
-#define HYVAE_TC_LAUNCH(T, OT)                                    \
-  switch (BN) {                                                   \
-    case 256: return launch_tc<T, OT, 256>(tmA, tmB, a, s);       \
-    case 128: return launch_tc<T, OT, 128>(tmA, tmB, a, s);       \
-    case 64: return launch_tc<T, OT, 64>(tmA, tmB, a, s);         \
-    default: return launch_tc<T, OT, 32>(tmA, tmB, a, s);         \
+  ProfScope prof(PC_CONV_TC, 2.0 * (double)y->B * y->T * y->H * y->W * y->C * x->C * k * k * k, stream);
+#define HYVAE_TC_LAUNCH(T, OT)                                                                              \
+  switch (BN) {                                                                                             \
+    case 256: return launch_tc<T, OT, 256, 1>(tmA, tmB, a, s);                                              \
+    case 128: return MT == 2 ? launch_tc<T, OT, 128, 2>(tmA, tmB, a, s) : launch_tc<T, OT, 128, 1>(tmA, tmB, a, s); \
+    case 64: return MT == 2 ? launch_tc<T, OT, 64, 2>(tmA, tmB, a, s) : launch_tc<T, OT, 64, 1>(tmA, tmB, a, s);    \
+    default: return MT == 2 ? launch_tc<T, OT, 32, 2>(tmA, tmB, a, s) : launch_tc<T, OT, 32, 1>(tmA, tmB, a, s);    \
   }
   const bool f32out = (y->dtype == HYVAE_F32);
   if (x->dtype == HYVAE_BF16) {

@@ -9,6 +9,9 @@ namespace hyvae {
 
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_prof_pool;
 
 static inline int grid_for(int64_t n, int block, int cap_mult = 32) {
   int64_t g = (n + block - 1) / block;
@@ -58,21 +61,22 @@ __global__ void vol_to_ncthw_kernel(Vol s, D* __restrict__ dst) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm statistics: per (b, group) sum and sum of squares.
+// GroupNorm statistics: per (b, group) sum and sum of squares, bit-reproducible run to run.
 // grid = (chunks, B); a thread owns one 8-channel vector position and strides over voxels, so its 16
-// partial sums stay in registers; block partials go through shared memory, then one fp64 atomic per
-// (group, moment) per block.
+// partial sums stay in registers; the block combines them through shared memory in a FIXED order
+// (no floating-point atomics), writes one fp64 partial per (group, moment), and the last block to
+// finish (atomic ticket) adds the partials in block order into `sums`.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void gn_stats_kernel(Vol x, int groups, int vox_per_block, double* __restrict__ sums) {
-  extern __shared__ float sh[];  // [2][C]
+__global__ void gn_stats_kernel(Vol x, int groups, int vox_per_block, double* __restrict__ partials,
+                                unsigned int* __restrict__ tickets, double* __restrict__ sums) {
+  extern __shared__ float sh[];  // [lanes][2*C]
+  __shared__ bool is_last;
   const int C = x.C, CV = C / 8;
-  const int b = blockIdx.y;
+  const int b = blockIdx.y, nblk = gridDim.x;
   const int64_t nvox = (int64_t)x.T * x.H * x.W;
   const int64_t v0 = (int64_t)blockIdx.x * vox_per_block;
   const int64_t v1 = min(v0 + vox_per_block, nvox);
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
   const int lanes = blockDim.x / CV;
   const int cv = threadIdx.x % CV, vl = threadIdx.x / CV;
   if (vl < lanes) {
@@ -93,16 +97,39 @@ __global__ void gn_stats_kernel(Vol x, int groups, int vox_per_block, double* __
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
     }
+    float* row = sh + (size_t)vl * 2 * C;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { atomicAdd(&sh[cv * 8 + j], s[j]); atomicAdd(&sh[C + cv * 8 + j], ss[j]); }
+    for (int j = 0; j < 8; ++j) { row[cv * 8 + j] = s[j]; row[C + cv * 8 + j] = ss[j]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {  // fixed-order sum over voxel lanes
+    float a = 0.f;
+    for (int l = 0; l < lanes; ++l) a += sh[(size_t)l * 2 * C + c];
+    sh[c] = a;  // lane-0 slot of this column: only this thread touches column c
   }
   __syncthreads();
   const int cpg = C / groups;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     double a = 0.0, q = 0.0;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += (double)sh[c]; q += (double)sh[C + c]; }
-    atomicAdd(&sums[((int64_t)b * groups + g) * 2 + 0], a);
-    atomicAdd(&sums[((int64_t)b * groups + g) * 2 + 1], q);
+    double* p = partials + (((int64_t)b * nblk + blockIdx.x) * groups + g) * 2;
+    p[0] = a; p[1] = q;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(&tickets[b], 1u) == (unsigned)(nblk - 1));
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      double a = 0.0, q = 0.0;
+      for (int k = 0; k < nblk; ++k) {
+        const volatile double* p = partials + (((int64_t)b * nblk + k) * groups + g) * 2;
+        a += p[0]; q += p[1];
+      }
+      sums[((int64_t)b * groups + g) * 2 + 0] = a;
+      sums[((int64_t)b * groups + g) * 2 + 1] = q;
+    }
   }
 }
 
@@ -298,6 +325,28 @@ int hyvae_version(void) { return HYVAE_VERSION; }
 const char* hyvae_last_error(void) { return g_err; }
 int64_t hyvae_launch_count(void) { return g_launches.load(); }
 
+int hyvae_profile_begin(void) {
+  for (auto& r : g_prof) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+  g_prof.clear();
+  g_prof_on = true;
+  return HYVAE_OK;
+}
+
+int hyvae_profile_end(double* ms, double* work, int64_t* launches, int32_t n_classes) {
+  g_prof_on = false;
+  HYVAE_CHECK_ARG(ms && work && launches && n_classes >= PC_COUNT, "profile_end needs %d classes", (int)PC_COUNT);
+  for (int i = 0; i < n_classes; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }
+  if (!g_prof.empty() && cudaEventSynchronize(g_prof.back().b) != cudaSuccess) return fail(HYVAE_ECUDA, "profile: event sync failed");
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return fail(HYVAE_ECUDA, "profile: elapsed time failed");
+    ms[r.cls] += t; work[r.cls] += r.work; launches[r.cls] += 1;
+    g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+  }
+  g_prof.clear();
+  return HYVAE_OK;
+}
+
 int hyvae_device_supports_tc(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -310,6 +359,7 @@ int hyvae_ncthw_to_vol(const void* src, int32_t src_dtype, const int64_t* ss, co
   HYVAE_CHECK_ARG(src != nullptr && ss != nullptr, "src is null");
   Vol d = make_vol(dst);
   int64_t n = (int64_t)d.B * d.Tp() * d.Hp() * d.Wp();
+  ProfScope prof(PC_LAYOUT, (double)n * d.C * (dtype_size(src_dtype) + dtype_size(dst->dtype)), stream);
   HYVAE_DISPATCH_DTYPE(src_dtype, S, HYVAE_DISPATCH_DTYPE(dst->dtype, D,
       (ncthw_to_vol_kernel<S, D><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const S*)src, d, ss[0], ss[1], ss[2], ss[3], ss[4]))));
   return check_launch("ncthw_to_vol");
@@ -320,28 +370,49 @@ int hyvae_vol_to_ncthw(const hyvae_vol* src, void* dst, int32_t dst_dtype, void*
   HYVAE_CHECK_ARG(dst != nullptr, "dst is null");
   Vol s = make_vol(src);
   int64_t n = (int64_t)s.B * s.T * s.H * s.W;
+  ProfScope prof(PC_LAYOUT, (double)n * s.C * (dtype_size(src->dtype) + dtype_size(dst_dtype)), stream);
   HYVAE_DISPATCH_DTYPE(src->dtype, S, HYVAE_DISPATCH_DTYPE(dst_dtype, D,
       (vol_to_ncthw_kernel<S, D><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s, (D*)dst))));
   return check_launch("vol_to_ncthw");
 }
 
-int hyvae_groupnorm_stats(const hyvae_vol* x, int32_t groups, double* sums, void* stream) {
-  if (int e = check_vol(x, "x")) return e;
-  HYVAE_CHECK_ARG(sums != nullptr, "sums is null");
-  HYVAE_CHECK_ARG(groups > 0 && x->C % groups == 0, "C=%d not divisible by groups=%d", x->C, groups);
-  HYVAE_CHECK_ARG(x->C % 8 == 0 && x->C / 8 <= 256, "GroupNorm needs C%%8==0 and C<=2048 (C=%d)", x->C);
-  Vol v = make_vol(x);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups * x->B, st) != cudaSuccess)
-    return fail(HYVAE_ECUDA, "memset sums failed");
+static void gn_stats_plan(const hyvae_vol* x, int* vpb_out, int* nblk_out) {
   const int block = 256, lanes = block / (x->C / 8);
   const int64_t nvox = (int64_t)x->T * x->H * x->W;
   int vpb = lanes * 64;
   // keep at least ~4 blocks per SM when the tensor is large enough
   while (vpb > lanes * 8 && (nvox + vpb - 1) / vpb * x->B < 4 * num_sms()) vpb >>= 1;
-  dim3 grid((unsigned)((nvox + vpb - 1) / vpb), (unsigned)x->B);
-  size_t smem = sizeof(float) * 2 * x->C;
-  HYVAE_DISPATCH_DTYPE(x->dtype, T, (gn_stats_kernel<T><<<grid, block, smem, st>>>(v, groups, vpb, sums)));
+  *vpb_out = vpb;
+  *nblk_out = (int)((nvox + vpb - 1) / vpb);
+}
+
+int64_t hyvae_groupnorm_workspace_bytes(const hyvae_vol* x, int32_t groups) {
+  if (x == nullptr || x->C % 8 != 0 || x->C / 8 > 256 || groups <= 0) return -1;
+  int vpb, nblk;
+  gn_stats_plan(x, &vpb, &nblk);
+  return 256 + (int64_t)sizeof(double) * 2 * groups * x->B * nblk;
+}
+
+int hyvae_groupnorm_stats(const hyvae_vol* x, int32_t groups, double* sums, void* workspace, int64_t workspace_bytes,
+                          void* stream) {
+  if (int e = check_vol(x, "x")) return e;
+  HYVAE_CHECK_ARG(sums != nullptr && workspace != nullptr, "sums / workspace is null");
+  HYVAE_CHECK_ARG(groups > 0 && x->C % groups == 0, "C=%d not divisible by groups=%d", x->C, groups);
+  HYVAE_CHECK_ARG(x->C % 8 == 0 && x->C / 8 <= 256, "GroupNorm needs C%%8==0 and C<=2048 (C=%d)", x->C);
+  HYVAE_CHECK_ARG(x->B <= 64, "GroupNorm batch %d > 64", x->B);
+  HYVAE_CHECK_ARG(workspace_bytes >= hyvae_groupnorm_workspace_bytes(x, groups), "workspace too small");
+  Vol v = make_vol(x);
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(PC_GN_STATS, (double)x->B * x->T * x->H * x->W * x->C * dtype_size(x->dtype), stream);
+  if (cudaMemsetAsync(workspace, 0, 256, st) != cudaSuccess) return fail(HYVAE_ECUDA, "memset tickets failed");
+  int vpb, nblk;
+  gn_stats_plan(x, &vpb, &nblk);
+  const int block = 256, lanes = block / (x->C / 8);
+  dim3 grid((unsigned)nblk, (unsigned)x->B);
+  size_t smem = sizeof(float) * 2 * x->C * lanes;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(workspace);
+  double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 256);
+  HYVAE_DISPATCH_DTYPE(x->dtype, T, (gn_stats_kernel<T><<<grid, block, smem, st>>>(v, groups, vpb, partials, tickets, sums)));
   return check_launch("groupnorm_stats");
 }
 
@@ -356,6 +427,7 @@ int hyvae_groupnorm_apply(const hyvae_vol* x, const double* sums, const float* g
   HYVAE_CHECK_ARG(groups > 0 && x->C % groups == 0 && x->C % 8 == 0, "bad C=%d / groups=%d", x->C, groups);
   Vol vx = make_vol(x), vy = make_vol(y);
   int64_t total = (int64_t)vy.Tp() * vy.Hp() * vy.Wp() * (x->C / 8);
+  ProfScope prof(PC_GN_APPLY, 2.0 * x->B * x->T * x->H * x->W * x->C * dtype_size(x->dtype), stream);
   dim3 grid((unsigned)grid_for(total, 256, 16), (unsigned)x->B);
   size_t smem = sizeof(float) * 2 * x->C;
   HYVAE_DISPATCH_DTYPE(x->dtype, T, (gn_apply_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
@@ -372,6 +444,7 @@ int hyvae_pad_upsample(const hyvae_vol* x, const hyvae_vol* y, int32_t up_t, int
   HYVAE_CHECK_ARG(y->T == Te && y->H == x->H * up_h && y->W == x->W * up_w, "y dims %dx%dx%d do not match upsampled x", y->T, y->H, y->W);
   Vol vx = make_vol(x), vy = make_vol(y);
   int64_t nvp = (int64_t)vy.B * vy.Tp() * vy.Hp() * vy.Wp();
+  ProfScope prof(PC_PAD_UPSAMPLE, (double)nvp * x->C * dtype_size(x->dtype) + (double)x->B * x->T * x->H * x->W * x->C * dtype_size(x->dtype), stream);
   if (x->C % 8 == 0) {
     HYVAE_DISPATCH_DTYPE(x->dtype, T, (pad_upsample_kernel<T, 8><<<grid_for(nvp * (x->C / 8), 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, up_t, up_h, up_w)));
   } else {
@@ -383,6 +456,7 @@ int hyvae_pad_upsample(const hyvae_vol* x, const hyvae_vol* y, int32_t up_t, int
 int hyvae_softmax_frame_causal(const float* S, void* P, int32_t p_dtype, int32_t B, int32_t L, int32_t n_hw,
                                float scale, void* stream) {
   HYVAE_CHECK_ARG(S && P && B > 0 && L > 0 && n_hw > 0 && L % n_hw == 0, "bad softmax arguments (L=%d n_hw=%d)", L, n_hw);
+  ProfScope prof(PC_SOFTMAX, (double)B * L * L * (4 + dtype_size(p_dtype)), stream);
   HYVAE_DISPATCH_DTYPE(p_dtype, T, (softmax_frame_causal_kernel<T><<<(unsigned)((int64_t)B * L), 256, 0, (cudaStream_t)stream>>>(
       S, (T*)P, L, n_hw, scale)));
   return check_launch("softmax_frame_causal");
@@ -396,6 +470,7 @@ int hyvae_avgpool_t(const hyvae_vol* x, const hyvae_vol* y, int32_t k, int32_t s
                   "avgpool_t: y shape mismatch");
   Vol vx = make_vol(x), vy = make_vol(y);
   int64_t total = (int64_t)y->B * y->T * y->H * y->W * y->C;
+  ProfScope prof(PC_TEMPORAL, (double)total * dtype_size(x->dtype) * 2, stream);
   HYVAE_DISPATCH_DTYPE(x->dtype, T, (temporal_kernel<T, 0><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, k, s, 0.f)));
   return check_launch("avgpool_t");
 }
@@ -406,6 +481,7 @@ int hyvae_interp_t_nearest(const hyvae_vol* x, const hyvae_vol* y, float inv_sca
   HYVAE_CHECK_ARG(y->H == x->H && y->W == x->W && y->C == x->C && y->B == x->B && x->dtype == y->dtype, "interp_t: y shape mismatch");
   Vol vx = make_vol(x), vy = make_vol(y);
   int64_t total = (int64_t)y->B * y->T * y->H * y->W * y->C;
+  ProfScope prof(PC_TEMPORAL, (double)total * dtype_size(x->dtype) * 2, stream);
   HYVAE_DISPATCH_DTYPE(x->dtype, T, (temporal_kernel<T, 1><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, 0, 0, inv_scale)));
   return check_launch("interp_t_nearest");
 }
@@ -422,6 +498,7 @@ int hyvae_blend_crop_scatter(void* cur, const void* above, const void* left, int
   HYVAE_CHECK_ARG(out == nullptr || (crop_y <= Yc && crop_x <= Xc && y0 + crop_y <= Yo && x0 + crop_x <= Xo && y0 >= 0 && x0 >= 0),
                   "crop window does not fit");
   int64_t total = N * Yc * Xc;
+  ProfScope prof(PC_BLEND, (double)total * dtype_size(dtype) + (out ? (double)N * crop_y * crop_x * dtype_size(dtype) : 0.0), stream);
   HYVAE_DISPATCH_DTYPE(dtype, T, (blend_crop_scatter_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (T*)cur, (const T*)above, (const T*)left, N, Yc, Xc, Ya, Xl, ev, eh, (T*)out, Yo, Xo, y0, x0, crop_y, crop_x,
       cur_ns, above_ns, left_ns, out_ns)));

@@ -104,7 +104,7 @@ class CausalConv3d(nn.Module):
         c = self.conv
         k, stride = c.kernel_size[0], tuple(int(s) for s in c.stride)
         w, b = c.packed(x.dtype)
-        rl = x.dtype in _16BIT
+        rl = False  # one rounding per stored tensor: conv + bias + residual are summed in fp32, then stored
         if tc_eligible(x.dtype, c.in_channels, c.out_channels, stride, k):
             if x.pad != self.halo or up != (1, 1, 1):
                 x = N.pad_upsample(x, up, self.halo)
@@ -133,7 +133,7 @@ class _GroupNorm(nn.Module):
 
     def forward_vol(self, x: Vol, silu: bool, pad=(0, 0, 0)) -> Vol:
         g, b = self._params()
-        return N.groupnorm(x, g, b, self.num_groups, self.eps, silu, pad, x.dtype in _16BIT)
+        return N.groupnorm(x, g, b, self.num_groups, self.eps, silu, pad, False)
 
 
 class UpsampleCausal3D(nn.Module):
@@ -256,7 +256,7 @@ class _Linear(nn.Module):
 def _gemm_nt(x: Vol, w: torch.Tensor, bias, cout: int, residual: Optional[Vol] = None, out_dtype=None,
              out: Optional[Vol] = None) -> Vol:
     """y[m][n] = sum_k x[m][k] * w[n][k] (+bias[n]) (+residual): a 1x1x1 'conv' on either kernel."""
-    rl = x.dtype in _16BIT
+    rl = False
     if tc_eligible(x.dtype, x.C, cout, (1, 1, 1), 1) and x.pad == (0, 0, 0):
         return N.conv3d_tc(x, w, bias, 1, (1, 1, 1), cout, residual, out_dtype, rl, out=out)
     return N.conv3d_direct(x, w, bias, 1, (1, 1, 1), cout, residual, (1, 1, 1), out_dtype, rl, out=out)

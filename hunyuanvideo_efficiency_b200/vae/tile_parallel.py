@@ -1,0 +1,163 @@
+"""One clip across several GPUs: the tiles of AutoencoderKLCausal3D's tiled encode / decode are independent
+sub-model calls (own replicate padding, own GroupNorm statistics, own attention), so they are the unit of
+partitioning (BASELINE config 4).  The reference runs the 720p decode replicated on every rank of
+a torchrun job (pipeline_hunyuan_video.py:1074-1082); here each rank computes a cost-balanced subset of the
+reference's tile grid and the results are exchanged with ONE collective per direction:
+
+  encode: all_gather of the tile moments (1.1 MB each) -> every rank blends the full latent (needed by all)
+  decode: gather of the decoded tiles to rank 0 (<= 1.5 GB over NVLink) -> rank 0 runs the raster-order blend
+
+The blend chain is order dependent, so assembly always happens on complete tile grids, in the reference's order.
+The tile functions / assemblers are injectable so the partition + exchange logic is testable on CPU (gloo).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass(frozen=True)
+class TileSpec:
+    tt: int                      # temporal tile index
+    i: int                       # spatial row
+    j: int                       # spatial column
+    t0: int
+    t1: int
+    h0: int
+    h1: int
+    w0: int
+    w1: int
+
+    @property
+    def cost(self) -> int:
+        return (self.t1 - self.t0) * (self.h1 - self.h0) * (self.w1 - self.w0)
+
+
+def tile_grid(T: int, H: int, W: int, *, temporal: bool, spatial: bool, min_t: int, min_s: int, overlap: float) -> List[TileSpec]:
+    """The reference's tile loops (autoencoder_kl_causal_3d.py:387-396,441-450,483-492,519-528) as data."""
+    if temporal and T > min_t:
+        tr = [(i, min(i + min_t + 1, T)) for i in range(0, T, int(min_t * (1 - overlap)))]
+    else:
+        tr = [(0, T)]
+    specs = []
+    for tt, (t0, t1) in enumerate(tr):
+        if spatial and (H > min_s or W > min_s):
+            s = int(min_s * (1 - overlap))
+            for i, h0 in enumerate(range(0, H, s)):
+                for j, w0 in enumerate(range(0, W, s)):
+                    specs.append(TileSpec(tt, i, j, t0, t1, h0, min(h0 + min_s, H), w0, min(w0 + min_s, W)))
+        else:
+            specs.append(TileSpec(tt, 0, 0, t0, t1, 0, H, 0, W))
+    return specs
+
+
+def lpt_assign(costs: Sequence[int], world: int) -> List[int]:
+    """Longest-processing-time-first: owner rank of every tile; deterministic, identical on all ranks."""
+    load = [0] * world
+    owner = [0] * len(costs)
+    for k in sorted(range(len(costs)), key=lambda k: (-costs[k], k)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        owner[k] = r
+        load[r] += costs[k]
+    return owner
+
+
+class TileParallelVAE:
+    def __init__(self, vae, rank: int, world: int, group=None,
+                 enc_tile: Optional[Callable] = None, dec_tile: Optional[Callable] = None,
+                 assemble_spatial: Optional[Callable] = None, assemble_temporal: Optional[Callable] = None):
+        self.vae, self.rank, self.world, self.group = vae, rank, world, group
+        self.enc_tile = enc_tile or vae._encode_tile
+        self.dec_tile = dec_tile or vae._decode_tile
+        self.assemble_spatial = assemble_spatial or vae._assemble_spatial
+        self.assemble_temporal = assemble_temporal or vae._assemble_temporal
+
+    # ---- exchange ---------------------------------------------------------------------------
+    def _exchange(self, mine: dict, shapes: List[Tuple[int, ...]], owner: List[int], dtype, device, to_all: bool):
+        """mine: {tile index: tensor}.  Returns the list of all tile tensors (on every rank if to_all, else on rank 0)."""
+        numel = [int(torch.Size(s).numel()) for s in shapes]
+        per_rank = [[k for k in range(len(shapes)) if owner[k] == r] for r in range(self.world)]
+        cap = max(sum(numel[k] for k in ks) for ks in per_rank)
+        send = torch.empty(max(cap, 1), dtype=dtype, device=device)
+        off = 0
+        for k in per_rank[self.rank]:
+            send[off:off + numel[k]].copy_(mine[k].reshape(-1))
+            off += numel[k]
+        if to_all:
+            recv = torch.empty(self.world * send.numel(), dtype=dtype, device=device)
+            dist.all_gather_into_tensor(recv, send, group=self.group)
+            bufs = recv.view(self.world, -1)
+        else:
+            lst = [torch.empty_like(send) for _ in range(self.world)] if self.rank == 0 else None
+            dist.gather(send, lst, dst=0, group=self.group)
+            if self.rank != 0:
+                return None
+            bufs = lst
+        tiles: List[Optional[torch.Tensor]] = [None] * len(shapes)
+        for r, ks in enumerate(per_rank):
+            off = 0
+            for k in ks:
+                tiles[k] = mine[k] if r == self.rank else bufs[r][off:off + numel[k]].view(shapes[k])
+                off += numel[k]
+        return tiles
+
+    # ---- one direction ----------------------------------------------------------------------
+    def _run(self, x: torch.Tensor, encode: bool, to_all: bool):
+        v = self.vae
+        B, _, T, H, W = x.shape
+        ov = v.tile_overlap_factor
+        if encode:
+            min_t, min_s, fn = v.tile_sample_min_tsize, v.tile_sample_min_size, self.enc_tile
+            ext_s, lim_s = int(v.tile_latent_min_size * ov), v.tile_latent_min_size - int(v.tile_latent_min_size * ov)
+            ext_t, lim_t = int(v.tile_latent_min_tsize * ov), v.tile_latent_min_tsize - int(v.tile_latent_min_tsize * ov)
+            cout, r_t, r_s = 2 * v.config.latent_channels, v.config.time_compression_ratio, v.config.spatial_compression_ratio
+            oshape = lambda s: (B, cout, (s.t1 - s.t0 - 1) // r_t + 1, -(-(s.h1 - s.h0) // r_s), -(-(s.w1 - s.w0) // r_s))
+        else:
+            min_t, min_s, fn = v.tile_latent_min_tsize, v.tile_latent_min_size, self.dec_tile
+            ext_s, lim_s = int(v.tile_sample_min_size * ov), v.tile_sample_min_size - int(v.tile_sample_min_size * ov)
+            ext_t, lim_t = int(v.tile_sample_min_tsize * ov), v.tile_sample_min_tsize - int(v.tile_sample_min_tsize * ov)
+            cout, r_t, r_s = v.config.out_channels, v.config.time_compression_ratio, v.config.spatial_compression_ratio
+            oshape = lambda s: (B, cout, (s.t1 - s.t0 - 1) * r_t + 1, (s.h1 - s.h0) * r_s, (s.w1 - s.w0) * r_s)
+        specs = tile_grid(T, H, W, temporal=v.use_temporal_tiling, spatial=v.use_spatial_tiling, min_t=min_t, min_s=min_s, overlap=ov)
+        owner = lpt_assign([s.cost for s in specs], self.world)
+        mine = {}
+        for k, s in enumerate(specs):
+            if owner[k] == self.rank:
+                t = fn(x[:, :, s.t0:s.t1, s.h0:s.h1, s.w0:s.w1])
+                assert tuple(t.shape) == oshape(s), (tuple(t.shape), oshape(s))
+                mine[k] = t.contiguous()
+        dtype = next(iter(mine.values())).dtype if mine else getattr(v, "dtype", x.dtype)
+        tiles = self._exchange(mine, [oshape(s) for s in specs], owner, dtype, x.device, to_all)
+        if tiles is None:
+            return None
+        # assemble: spatial grids per temporal tile, then the temporal chain
+        n_tt = max(s.tt for s in specs) + 1
+        row = []
+        for tt in range(n_tt):
+            ks = [k for k, s in enumerate(specs) if s.tt == tt]
+            ni = max(specs[k].i for k in ks) + 1
+            grid = [[None] * (max(specs[k].j for k in ks) + 1) for _ in range(ni)]
+            for k in ks:
+                grid[specs[k].i][specs[k].j] = tiles[k]
+            single = len(ks) == 1 and not (v.use_spatial_tiling and (H > min_s or W > min_s))
+            row.append((grid[0][0] if single else self.assemble_spatial(grid, ext_s, lim_s), 1 if tt > 0 else 0))
+        if n_tt == 1 and not (v.use_temporal_tiling and T > min_t):
+            return row[0][0]
+        return self.assemble_temporal(row, ext_t, lim_t)
+
+    def encode_moments(self, x: torch.Tensor) -> torch.Tensor:
+        """Blended moments of the whole clip, on every rank."""
+        return self._run(x, True, True)
+
+    def decode(self, z: torch.Tensor) -> Optional[torch.Tensor]:
+        """Decoded clip on rank 0 (None elsewhere)."""
+        return self._run(z, False, False)
+
+    def roundtrip(self, x: torch.Tensor) -> Optional[torch.Tensor]:
+        """forward(sample_posterior=False): encode -> mode() -> decode (autoencoder_kl_causal_3d.py:543-578)."""
+        moments = self.encode_moments(x)
+        mean = moments[:, : moments.shape[1] // 2]
+        return self.decode(mean)

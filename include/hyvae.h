@@ -75,9 +75,13 @@ int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const float* bias,
 /* ---- GroupNorm (+SiLU) -------------------------------------------------------------------------
  * Replaces nn.GroupNorm(32,C,eps=1e-6) + SiLU, unet_causal_3d_blocks.py:359-363,401-405 and
  * vae.py:131-133,287-291.  Two launches: statistics (fp32/fp64 accumulation) then apply.
- *   sums: [B][groups][2] float64 workspace (sum, sum of squares); zeroed by _stats.
+ *   sums: [B][groups][2] float64 (sum, sum of squares), written by _stats.
+ *   workspace: hyvae_groupnorm_workspace_bytes() bytes (per-block partials, combined in a fixed order by
+ *   the last block to finish, so the statistics are bit-reproducible; no floating-point atomics).
  *   y may carry a halo: it is filled with the replicated normalised values. */
-int hyvae_groupnorm_stats(const hyvae_vol* x, int32_t groups, double* sums, void* stream);
+int64_t hyvae_groupnorm_workspace_bytes(const hyvae_vol* x, int32_t groups);
+int hyvae_groupnorm_stats(const hyvae_vol* x, int32_t groups, double* sums, void* workspace, int64_t workspace_bytes,
+                          void* stream);
 int hyvae_groupnorm_apply(const hyvae_vol* x, const double* sums, const float* gamma, const float* beta,
                           int32_t groups, float eps, int32_t silu, int32_t round_like_ref, const hyvae_vol* y,
                           void* stream);
@@ -116,6 +120,15 @@ int hyvae_blend_crop_scatter(void* cur, const void* above, const void* left, int
                              int32_t Yc, int32_t Xc, int32_t Ya, int32_t Xl, int32_t ev, int32_t eh,
                              void* out, int32_t Yo, int32_t Xo, int32_t y0, int32_t x0, int32_t crop_y,
                              int32_t crop_x, const int64_t* n_strides, void* stream);
+
+/* ---- measurement hooks (bench.py) ---------------------------------------------------------------
+ * profile_begin/end bracket a region; while on, every C-ABI call is timed with two CUDA events on its
+ * stream.  profile_end synchronises and returns, per kernel class (0 conv_tc, 1 conv_direct, 2 gn_stats,
+ * 3 gn_apply, 4 pad_upsample, 5 softmax, 6 layout, 7 blend, 8 temporal), the summed device milliseconds,
+ * the summed ALGORITHMIC work (flops for convs, bytes for the HBM-bound classes) and the launch count. */
+#define HYVAE_PROFILE_CLASSES 9
+int hyvae_profile_begin(void);
+int hyvae_profile_end(double* ms, double* work, int64_t* launches, int32_t n_classes);
 
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t hyvae_launch_count(void);

@@ -260,13 +260,9 @@ def _dec_tile(sd, cfg, z, t_ops):
     return decoder_forward(sd, cfg, z, t_ops)
 
 
-def _spatial_tiled(fn, x: Tensor, tile: int, stride: int, extent: int, limit: int) -> Tensor:
-    """Shared body of spatial_tiled_encode/decode (:362-420 / :422-469): raster tile grid, then an
-    IN-PLACE raster-order blend chain (v from the already blended tile above, then h from the already
-    blended tile on the left), crop to `limit`, concatenate."""
-    rows = []
-    for i in range(0, x.shape[-2], stride):
-        rows.append([fn(x[:, :, :, i:i + tile, j:j + tile]) for j in range(0, x.shape[-1], stride)])
+def spatial_assemble(rows, extent: int, limit: int) -> Tensor:
+    """Second half of spatial_tiled_encode/decode (:397-412 / :451-465): IN-PLACE raster-order blend chain
+    (v from the already blended tile above, then h from the already blended tile on the left), crop, cat."""
     out_rows = []
     for i, row in enumerate(rows):
         out = []
@@ -278,6 +274,14 @@ def _spatial_tiled(fn, x: Tensor, tile: int, stride: int, extent: int, limit: in
             out.append(t[:, :, :, :limit, :limit])
         out_rows.append(torch.cat(out, dim=-1))
     return torch.cat(out_rows, dim=-2)
+
+
+def _spatial_tiled(fn, x: Tensor, tile: int, stride: int, extent: int, limit: int) -> Tensor:
+    """Shared body of spatial_tiled_encode/decode (:362-420 / :422-469): raster tile grid, then assemble."""
+    rows = []
+    for i in range(0, x.shape[-2], stride):
+        rows.append([fn(x[:, :, :, i:i + tile, j:j + tile]) for j in range(0, x.shape[-1], stride)])
+    return spatial_assemble(rows, extent, limit)
 
 
 def spatial_tiled_encode(sd, cfg, x, tl: Tiling, t_ops=None) -> Tensor:
@@ -296,6 +300,19 @@ def spatial_tiled_decode(sd, cfg, z, tl: Tiling, t_ops=None) -> Tensor:
                           tl.sample_min_size - extent)
 
 
+def temporal_assemble(row, extent: int, limit: int) -> Tensor:
+    """Second half of temporal_tiled_encode/decode (:493-501 / :529-537); `row` holds the tiles with the first
+    frame of tiles i>0 already dropped (:491,527)."""
+    out = []
+    for i, t in enumerate(row):
+        if i > 0:
+            t = blend_t(row[i - 1], t, extent)
+            out.append(t[:, :, :limit])
+        else:
+            out.append(t[:, :, :limit + 1])
+    return torch.cat(out, dim=2)
+
+
 def _temporal_tiled(fn_plain, fn_spatial, x: Tensor, tl: Tiling, tile_t: int, stride: int, extent: int,
                     limit: int, min_size: int) -> Tensor:
     """Shared body of temporal_tiled_encode/decode (:471-508 / :510-541)."""
@@ -309,14 +326,7 @@ def _temporal_tiled(fn_plain, fn_spatial, x: Tensor, tl: Tiling, tile_t: int, st
         if i > 0:
             t = t[:, :, 1:]
         row.append(t)
-    out = []
-    for i, t in enumerate(row):
-        if i > 0:
-            t = blend_t(row[i - 1], t, extent)
-            out.append(t[:, :, :limit])
-        else:
-            out.append(t[:, :, :limit + 1])
-    return torch.cat(out, dim=2)
+    return temporal_assemble(row, extent, limit)
 
 
 def encode_moments(sd, cfg, x: Tensor, tl: Tiling, t_ops=None) -> Tensor:

@@ -233,20 +233,68 @@ def test_model_fp32_vs_reference_golden(name):
     assert O.psnr(a["dec"], dec.cpu()) > 80
 
 
+def _exact_eval_of_16bit_model(meta, dtype):
+    """fp32 oracle evaluated on the SAME parameters and input the 16-bit model holds (weights and video
+    rounded to `dtype`, then exact arithmetic): the value a 16-bit implementation is approximating."""
+    cfg = getattr(W, meta["cfg"])
+    sd = {k: v.to(dtype).float() for k, v in W.make_state_dict(cfg, meta["weight_seed"]).items()}
+    tl = O.Tiling.from_cfg(cfg, meta["spatial"], meta["temporal"])
+    x = W.make_video(tuple(meta["shape"]), meta["video_seed"]).to(dtype).float()
+    mom = O.encode_moments(sd, cfg, x, tl, meta["t_ops"])
+    mean, _ = O.posterior_mean_logvar(mom)
+    zin = mean.to(dtype).float()
+    return mean, zin, O.decode(sd, cfg, zin.clone(), tl, meta["t_ops"])
+
+
 @pytest.mark.parametrize("name", ["small_untiled", "small_tiled", "hy_untiled"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-def test_model_16bit_vs_reference_golden(name, dtype):
+def test_model_16bit_vs_reference(name, dtype):
+    """BASELINE.json tolerances for 16-bit models: latents within 2e-2 relative, decode PSNR >= 45 dB.
+    Checked against (a) the exact evaluation of the same 16-bit parameters and (b) the fp32 golden output of
+    the unmodified reference (which additionally contains the 16-bit weight rounding itself)."""
     meta, a = load_golden(name)
     m = _build(getattr(W, meta["cfg"]), dtype)
     m.enable_spatial_tiling(meta["spatial"])
     m.enable_temporal_tiling(meta["temporal"])
     x = W.make_video(tuple(meta["shape"]), meta["video_seed"]).to(_dev(), dtype)
-    post = m.encode(x).latent_dist
-    mean_ref, _ = O.posterior_mean_logvar(a["moments"])
-    assert O.rel_err(mean_ref, post.mode().float().cpu()) < BF16_TOL
-    dec = m.decode(mean_ref.to(_dev(), dtype)).sample
-    assert O.rel_err(a["dec"], dec.float().cpu()) < BF16_TOL
-    assert O.psnr(a["dec"], dec.float().cpu()) > PSNR_MIN
+    mean_exact, zin, dec_exact = _exact_eval_of_16bit_model(meta, dtype)
+    mean = m.encode(x).latent_dist.mode().float().cpu()
+    dec = m.decode(zin.to(_dev(), dtype)).sample.float().cpu()
+    assert O.rel_err(mean_exact, mean) < BF16_TOL
+    assert O.rel_err(dec_exact, dec) < BF16_TOL and O.psnr(dec_exact, dec) > PSNR_MIN
+    mean_gold, _ = O.posterior_mean_logvar(a["moments"])
+    assert O.rel_err(mean_gold, mean) < BF16_TOL
+    dec_g = m.decode(mean_gold.to(_dev(), dtype)).sample.float().cpu()
+    assert O.rel_err(a["dec"], dec_g) < BF16_TOL and O.psnr(a["dec"], dec_g) > PSNR_MIN
+
+
+def test_pure_bf16_mode_is_no_worse_than_the_reference_in_bf16():
+    """`bf16_compute = "bf16"` keeps every operand in bf16 like the reference.  The reference's own all-bf16 CPU
+    run of this case deviates from its fp32 run by 2.7e-2 (latent) / 7.2e-2 (decode), PSNR 38.0 dB (measured with
+    oracle/_refshim, DESIGN.md "Precision"); the CUDA path must not be worse than that by more than 25 %."""
+    meta, a = load_golden("small_untiled")
+    m = _build(getattr(W, meta["cfg"]), torch.bfloat16)
+    m.bf16_compute = "bf16"
+    x = W.make_video(tuple(meta["shape"]), meta["video_seed"]).to(_dev(), torch.bfloat16)
+    mean_gold, _ = O.posterior_mean_logvar(a["moments"])
+    mean = m.encode(x).latent_dist.mode().float().cpu()
+    dec = m.decode(mean_gold.to(_dev(), torch.bfloat16)).sample.float().cpu()
+    assert O.rel_err(mean_gold, mean) < 1.25 * 2.7e-2
+    assert O.rel_err(a["dec"], dec) < 1.25 * 7.2e-2
+
+
+def test_groupnorm_and_decoder_are_bit_reproducible():
+    N = _N()
+    x = N.Vol(1, 9, 64, 64, 128, torch.bfloat16, _dev())
+    x.t.normal_()
+    g, b = torch.ones(128, device=_dev()), torch.zeros(128, device=_dev())
+    ys = [N.groupnorm(x, g, b, 32, 1e-6, True, pad=(2, 1, 1)).t.clone() for _ in range(4)]
+    assert all(torch.equal(ys[0], y) for y in ys[1:])
+    cfg = dict(W.SMALL_CONFIG, block_out_channels=[64, 128, 256, 256])
+    m = _build(cfg, torch.bfloat16)
+    z = W.make_latent((1, 16, 5, 12, 10)).to(_dev(), torch.bfloat16)
+    outs = [m.decode(z).sample.clone() for _ in range(4)]
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
 
 
 def test_tc_model_path_matches_direct_path_bf16():
