@@ -33,10 +33,11 @@ _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 # name -> argtypes; every entry returns int status (include/hyvae.h)
 _SIGNATURES = {
-    "hyvae_ncthw_to_vol": [_vp, _i32, C.POINTER(_i64), _VP, _vp],
-    "hyvae_vol_to_ncthw": [_VP, _vp, _i32, _vp],
+    "hyvae_ncthw_to_vol": [_vp, _i32, _i32, C.POINTER(_i64), _VP, _vp],
+    "hyvae_vol_to_ncthw": [_VP, _vp, _i32, _i32, _vp],
     "hyvae_conv3d_causal_direct": [_VP, _vp, _vp, _VP, _VP, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
-    "hyvae_conv3d_causal_tc": [_VP, _vp, _vp, _VP, _VP, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "hyvae_conv3d_causal_tc": [_VP, _vp, _vp, _VP, _VP, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
+    "hyvae_groupnorm_finalize": [_vp, _i32, _i64, _i32, _vp, _vp],
     "hyvae_groupnorm_stats": [_VP, _i32, _vp, _vp, _i64, _vp],
     "hyvae_groupnorm_apply": [_VP, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _VP, _vp],
     "hyvae_pad_upsample": [_VP, _VP, _i32, _i32, _i32, _vp],
@@ -47,7 +48,8 @@ _SIGNATURES = {
                                  _i32, _i32, _i32, _i32, C.POINTER(_i64), _vp],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["hyvae_version", "hyvae_last_error", "hyvae_device_supports_tc", "hyvae_launch_count",
-                                       "hyvae_groupnorm_workspace_bytes", "hyvae_profile_begin", "hyvae_profile_end"])
+                                       "hyvae_groupnorm_workspace_bytes", "hyvae_profile_begin", "hyvae_profile_end",
+                                       "hyvae_conv3d_tc_gn_rows"])
 
 _lib = None
 
@@ -70,6 +72,8 @@ def lib():
         l.hyvae_launch_count.restype = C.c_int64
         l.hyvae_groupnorm_workspace_bytes.restype = C.c_int64
         l.hyvae_groupnorm_workspace_bytes.argtypes = [_VP, _i32]
+        l.hyvae_conv3d_tc_gn_rows.restype = C.c_int64
+        l.hyvae_conv3d_tc_gn_rows.argtypes = [_VP, _i32, _i32]
         _lib = l
     return _lib
 
@@ -117,7 +121,7 @@ def device_supports_tc() -> bool:
 class Vol:
     """Channels-last activation volume [B][T+pt][H+2ph][W+2pw][C] in HBM (see hyvae_vol)."""
 
-    __slots__ = ("t", "B", "T", "H", "W", "C", "pad", "_c")
+    __slots__ = ("t", "B", "T", "H", "W", "C", "pad", "_c", "c_valid", "gn_sums", "gn_groups")
 
     def __init__(self, B, T, H, W, Cn, dtype, device, pad: Tuple[int, int, int] = (0, 0, 0), tensor=None):
         pt, ph, pw = pad
@@ -130,6 +134,9 @@ class Vol:
             raise HyvaeError("hyvae volumes live in CUDA memory; there is no CPU execution path")
         self.t, self.B, self.T, self.H, self.W, self.C, self.pad = tensor, B, T, H, W, Cn, tuple(pad)
         self._c = _CVol(tensor.data_ptr(), _DT[tensor.dtype], B, T, H, W, Cn, pt, ph, pw)
+        self.c_valid = Cn        # channels that carry data (C may be zero-padded up to a multiple of 8)
+        self.gn_sums = None      # [B][groups][2] fp64 GroupNorm statistics emitted by the producing conv, if any
+        self.gn_groups = 0
 
     @property
     def dtype(self):
@@ -156,17 +163,19 @@ class Vol:
 
     # ---- NCTHW <-> volume -------------------------------------------------------------------
     @staticmethod
-    def from_ncthw(x: torch.Tensor, dtype=None, pad=(0, 0, 0)) -> "Vol":
+    def from_ncthw(x: torch.Tensor, dtype=None, pad=(0, 0, 0), channels: Optional[int] = None) -> "Vol":
+        """`channels` > x.shape[1] zero-pads the channel axis (3 -> 8 for the tensor-core conv_in)."""
         assert x.ndim == 5
         B, Cn, T, H, W = x.shape
-        v = Vol(B, T, H, W, Cn, dtype or x.dtype, x.device, pad)
+        v = Vol(B, T, H, W, channels or Cn, dtype or x.dtype, x.device, pad)
+        v.c_valid = Cn
         strides = (_i64 * 5)(*x.stride())
-        _check(lib().hyvae_ncthw_to_vol(x.data_ptr(), _DT[x.dtype], strides, v.ref(), _stream()), "ncthw_to_vol")
+        _check(lib().hyvae_ncthw_to_vol(x.data_ptr(), _DT[x.dtype], Cn, strides, v.ref(), _stream()), "ncthw_to_vol")
         return v
 
     def to_ncthw(self, dtype=None) -> torch.Tensor:
-        out = torch.empty((self.B, self.C, self.T, self.H, self.W), dtype=dtype or self.dtype, device=self.device)
-        _check(lib().hyvae_vol_to_ncthw(self.ref(), out.data_ptr(), _DT[out.dtype], _stream()), "vol_to_ncthw")
+        out = torch.empty((self.B, self.c_valid, self.T, self.H, self.W), dtype=dtype or self.dtype, device=self.device)
+        _check(lib().hyvae_vol_to_ncthw(self.ref(), out.data_ptr(), _DT[out.dtype], self.c_valid, _stream()), "vol_to_ncthw")
         return out
 
 
@@ -192,32 +201,47 @@ def conv3d_direct(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, resi
 
 
 def conv3d_tc(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, residual: Optional[Vol] = None,
-              out_dtype=None, round_like_ref=True, variant=0, out: Optional[Vol] = None) -> Vol:
+              out_dtype=None, round_like_ref=True, variant=0, out: Optional[Vol] = None, gn_groups: int = 0) -> Vol:
+    """gn_groups > 0: the epilogue also emits GroupNorm partial statistics of y; they are reduced here
+    (hyvae_groupnorm_finalize) and travel with the returned volume (y.gn_sums), sparing the consumer's stats pass."""
     To, Ho, Wo = conv_out_dims(x.T, x.H, x.W, stride)
     y = out if out is not None else Vol(x.B, To, Ho, Wo, cout, out_dtype or x.dtype, x.device)
+    part, rows = None, 0
+    if gn_groups > 0 and cout % gn_groups == 0 and (cout // gn_groups) in (1, 2, 4, 8, 16, 32):
+        rows = int(lib().hyvae_conv3d_tc_gn_rows(y.ref(), stride[1], stride[2]))
+        part = torch.empty((x.B, rows, gn_groups, 2), dtype=torch.float32, device=x.device)
     _check(lib().hyvae_conv3d_causal_tc(x.ref(), w.data_ptr(), _ptr(bias), residual.ref() if residual else None, y.ref(),
-                                        k, stride[0], stride[1], stride[2], int(round_like_ref), variant, _stream()),
+                                        k, stride[0], stride[1], stride[2], int(round_like_ref), variant,
+                                        _ptr(part), gn_groups if part is not None else 0, _stream()),
            "conv3d_causal_tc")
+    if part is not None:
+        sums = torch.empty((x.B, gn_groups, 2), dtype=torch.float64, device=x.device)
+        _check(lib().hyvae_groupnorm_finalize(part.data_ptr(), x.B, rows, gn_groups, sums.data_ptr(), _stream()), "groupnorm_finalize")
+        y.gn_sums, y.gn_groups = sums, gn_groups
     return y
 
 
 def groupnorm(x: Vol, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
               pad=(0, 0, 0), round_like_ref=True) -> Vol:
-    sums = torch.empty((x.B, groups, 2), dtype=torch.float64, device=x.device)
-    nbytes = lib().hyvae_groupnorm_workspace_bytes(x.ref(), groups)
-    if nbytes < 0:
-        raise HyvaeError(f"GroupNorm: unsupported channel count C={x.C} (needs C % 8 == 0)")
-    ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
-    _check(lib().hyvae_groupnorm_stats(x.ref(), groups, sums.data_ptr(), ws.data_ptr(), nbytes, _stream()), "groupnorm_stats")
+    if x.gn_sums is not None and x.gn_groups == groups:
+        sums = x.gn_sums   # statistics came with the tensor, from the conv epilogue that produced it
+    else:
+        sums = torch.empty((x.B, groups, 2), dtype=torch.float64, device=x.device)
+        nbytes = lib().hyvae_groupnorm_workspace_bytes(x.ref(), groups)
+        if nbytes < 0:
+            raise HyvaeError(f"GroupNorm: unsupported channel count C={x.C} (needs C % 8 == 0)")
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+        _check(lib().hyvae_groupnorm_stats(x.ref(), groups, sums.data_ptr(), ws.data_ptr(), nbytes, _stream()), "groupnorm_stats")
     y = x.like(pad=pad)
     _check(lib().hyvae_groupnorm_apply(x.ref(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), groups, eps, int(silu),
                                        int(round_like_ref), y.ref(), _stream()), "groupnorm_apply")
     return y
 
 
-def pad_upsample(x: Vol, up=(1, 1, 1), pad=(0, 0, 0)) -> Vol:
+def pad_upsample(x: Vol, up=(1, 1, 1), pad=(0, 0, 0), channels: Optional[int] = None) -> Vol:
     T = 1 + 2 * (x.T - 1) if up[0] == 2 else x.T
-    y = Vol(x.B, T, x.H * up[1], x.W * up[2], x.C, x.dtype, x.device, pad)
+    y = Vol(x.B, T, x.H * up[1], x.W * up[2], channels or x.C, x.dtype, x.device, pad)
+    y.c_valid = x.c_valid
     _check(lib().hyvae_pad_upsample(x.ref(), y.ref(), up[0], up[1], up[2], _stream()), "pad_upsample")
     return y
 

@@ -138,6 +138,9 @@ struct TcArgs {
   int64_t m_tiles;      // B * To * tiles_h * tiles_w
   int64_t total_tiles;  // ceil(m_tiles / MT) * n_tiles
   int round_like_ref;
+  float* gn_part;       // optional [B][m_tiles_per_b * 4][gn_groups][2] partial (sum, sum of squares) of the output
+  int gn_groups, gn_cpg;
+  int64_t m_tiles_per_b;
 };
 
 constexpr int TC_THREADS = 192;
@@ -160,6 +163,21 @@ template <int BN, int MT> struct TcCfg {
 template <typename T> struct TcFmt;
 template <> struct TcFmt<__nv_bfloat16> { static constexpr int fmt = 1; };
 template <> struct TcFmt<__half> { static constexpr int fmt = 0; };
+
+// GroupNorm partial statistics of one 32-column chunk of the epilogue: per group of CPG channels, the sum and sum of
+// squares over this warp's 32 rows (fixed shuffle tree -> bit-reproducible); lane 0 writes them.
+template <int CPG>
+__device__ __forceinline__ void gn_chunk_stats(const float* f, bool valid, float* dst, int lane, int ngroups_valid) {
+#pragma unroll
+  for (int g = 0; g < 32 / CPG; ++g) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) { const float u = valid ? f[g * CPG + c] : 0.f; s += u; q = fmaf(u, u, q); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (lane == 0 && g < ngroups_valid) { dst[2 * g] = s; dst[2 * g + 1] = q; }
+  }
+}
 
 struct MTile { int b, t, h0, w0; bool valid; };
 __device__ __forceinline__ MTile decode_mtile(const TcArgs& a, int64_t mt) {
@@ -291,28 +309,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS + i * BN + j * 32), v);
           tmem_ld_wait();
-          if (valid) {
+          float f[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+          const int nc = n0 + j * 32;
+          if (nc < a.Cout) {  // warp-uniform
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const int n = n0 + j * 32 + g * 8;
+              const int n = nc + g * 8;
               if (n < a.Cout) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
                 if (a.bias) {
                   const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n);
                   const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n + 4);
-                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                  f[g * 8 + 0] += b0.x; f[g * 8 + 1] += b0.y; f[g * 8 + 2] += b0.z; f[g * 8 + 3] += b0.w;
+                  f[g * 8 + 4] += b1.x; f[g * 8 + 5] += b1.y; f[g * 8 + 6] += b1.z; f[g * 8 + 7] += b1.w;
                 }
-                if (rs) {
+                if (rs && valid) {
                   Vec8<T> r; r.load(rs + ro + n);
                   float rf[8]; r.get(rf);
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] = (a.round_like_ref ? rnd<T>(f[e]) : f[e]) + rf[e];
+                  for (int e = 0; e < 8; ++e) f[g * 8 + e] = (a.round_like_ref ? rnd<T>(f[g * 8 + e]) : f[g * 8 + e]) + rf[e];
                 }
-                Vec8<OT> o; o.set(f);
-                o.store(yd + yo + n);
+                if (valid) {
+                  Vec8<OT> o; o.set(&f[g * 8]);
+                  o.store(yd + yo + n);
+                }
+              }
+            }
+            if (a.gn_part) {
+              const int64_t prow = (int64_t)m.b * a.m_tiles_per_b * 4 + ((mg * MT + i) - (int64_t)m.b * a.m_tiles_per_b) * 4 + q;
+              float* dst = a.gn_part + (prow * a.gn_groups + nc / a.gn_cpg) * 2;
+              const int ng = (a.Cout - nc) / a.gn_cpg;
+              switch (a.gn_cpg) {
+                case 1: gn_chunk_stats<1>(f, valid, dst, lane, ng); break;
+                case 2: gn_chunk_stats<2>(f, valid, dst, lane, ng); break;
+                case 4: gn_chunk_stats<4>(f, valid, dst, lane, ng); break;
+                case 8: gn_chunk_stats<8>(f, valid, dst, lane, ng); break;
+                case 16: gn_chunk_stats<16>(f, valid, dst, lane, ng); break;
+                default: gn_chunk_stats<32>(f, valid, dst, lane, ng); break;
               }
             }
           }
@@ -365,9 +399,29 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArg
 
 using namespace hyvae;
 
+// tile shape: TH x TW = 128 output voxels of one frame, chosen to minimise padded area
+static void pick_tile(int Ho, int Wo, int sh, int sw, int* TH, int* TW) {
+  int best_tw = 16; int64_t best_area = -1;
+  for (int tw = 8; tw <= 128; tw <<= 1) {
+    int th = 128 / tw;
+    if (tw * sw > 256 || th * sh > 256) continue;
+    int64_t area = (int64_t)((Ho + th - 1) / th) * th * ((Wo + tw - 1) / tw) * tw;
+    if (best_area < 0 || area < best_area || (area == best_area && tw == 16)) { best_area = area; best_tw = tw; }
+  }
+  *TW = best_tw; *TH = 128 / best_tw;
+}
+
+extern "C" int64_t hyvae_conv3d_tc_gn_rows(const hyvae_vol* y, int32_t sh, int32_t sw) {
+  if (y == nullptr) return -1;
+  int TH, TW;
+  pick_tile(y->H, y->W, sh, sw, &TH, &TW);
+  return (int64_t)y->T * ((y->H + TH - 1) / TH) * ((y->W + TW - 1) / TW) * 4;
+}
+
 extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
                                       const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
-                                      int32_t round_like_ref, int32_t variant, void* stream) {
+                                      int32_t round_like_ref, int32_t variant, float* gn_partials, int32_t gn_groups,
+                                      void* stream) {
   if (int e = check_vol(x, "x")) return e;
   if (int e = check_vol(y, "y")) return e;
   HYVAE_CHECK_ARG(w != nullptr, "w is null");
@@ -399,19 +453,18 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
   a.B = y->B; a.To = y->T; a.Ho = y->H; a.Wo = y->W; a.Cin = x->C; a.Cout = y->C;
   a.k = k; a.st = st; a.sh = sh; a.sw = sw; a.round_like_ref = round_like_ref;
 
-  // tile shape: TH x TW = 128 output voxels of one frame, chosen to minimise padded area
-  int best_tw = 16; int64_t best_area = -1;
-  for (int tw = 8; tw <= 128; tw <<= 1) {
-    int th = 128 / tw;
-    if (tw * sw > 256 || th * sh > 256) continue;
-    int64_t area = (int64_t)((y->H + th - 1) / th) * th * ((y->W + tw - 1) / tw) * tw;
-    if (best_area < 0 || area < best_area || (area == best_area && tw == 16)) { best_area = area; best_tw = tw; }
-  }
-  a.TW = best_tw; a.TH = 128 / best_tw;
+  pick_tile(y->H, y->W, sh, sw, &a.TH, &a.TW);
   a.tiles_h = (y->H + a.TH - 1) / a.TH; a.tiles_w = (y->W + a.TW - 1) / a.TW;
   const int BN = y->C > 128 ? 256 : (y->C > 64 ? 128 : (y->C > 32 ? 64 : 32));
   a.n_tiles = (y->C + BN - 1) / BN;
   a.m_tiles = (int64_t)y->B * y->T * a.tiles_h * a.tiles_w;
+  a.m_tiles_per_b = (int64_t)y->T * a.tiles_h * a.tiles_w;
+  a.gn_part = gn_partials; a.gn_groups = gn_groups; a.gn_cpg = 0;
+  if (gn_partials) {
+    HYVAE_CHECK_ARG(gn_groups > 0 && y->C % gn_groups == 0, "gn_groups=%d does not divide Cout=%d", gn_groups, y->C);
+    a.gn_cpg = y->C / gn_groups;
+    HYVAE_CHECK_ARG(a.gn_cpg <= 32 && (a.gn_cpg & (a.gn_cpg - 1)) == 0, "fused GroupNorm statistics need Cout/groups in {1,2,4,8,16,32} (got %d)", a.gn_cpg);
+  }
   // two m-tiles per CTA tile for the narrow-N layers once there is enough work to fill the chip (variant 1 forces MT=1)
   const int MT = (BN <= 128 && a.m_tiles >= 2 * (int64_t)num_sms() && variant != 1) ? 2 : 1;
   a.total_tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;

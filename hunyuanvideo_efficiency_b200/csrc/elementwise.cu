@@ -25,7 +25,7 @@ static inline int grid_for(int64_t n, int block, int cap_mult = 32) {
 // NCTHW <-> channels-last volume
 // ------------------------------------------------------------------------------------------------
 template <typename S, typename D>
-__global__ void ncthw_to_vol_kernel(const S* __restrict__ src, Vol d, int64_t sb, int64_t sc, int64_t st, int64_t sh, int64_t sw) {
+__global__ void ncthw_to_vol_kernel(const S* __restrict__ src, Vol d, int src_C, int64_t sb, int64_t sc, int64_t st, int64_t sh, int64_t sw) {
   const int64_t nvox = (int64_t)d.B * d.Tp() * d.Hp() * d.Wp();
   D* dst = reinterpret_cast<D*>(d.p);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvox; i += (int64_t)gridDim.x * blockDim.x) {
@@ -39,12 +39,12 @@ __global__ void ncthw_to_vol_kernel(const S* __restrict__ src, Vol d, int64_t sb
     int w = min(max(wp - d.pw, 0), d.W - 1);
     const S* s = src + b * sb + t * st + h * sh + w * sw;
     D* o = dst + i * d.C;
-    for (int c = 0; c < d.C; ++c) o[c] = from_f<D>(to_f<S>(s[c * sc]));
+    for (int c = 0; c < d.C; ++c) o[c] = c < src_C ? from_f<D>(to_f<S>(s[c * sc])) : from_f<D>(0.f);  // zero channel padding
   }
 }
 
 template <typename S, typename D>
-__global__ void vol_to_ncthw_kernel(Vol s, D* __restrict__ dst) {
+__global__ void vol_to_ncthw_kernel(Vol s, D* __restrict__ dst, int dst_C) {
   const int64_t thw = (int64_t)s.T * s.H * s.W;
   const int64_t nvox = (int64_t)s.B * thw;
   const S* src = reinterpret_cast<const S*>(s.p);
@@ -55,8 +55,8 @@ __global__ void vol_to_ncthw_kernel(Vol s, D* __restrict__ dst) {
     int t = (int)(r % s.T);
     int b = (int)(r / s.T);
     const S* p = src + s.at(b, t, h, w);
-    D* o = dst + (int64_t)b * s.C * thw + ((int64_t)t * s.H + h) * s.W + w;
-    for (int c = 0; c < s.C; ++c) o[c * thw] = from_f<D>(to_f<S>(p[c]));
+    D* o = dst + (int64_t)b * dst_C * thw + ((int64_t)t * s.H + h) * s.W + w;
+    for (int c = 0; c < dst_C; ++c) o[c * thw] = from_f<D>(to_f<S>(p[c]));
   }
 }
 
@@ -133,10 +133,16 @@ __global__ void gn_stats_kernel(Vol x, int groups, int vox_per_block, double* __
   }
 }
 
-// GroupNorm apply (+SiLU) into a possibly padded destination.  grid = (chunks, B).
+// GroupNorm apply (+SiLU) into a possibly padded destination.  grid = (row chunks, B).
+// A block walks destination rows (tp, hp): Wp*C contiguous elements each, read from the clamped source row,
+// so the inner loop is a coalesced 16-byte stream with 32-bit index math only.
+template <typename T> struct FastMath { static constexpr bool value = true; };
+template <> struct FastMath<float> { static constexpr bool value = false; };
+
 template <typename T>
-__global__ void gn_apply_kernel(Vol x, Vol y, const double* __restrict__ sums, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, int groups, float eps, int silu, int round_like_ref) {
+__global__ void __launch_bounds__(256) gn_apply_kernel(Vol x, Vol y, const double* __restrict__ sums, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int groups, float eps, int silu, int round_like_ref,
+                                int rows_per_block) {
   extern __shared__ float sh[];  // scale[C], shift[C]
   const int C = x.C, CV = C / 8, b = blockIdx.y;
   const int cpg = C / groups;
@@ -152,30 +158,64 @@ __global__ void gn_apply_kernel(Vol x, Vol y, const double* __restrict__ sums, c
     sh[C + c] = beta[c] - (float)mean * sc;
   }
   __syncthreads();
-  const int64_t nvp = (int64_t)y.Tp() * y.Hp() * y.Wp();
-  const int64_t total = nvp * CV;
+  const int Wp = y.Wp(), Hp = y.Hp();
+  const int nrows = y.Tp() * Hp;
+  const int row_elems = Wp * CV;  // 8-channel vectors per destination row
   const T* xs = reinterpret_cast<const T*>(x.p);
   T* yd = reinterpret_cast<T*>(y.p) + (int64_t)b * y.sB;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(i % CV);
-    int64_t v = i / CV;
-    int wp = (int)(v % y.Wp()); int64_t r = v / y.Wp();
-    int hp = (int)(r % y.Hp()); int tp = (int)(r / y.Hp());
-    int t = max(tp - y.pt, 0);
-    int h = min(max(hp - y.ph, 0), y.H - 1);
-    int w = min(max(wp - y.pw, 0), y.W - 1);
-    Vec8<T> q; q.load(xs + x.at(b, t, h, w) + cv * 8);
-    float f[8]; q.get(f);
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, nrows);
+  const bool pow2 = (CV & (CV - 1)) == 0;
+  const int shift = 31 - __clz(CV);
+  for (int r = r0; r < r1; ++r) {
+    const int tp = r / Hp, hp = r - tp * Hp;
+    const int t = max(tp - y.pt, 0), h = min(max(hp - y.ph, 0), y.H - 1);
+    const T* srow = xs + x.at(b, t, h, 0);
+    T* drow = yd + (int64_t)r * Wp * C;
+    for (int i = threadIdx.x; i < row_elems; i += blockDim.x) {
+      const int wp = pow2 ? (i >> shift) : (i / CV);
+      const int cv = i - wp * CV;
+      const int w = min(max(wp - y.pw, 0), y.W - 1);
+      Vec8<T> q; q.load(srow + (int64_t)w * x.sW + cv * 8);
+      float f[8]; q.get(f);
+      const float4 s0 = *reinterpret_cast<const float4*>(&sh[cv * 8]), s1 = *reinterpret_cast<const float4*>(&sh[cv * 8 + 4]);
+      const float4 h0 = *reinterpret_cast<const float4*>(&sh[C + cv * 8]), h1 = *reinterpret_cast<const float4*>(&sh[C + cv * 8 + 4]);
+      const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const float sf[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int c = cv * 8 + j;
-      float u = fmaf(f[j], sh[c], sh[C + c]);
-      if (round_like_ref) u = rnd<T>(u);
-      if (silu) u = u / (1.f + expf(-u));
-      f[j] = u;
+      for (int j = 0; j < 8; ++j) {
+        float u = fmaf(f[j], sc[j], sf[j]);
+        if (round_like_ref) u = rnd<T>(u);
+        if (silu) u = FastMath<T>::value ? __fdividef(u, 1.f + __expf(-u)) : u / (1.f + expf(-u));
+        f[j] = u;
+      }
+      q.set(f);
+      q.store(drow + (int64_t)i * 8);
     }
-    q.set(f);
-    q.store(yd + v * C + cv * 8);
+  }
+}
+
+// Sum per-tile GroupNorm partials (written by the conv epilogue) in a fixed order: grid = (groups, B).
+// part: [B][rows][groups][2] fp32 -> sums: [B][groups][2] fp64.  One block per (group, batch); threads stride
+// over rows, then a fixed-shape tree in shared memory: bit-reproducible.
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ part, int64_t rows, int groups,
+                                                          double* __restrict__ sums) {
+  __shared__ double sa[256], sq[256];
+  const int g = blockIdx.x, b = blockIdx.y;
+  const float* p = part + ((int64_t)b * rows * groups + g) * 2;
+  double a = 0.0, q = 0.0;
+  for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) {
+    a += (double)p[r * groups * 2];
+    q += (double)p[r * groups * 2 + 1];
+  }
+  sa[threadIdx.x] = a; sq[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sq[threadIdx.x] += sq[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    sums[((int64_t)b * groups + g) * 2] = sa[0];
+    sums[((int64_t)b * groups + g) * 2 + 1] = sq[0];
   }
 }
 
@@ -184,7 +224,7 @@ __global__ void gn_apply_kernel(Vol x, Vol y, const double* __restrict__ sums, c
 // ------------------------------------------------------------------------------------------------
 template <typename T, int VEC>
 __global__ void pad_upsample_kernel(Vol x, Vol y, int up_t, int up_h, int up_w) {
-  const int CV = x.C / VEC;
+  const int CV = y.C / VEC;  // y.C == x.C on the vector path; y.C >= x.C (zero channel padding) on the scalar path
   const int64_t nvp = (int64_t)y.B * y.Tp() * y.Hp() * y.Wp();
   const int64_t total = nvp * CV;
   const T* xs = reinterpret_cast<const T*>(x.p);
@@ -204,7 +244,7 @@ __global__ void pad_upsample_kernel(Vol x, Vol y, int up_t, int up_h, int up_w) 
     const T* s = xs + x.at(b, ts, hs, ws) + cv * VEC;
     T* o = yd + v * y.C + cv * VEC;
     if (VEC == 8) { Vec8<T> q; q.load(s); q.store(o); }
-    else { o[0] = s[0]; }
+    else { o[0] = (cv < x.C) ? s[0] : from_f<T>(0.f); }
   }
 }
 
@@ -354,25 +394,27 @@ int hyvae_device_supports_tc(void) {
   return major == 10;
 }
 
-int hyvae_ncthw_to_vol(const void* src, int32_t src_dtype, const int64_t* ss, const hyvae_vol* dst, void* stream) {
+int hyvae_ncthw_to_vol(const void* src, int32_t src_dtype, int32_t src_C, const int64_t* ss, const hyvae_vol* dst, void* stream) {
   if (int e = check_vol(dst, "dst")) return e;
   HYVAE_CHECK_ARG(src != nullptr && ss != nullptr, "src is null");
+  HYVAE_CHECK_ARG(src_C > 0 && src_C <= dst->C, "src_C=%d must be in [1, dst C=%d]", src_C, dst->C);
   Vol d = make_vol(dst);
   int64_t n = (int64_t)d.B * d.Tp() * d.Hp() * d.Wp();
   ProfScope prof(PC_LAYOUT, (double)n * d.C * (dtype_size(src_dtype) + dtype_size(dst->dtype)), stream);
   HYVAE_DISPATCH_DTYPE(src_dtype, S, HYVAE_DISPATCH_DTYPE(dst->dtype, D,
-      (ncthw_to_vol_kernel<S, D><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const S*)src, d, ss[0], ss[1], ss[2], ss[3], ss[4]))));
+      (ncthw_to_vol_kernel<S, D><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const S*)src, d, src_C, ss[0], ss[1], ss[2], ss[3], ss[4]))));
   return check_launch("ncthw_to_vol");
 }
 
-int hyvae_vol_to_ncthw(const hyvae_vol* src, void* dst, int32_t dst_dtype, void* stream) {
+int hyvae_vol_to_ncthw(const hyvae_vol* src, void* dst, int32_t dst_dtype, int32_t dst_C, void* stream) {
   if (int e = check_vol(src, "src")) return e;
   HYVAE_CHECK_ARG(dst != nullptr, "dst is null");
+  HYVAE_CHECK_ARG(dst_C > 0 && dst_C <= src->C, "dst_C=%d must be in [1, src C=%d]", dst_C, src->C);
   Vol s = make_vol(src);
   int64_t n = (int64_t)s.B * s.T * s.H * s.W;
-  ProfScope prof(PC_LAYOUT, (double)n * s.C * (dtype_size(src->dtype) + dtype_size(dst_dtype)), stream);
+  ProfScope prof(PC_LAYOUT, (double)n * dst_C * (dtype_size(src->dtype) + dtype_size(dst_dtype)), stream);
   HYVAE_DISPATCH_DTYPE(src->dtype, S, HYVAE_DISPATCH_DTYPE(dst_dtype, D,
-      (vol_to_ncthw_kernel<S, D><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s, (D*)dst))));
+      (vol_to_ncthw_kernel<S, D><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s, (D*)dst, dst_C))));
   return check_launch("vol_to_ncthw");
 }
 
@@ -426,29 +468,40 @@ int hyvae_groupnorm_apply(const hyvae_vol* x, const double* sums, const float* g
   HYVAE_CHECK_ARG(x->B == y->B && x->T == y->T && x->H == y->H && x->W == y->W && x->C == y->C, "shape mismatch");
   HYVAE_CHECK_ARG(groups > 0 && x->C % groups == 0 && x->C % 8 == 0, "bad C=%d / groups=%d", x->C, groups);
   Vol vx = make_vol(x), vy = make_vol(y);
-  int64_t total = (int64_t)vy.Tp() * vy.Hp() * vy.Wp() * (x->C / 8);
   ProfScope prof(PC_GN_APPLY, 2.0 * x->B * x->T * x->H * x->W * x->C * dtype_size(x->dtype), stream);
-  dim3 grid((unsigned)grid_for(total, 256, 16), (unsigned)x->B);
+  // rows of Wp*C contiguous elements; give each block >= ~64 KB of output, and keep >= ~8 blocks per SM when possible
+  const int nrows = vy.Tp() * vy.Hp();
+  const int64_t row_bytes = (int64_t)vy.Wp() * x->C * dtype_size(x->dtype);
+  int rpb = (int)((65536 + row_bytes - 1) / row_bytes);
+  while (rpb > 1 && (int64_t)((nrows + rpb - 1) / rpb) * x->B < 8 * num_sms()) rpb >>= 1;
+  dim3 grid((unsigned)((nrows + rpb - 1) / rpb), (unsigned)x->B);
   size_t smem = sizeof(float) * 2 * x->C;
   HYVAE_DISPATCH_DTYPE(x->dtype, T, (gn_apply_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
-      vx, vy, sums, gamma, beta, groups, eps, silu, round_like_ref)));
+      vx, vy, sums, gamma, beta, groups, eps, silu, round_like_ref, rpb)));
   return check_launch("groupnorm_apply");
+}
+
+int hyvae_groupnorm_finalize(const float* partials, int32_t B, int64_t rows, int32_t groups, double* sums, void* stream) {
+  HYVAE_CHECK_ARG(partials && sums && B > 0 && rows > 0 && groups > 0, "bad finalize arguments");
+  ProfScope prof(PC_GN_STATS, (double)B * rows * groups * 8, stream);
+  gn_finalize_kernel<<<dim3((unsigned)groups, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(partials, rows, groups, sums);
+  return check_launch("groupnorm_finalize");
 }
 
 int hyvae_pad_upsample(const hyvae_vol* x, const hyvae_vol* y, int32_t up_t, int32_t up_h, int32_t up_w, void* stream) {
   if (int e = check_vol(x, "x")) return e;
   if (int e = check_vol(y, "y")) return e;
-  HYVAE_CHECK_ARG(x->dtype == y->dtype && x->C == y->C && x->B == y->B, "dtype/C/B mismatch");
+  HYVAE_CHECK_ARG(x->dtype == y->dtype && x->C <= y->C && x->B == y->B, "dtype/C/B mismatch");
   HYVAE_CHECK_ARG((up_t == 1 || up_t == 2) && (up_h == 1 || up_h == 2) && (up_w == 1 || up_w == 2), "up factors must be 1 or 2");
   int Te = up_t == 2 ? 1 + 2 * (x->T - 1) : x->T;
   HYVAE_CHECK_ARG(y->T == Te && y->H == x->H * up_h && y->W == x->W * up_w, "y dims %dx%dx%d do not match upsampled x", y->T, y->H, y->W);
   Vol vx = make_vol(x), vy = make_vol(y);
   int64_t nvp = (int64_t)vy.B * vy.Tp() * vy.Hp() * vy.Wp();
   ProfScope prof(PC_PAD_UPSAMPLE, (double)nvp * x->C * dtype_size(x->dtype) + (double)x->B * x->T * x->H * x->W * x->C * dtype_size(x->dtype), stream);
-  if (x->C % 8 == 0) {
+  if (x->C % 8 == 0 && x->C == y->C) {
     HYVAE_DISPATCH_DTYPE(x->dtype, T, (pad_upsample_kernel<T, 8><<<grid_for(nvp * (x->C / 8), 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, up_t, up_h, up_w)));
   } else {
-    HYVAE_DISPATCH_DTYPE(x->dtype, T, (pad_upsample_kernel<T, 1><<<grid_for(nvp * x->C, 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, up_t, up_h, up_w)));
+    HYVAE_DISPATCH_DTYPE(x->dtype, T, (pad_upsample_kernel<T, 1><<<grid_for(nvp * y->C, 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, up_t, up_h, up_w)));
   }
   return check_launch("pad_upsample");
 }

@@ -30,8 +30,8 @@ def tc_eligible(dtype, cin: int, cout: int, stride, k: int) -> bool:
     """Tensor-core (tcgen05) path iff the shape fits it; everything else runs the CUDA-core kernel."""
     if os.environ.get("HYVAE_FORCE_DIRECT", "0") == "1":
         return False
-    return (N.device_supports_tc() and dtype in _16BIT and cin % 8 == 0 and cin >= 64 and cout % 8 == 0
-            and cout >= 32 and stride[1] <= 2 and stride[2] <= 2)
+    del cin, cout, k  # any channel count works: operands are zero-padded to multiples of 8 (TMA fills the rest)
+    return N.device_supports_tc() and dtype in _16BIT and stride[1] <= 2 and stride[2] <= 2
 
 
 def prepare_causal_attention_mask(n_frame: int, n_hw: int, dtype, device, batch_size: int = None):
@@ -61,15 +61,24 @@ class _Conv3dParams(nn.Module):
             nn.init.uniform_(self.bias, -bound, bound)
         self._packed = None
 
-    def packed(self, dtype):
-        """[taps][Cout][Cin] weights in the activation dtype + fp32 bias (kernel layout), cached."""
+    def packed(self, dtype, pad8: bool = False):
+        """[taps][Cout][Cin] weights in the activation dtype + fp32 bias (kernel layout), cached.  pad8 zero-pads
+        Cout and Cin up to multiples of 8 (16-byte rows) for the tensor-core kernel."""
         w = self.weight
-        key = (w._version, w.data_ptr(), dtype, w.device, None if self.bias is None else self.bias._version)
+        key = (w._version, w.data_ptr(), dtype, w.device, None if self.bias is None else self.bias._version, pad8)
         if self._packed is None or self._packed[0] != key:
             k = self.kernel_size[0]
-            pw = w.detach().permute(2, 3, 4, 0, 1).reshape(k * k * k, self.out_channels, self.in_channels).to(dtype).contiguous()
-            pb = None if self.bias is None else self.bias.detach().float().contiguous()
-            self._packed = (key, pw, pb)
+            co, ci = self.out_channels, self.in_channels
+            pw = w.detach().permute(2, 3, 4, 0, 1).reshape(k * k * k, co, ci).to(dtype)
+            pb = None if self.bias is None else self.bias.detach().float()
+            if pad8 and (co % 8 or ci % 8):
+                cop, cip = -(-co // 8) * 8, -(-ci // 8) * 8
+                full = torch.zeros((k * k * k, cop, cip), dtype=dtype, device=w.device)
+                full[:, :co, :ci] = pw
+                pw = full
+                if pb is not None:
+                    pb = torch.cat([pb, torch.zeros(cop - co, device=w.device)])
+            self._packed = (key, pw.contiguous(), None if pb is None else pb.contiguous())
         return self._packed[1], self._packed[2]
 
 
@@ -89,6 +98,7 @@ class CausalConv3d(nn.Module):
         k = kernel_size
         self.time_causal_padding = (k // 2, k // 2, k // 2, k // 2, k - 1, 0)
         self.conv = _Conv3dParams(chan_in, chan_out, k, stride, bias=kwargs.get("bias", True))
+        self.emit_gn_groups = 0  # >0: the consumer is a GroupNorm with that many groups -> stats from the epilogue
 
     @property
     def halo(self) -> Tuple[int, int, int]:
@@ -100,15 +110,28 @@ class CausalConv3d(nn.Module):
         c = self.conv
         return self.halo if tc_eligible(dtype, c.in_channels, c.out_channels, c.stride, c.kernel_size[0]) else (0, 0, 0)
 
+    def input_layout(self, dtype):
+        """(halo, channel count) a producer should write so that this conv needs no extra pad pass."""
+        c = self.conv
+        if tc_eligible(dtype, c.in_channels, c.out_channels, c.stride, c.kernel_size[0]):
+            return self.halo, -(-c.in_channels // 8) * 8
+        return (0, 0, 0), c.in_channels
+
     def forward_vol(self, x: Vol, residual: Optional[Vol] = None, up=(1, 1, 1), out_dtype=None) -> Vol:
         c = self.conv
         k, stride = c.kernel_size[0], tuple(int(s) for s in c.stride)
-        w, b = c.packed(x.dtype)
         rl = False  # one rounding per stored tensor: conv + bias + residual are summed in fp32, then stored
         if tc_eligible(x.dtype, c.in_channels, c.out_channels, stride, k):
-            if x.pad != self.halo or up != (1, 1, 1):
-                x = N.pad_upsample(x, up, self.halo)
-            return N.conv3d_tc(x, w, b, k, stride, c.out_channels, residual, out_dtype, rl)
+            w, b = c.packed(x.dtype, pad8=True)
+            cin_p, cout_p = w.shape[2], w.shape[1]
+            if x.pad != self.halo or up != (1, 1, 1) or x.C != cin_p:
+                x = N.pad_upsample(x, up, self.halo, channels=cin_p)
+            y = N.conv3d_tc(x, w, b, k, stride, cout_p, residual, out_dtype, rl, gn_groups=self.emit_gn_groups)
+            y.c_valid = c.out_channels
+            return y
+        w, b = c.packed(x.dtype)
+        if x.C != c.in_channels:
+            raise N.HyvaeError(f"CausalConv3d: input has {x.C} channels, expected {c.in_channels}")
         return N.conv3d_direct(x, w, b, k, stride, c.out_channels, residual, up, out_dtype, rl)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -153,6 +176,8 @@ class UpsampleCausal3D(nn.Module):
         if any(f not in (1, 2) for f in self.upsample_factor):
             raise NotImplementedError(f"upsample_factor {upsample_factor}")
         conv = CausalConv3d(self.channels, self.out_channels, kernel_size=kernel_size or 3, bias=bias) if use_conv else None
+        if conv is not None:
+            conv.emit_gn_groups = 32  # next consumer: the following resnet's norm1 (ignored unless its groups match)
         if name == "conv":
             self.conv = conv
         else:
@@ -183,6 +208,7 @@ class DownsampleCausal3D(nn.Module):
         self.channels, self.out_channels = channels, out_channels or channels
         self.use_conv, self.padding, self.name = use_conv, padding, name
         self.conv = CausalConv3d(self.channels, self.out_channels, kernel_size=kernel_size, stride=stride, bias=bias)
+        self.conv.emit_gn_groups = 32
         if name == "conv":
             self.Conv2d_0 = self.conv
 
@@ -221,6 +247,9 @@ class ResnetBlockCausal3D(nn.Module):
         self.use_in_shortcut = (in_channels != c3) if use_in_shortcut is None else use_in_shortcut
         self.conv_shortcut = (CausalConv3d(in_channels, c3, kernel_size=1, stride=1, bias=conv_shortcut_bias)
                               if self.use_in_shortcut else None)
+        # both convs feed a GroupNorm (norm2; the next block's norm1 / conv_norm_out / the attention's group_norm)
+        self.conv1.emit_gn_groups = self.norm2.num_groups
+        self.conv2.emit_gn_groups = groups
 
     def forward_vol(self, x: Vol) -> Vol:
         if self.output_scale_factor != 1.0:

@@ -124,6 +124,7 @@ class EncoderCausal3D(nn.Module):
         super().__init__()
         self.layers_per_block = layers_per_block
         self.conv_in = CausalConv3d(in_channels, block_out_channels[0], kernel_size=3, stride=1)
+        self.conv_in.emit_gn_groups = norm_num_groups
         self.down_blocks = nn.ModuleList([])
         plan = _sampler_plan(len(block_out_channels), spatial_compression_ratio, time_compression_ratio)
         oc = block_out_channels[0]
@@ -164,6 +165,7 @@ class DecoderCausal3D(nn.Module):
             raise NotImplementedError("norm_type 'spatial'")
         self.layers_per_block = layers_per_block
         self.conv_in = CausalConv3d(in_channels, block_out_channels[-1], kernel_size=3, stride=1)
+        self.conv_in.emit_gn_groups = norm_num_groups
         self.mid_block = UNetMidBlockCausal3D(
             in_channels=block_out_channels[-1], resnet_eps=1e-6, resnet_act_fn=act_fn, output_scale_factor=1,
             resnet_time_scale_shift="default", attention_head_dim=block_out_channels[-1], resnet_groups=norm_num_groups,
@@ -340,7 +342,9 @@ class AutoencoderKLCausal3D(nn.Module):
         return dt
 
     def _encode_tile(self, x: torch.Tensor) -> torch.Tensor:
-        v = Vol.from_ncthw(x, dtype=self._act_dtype())
+        act = self._act_dtype()
+        pad, ch = self.encoder.conv_in.input_layout(act)   # tensor-core conv_in: halo + 3->8 channels written here
+        v = Vol.from_ncthw(x, dtype=act, pad=pad, channels=ch)
         return self.quant_conv.forward_vol(self.encoder.forward_vol(v)).to_ncthw(dtype=self.dtype)
 
     def _decode_tile(self, z: torch.Tensor) -> torch.Tensor:

@@ -47,9 +47,12 @@ int hyvae_device_supports_tc(void);
 
 /* ---- layout: torch NCTHW <-> channels-last volume ---------------------------------------------
  * Replaces the implicit NCDHW layout of every reference tensor; `dst` halo is filled by replication. */
-/* src_strides: element strides of the (possibly sliced) source view in (B,C,T,H,W) order. */
-int hyvae_ncthw_to_vol(const void* src, int32_t src_dtype, const int64_t* src_strides, const hyvae_vol* dst, void* stream);
-int hyvae_vol_to_ncthw(const hyvae_vol* src, void* dst, int32_t dst_dtype, void* stream);
+/* src_strides: element strides of the (possibly sliced) source view in (B,C,T,H,W) order.  src_C <= dst->C:
+ * extra destination channels are zero (3 -> 8 channel padding for the tensor-core conv_in).  dst_C <= src->C:
+ * only the first dst_C channels are written out (8 -> 3 after the tensor-core conv_out). */
+int hyvae_ncthw_to_vol(const void* src, int32_t src_dtype, int32_t src_C, const int64_t* src_strides, const hyvae_vol* dst,
+                       void* stream);
+int hyvae_vol_to_ncthw(const hyvae_vol* src, void* dst, int32_t dst_dtype, int32_t dst_C, void* stream);
 
 /* ---- CausalConv3d ------------------------------------------------------------------------------
  * Replaces F.pad(replicate)+nn.Conv3d, unet_causal_3d_blocks.py:73-75 (k=3 or k=1; stride from
@@ -63,14 +66,18 @@ int hyvae_vol_to_ncthw(const hyvae_vol* src, void* dst, int32_t dst_dtype, void*
  *             the reference's two separate kernels do in bf16/fp16).
  *   y:        same dtype as x, or HYVAE_F32 (used for the attention scores S = Q K^T).
  * _direct: CUDA-core implicit GEMM, any shape/dtype; replicate padding by index clamping.
- * _tc:     tcgen05/TMEM implicit GEMM fed by TMA; needs bf16/f16, Cin%64==0, Cout%16==0, up_*==1 and
- *          x carrying the halo (pt,ph,pw) = (k-1,k/2,k/2). */
+ * _tc:     tcgen05/TMEM implicit GEMM fed by TMA; needs bf16/f16, up_*==1 and
+ *          x carrying the halo (pt,ph,pw) = (k-1,k/2,k/2).  Cin%8==0 and Cout%8==0 suffice (TMA zero-fills the
+ *          rest); gn_partials != NULL additionally emits GroupNorm partial statistics of y from the epilogue. */
 int hyvae_conv3d_causal_direct(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
                                const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
                                int32_t up_t, int32_t up_h, int32_t up_w, int32_t round_like_ref, void* stream);
 int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
                            const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
-                           int32_t round_like_ref, int32_t variant, void* stream);
+                           int32_t round_like_ref, int32_t variant, float* gn_partials, int32_t gn_groups, void* stream);
+/* rows-per-batch of the gn_partials buffer the call above fills for output volume y:
+ * gn_partials is [B][rows][gn_groups][2] fp32 (see hyvae_groupnorm_finalize). */
+int64_t hyvae_conv3d_tc_gn_rows(const hyvae_vol* y, int32_t sh, int32_t sw);
 
 /* ---- GroupNorm (+SiLU) -------------------------------------------------------------------------
  * Replaces nn.GroupNorm(32,C,eps=1e-6) + SiLU, unet_causal_3d_blocks.py:359-363,401-405 and
@@ -85,10 +92,14 @@ int hyvae_groupnorm_stats(const hyvae_vol* x, int32_t groups, double* sums, void
 int hyvae_groupnorm_apply(const hyvae_vol* x, const double* sums, const float* gamma, const float* beta,
                           int32_t groups, float eps, int32_t silu, int32_t round_like_ref, const hyvae_vol* y,
                           void* stream);
+/* Statistics from the PRODUCER: hyvae_conv3d_causal_tc can emit per-tile partial sums of its own output
+ * (gn_partials, [B][rows][groups][2] fp32 with rows = hyvae_conv3d_tc_gn_rows()); _finalize adds them in a fixed
+ * order into `sums`, replacing the _stats pass over the tensor. */
+int hyvae_groupnorm_finalize(const float* partials, int32_t B, int64_t rows, int32_t groups, double* sums, void* stream);
 
 /* ---- pad / nearest upsample --------------------------------------------------------------------
  * Replaces F.pad(replicate) :74 and F.interpolate(nearest)+cat of UpsampleCausal3D.forward :152-171:
- * y (T' = 1+up_t*(T-1) if up_t==2, H*up_h, W*up_w, with any halo) <- x. */
+ * y (T' = 1+up_t*(T-1) if up_t==2, H*up_h, W*up_w, with any halo) <- x.  y->C may exceed x->C (zero channels). */
 int hyvae_pad_upsample(const hyvae_vol* x, const hyvae_vol* y, int32_t up_t, int32_t up_h, int32_t up_w, void* stream);
 
 /* ---- mid-block attention softmax ---------------------------------------------------------------

@@ -7,7 +7,7 @@ timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "not tc_ and 
 echo "== stage 2: whole model on the CUDA-core path"
 HYVAE_FORCE_DIRECT=1 timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "model_fp32 or model_16bit or pure_bf16" 2>&1 | tail -15 | tee gpurun_out/stage2.log
 echo "== stage 3: tcgen05 conv"
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "tc_conv or tc_gemm or tc_big" 2>&1 | tail -30 | tee gpurun_out/stage3.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "tc_conv or tc_gemm or tc_big or tc_thin" 2>&1 | tail -30 | tee gpurun_out/stage3.log
 echo "== stage 4: model with tcgen05"
 timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "model_16bit or tc_model or full_size or reproducible or pure_bf16" 2>&1 | tail -30 | tee gpurun_out/stage4.log
 echo "== stage 5: microbench"
