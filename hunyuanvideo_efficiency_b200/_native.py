@@ -73,7 +73,7 @@ def lib():
         l.hyvae_groupnorm_workspace_bytes.restype = C.c_int64
         l.hyvae_groupnorm_workspace_bytes.argtypes = [_VP, _i32]
         l.hyvae_conv3d_tc_gn_rows.restype = C.c_int64
-        l.hyvae_conv3d_tc_gn_rows.argtypes = [_VP, _i32, _i32]
+        l.hyvae_conv3d_tc_gn_rows.argtypes = []
         _lib = l
     return _lib
 
@@ -208,8 +208,8 @@ def conv3d_tc(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, residual
     y = out if out is not None else Vol(x.B, To, Ho, Wo, cout, out_dtype or x.dtype, x.device)
     part, rows = None, 0
     if gn_groups > 0 and cout % gn_groups == 0 and (cout // gn_groups) in (1, 2, 4, 8, 16, 32):
-        rows = int(lib().hyvae_conv3d_tc_gn_rows(y.ref(), stride[1], stride[2]))
-        part = torch.empty((x.B, rows, gn_groups, 2), dtype=torch.float32, device=x.device)
+        rows = int(lib().hyvae_conv3d_tc_gn_rows())
+        part = torch.zeros((x.B, rows, gn_groups, 2), dtype=torch.float64, device=x.device)
     _check(lib().hyvae_conv3d_causal_tc(x.ref(), w.data_ptr(), _ptr(bias), residual.ref() if residual else None, y.ref(),
                                         k, stride[0], stride[1], stride[2], int(round_like_ref), variant,
                                         _ptr(part), gn_groups if part is not None else 0, _stream()),

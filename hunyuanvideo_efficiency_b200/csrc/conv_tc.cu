@@ -138,8 +138,8 @@ struct TcArgs {
   int64_t m_tiles;      // B * To * tiles_h * tiles_w
   int64_t total_tiles;  // ceil(m_tiles / MT) * n_tiles
   int round_like_ref;
-  float* gn_part;       // optional [B][m_tiles_per_b * 4][gn_groups][2] partial (sum, sum of squares) of the output
-  int gn_groups, gn_cpg;
+  double* gn_part;      // optional [B][gn_rows][gn_groups][2] (sum, sum of squares) of the output; row = CTA * 4 + warp
+  int gn_groups, gn_cpg, gn_rows;
   int64_t m_tiles_per_b;
 };
 
@@ -165,9 +165,10 @@ template <> struct TcFmt<__nv_bfloat16> { static constexpr int fmt = 1; };
 template <> struct TcFmt<__half> { static constexpr int fmt = 0; };
 
 // GroupNorm partial statistics of one 32-column chunk of the epilogue: per group of CPG channels, the sum and sum of
-// squares over this warp's 32 rows (fixed shuffle tree -> bit-reproducible); lane 0 writes them.
+// squares over this warp's 32 rows (fixed shuffle tree); lane 0 adds them to the fp64 slot that this (CTA, warp)
+// owns for the tile's batch item.  The tile order of a CTA is static, so the result is bit-reproducible.
 template <int CPG>
-__device__ __forceinline__ void gn_chunk_stats(const float* f, bool valid, float* dst, int lane, int ngroups_valid) {
+__device__ __forceinline__ void gn_chunk_stats(const float* f, bool valid, double* dst, int lane, int ngroups_valid) {
 #pragma unroll
   for (int g = 0; g < 32 / CPG; ++g) {
     float s = 0.f, q = 0.f;
@@ -175,7 +176,7 @@ __device__ __forceinline__ void gn_chunk_stats(const float* f, bool valid, float
     for (int c = 0; c < CPG; ++c) { const float u = valid ? f[g * CPG + c] : 0.f; s += u; q = fmaf(u, u, q); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-    if (lane == 0 && g < ngroups_valid) { dst[2 * g] = s; dst[2 * g + 1] = q; }
+    if (lane == 0 && g < ngroups_valid) { dst[2 * g] += (double)s; dst[2 * g + 1] += (double)q; }  // private slot: plain RMW
   }
 }
 
@@ -337,8 +338,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             if (a.gn_part) {
-              const int64_t prow = (int64_t)m.b * a.m_tiles_per_b * 4 + ((mg * MT + i) - (int64_t)m.b * a.m_tiles_per_b) * 4 + q;
-              float* dst = a.gn_part + (prow * a.gn_groups + nc / a.gn_cpg) * 2;
+              const int64_t prow = (int64_t)m.b * a.gn_rows + blockIdx.x * 4 + q;
+              double* dst = a.gn_part + (prow * a.gn_groups + nc / a.gn_cpg) * 2;
               const int ng = (a.Cout - nc) / a.gn_cpg;
               switch (a.gn_cpg) {
                 case 1: gn_chunk_stats<1>(f, valid, dst, lane, ng); break;
@@ -411,16 +412,11 @@ static void pick_tile(int Ho, int Wo, int sh, int sw, int* TH, int* TW) {
   *TW = best_tw; *TH = 128 / best_tw;
 }
 
-extern "C" int64_t hyvae_conv3d_tc_gn_rows(const hyvae_vol* y, int32_t sh, int32_t sw) {
-  if (y == nullptr) return -1;
-  int TH, TW;
-  pick_tile(y->H, y->W, sh, sw, &TH, &TW);
-  return (int64_t)y->T * ((y->H + TH - 1) / TH) * ((y->W + TW - 1) / TW) * 4;
-}
+extern "C" int64_t hyvae_conv3d_tc_gn_rows(void) { return (int64_t)num_sms() * 4; }
 
 extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
                                       const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
-                                      int32_t round_like_ref, int32_t variant, float* gn_partials, int32_t gn_groups,
+                                      int32_t round_like_ref, int32_t variant, double* gn_partials, int32_t gn_groups,
                                       void* stream) {
   if (int e = check_vol(x, "x")) return e;
   if (int e = check_vol(y, "y")) return e;
@@ -459,7 +455,7 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
   a.n_tiles = (y->C + BN - 1) / BN;
   a.m_tiles = (int64_t)y->B * y->T * a.tiles_h * a.tiles_w;
   a.m_tiles_per_b = (int64_t)y->T * a.tiles_h * a.tiles_w;
-  a.gn_part = gn_partials; a.gn_groups = gn_groups; a.gn_cpg = 0;
+  a.gn_part = gn_partials; a.gn_groups = gn_groups; a.gn_cpg = 0; a.gn_rows = num_sms() * 4;
   if (gn_partials) {
     HYVAE_CHECK_ARG(gn_groups > 0 && y->C % gn_groups == 0, "gn_groups=%d does not divide Cout=%d", gn_groups, y->C);
     a.gn_cpg = y->C / gn_groups;

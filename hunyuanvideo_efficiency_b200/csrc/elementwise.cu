@@ -139,6 +139,23 @@ __global__ void gn_stats_kernel(Vol x, int groups, int vox_per_block, double* __
 template <typename T> struct FastMath { static constexpr bool value = true; };
 template <> struct FastMath<float> { static constexpr bool value = false; };
 
+// y = silu(u) with one MUFU (ex2) per element on the 16-bit paths: the reciprocal is two Newton steps on the FMA pipe
+// (MUFU rate, 16/clk/SM, is what bounds this kernel otherwise).  fp32 keeps expf and a true division.
+template <typename T>
+__device__ __forceinline__ float gn_act(float u, int silu, int round_like_ref) {
+  if (round_like_ref) u = rnd<T>(u);
+  if (!silu) return u;
+  if (FastMath<T>::value) {
+    const float d = 1.f + __expf(-u);                 // d in [1, inf)
+    float r = __int_as_float(0x7EF311C7 - __float_as_int(d));  // fast reciprocal seed (~12 % error)
+    r = r * fmaf(-d, r, 2.f);
+    r = r * fmaf(-d, r, 2.f);
+    r = r * fmaf(-d, r, 2.f);                         // 3 Newton steps: < 1e-6 relative
+    return (d > 1e30f) ? 0.f : u * r;
+  }
+  return u / (1.f + expf(-u));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) gn_apply_kernel(Vol x, Vol y, const double* __restrict__ sums, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int groups, float eps, int silu, int round_like_ref,
@@ -166,46 +183,69 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Vol x, Vol y, const doubl
   const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, nrows);
   const bool pow2 = (CV & (CV - 1)) == 0;
   const int shift = 31 - __clz(CV);
+  const bool fixed_cv = (blockDim.x % CV) == 0;
+  const int mycv = threadIdx.x % CV;
+  float rsc[8], rsf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { rsc[j] = sh[mycv * 8 + j]; rsf[j] = sh[C + mycv * 8 + j]; }
   for (int r = r0; r < r1; ++r) {
     const int tp = r / Hp, hp = r - tp * Hp;
     const int t = max(tp - y.pt, 0), h = min(max(hp - y.ph, 0), y.H - 1);
     const T* srow = xs + x.at(b, t, h, 0);
     T* drow = yd + (int64_t)r * Wp * C;
-    for (int i = threadIdx.x; i < row_elems; i += blockDim.x) {
-      const int wp = pow2 ? (i >> shift) : (i / CV);
-      const int cv = i - wp * CV;
-      const int w = min(max(wp - y.pw, 0), y.W - 1);
-      Vec8<T> q; q.load(srow + (int64_t)w * x.sW + cv * 8);
-      float f[8]; q.get(f);
-      const float4 s0 = *reinterpret_cast<const float4*>(&sh[cv * 8]), s1 = *reinterpret_cast<const float4*>(&sh[cv * 8 + 4]);
-      const float4 h0 = *reinterpret_cast<const float4*>(&sh[C + cv * 8]), h1 = *reinterpret_cast<const float4*>(&sh[C + cv * 8 + 4]);
-      const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-      const float sf[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    if (fixed_cv) {
+      // blockDim % CV == 0: this thread always lands on the same 8 channels -> scale/shift live in registers;
+      // two 16-byte vectors in flight per thread
+      for (int i = threadIdx.x; i < row_elems; i += 2 * blockDim.x) {
+        const int i2 = i + blockDim.x;
+        const bool has2 = i2 < row_elems;
+        const int wp0 = pow2 ? (i >> shift) : (i / CV), wp1 = pow2 ? (i2 >> shift) : (i2 / CV);
+        const int w0 = min(max(wp0 - y.pw, 0), y.W - 1), w1 = min(max(wp1 - y.pw, 0), y.W - 1);
+        Vec8<T> q0, q1;
+        q0.load(srow + (int64_t)w0 * x.sW + mycv * 8);
+        if (has2) q1.load(srow + (int64_t)w1 * x.sW + mycv * 8);
+        float f[8];
+        q0.get(f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float u = fmaf(f[j], sc[j], sf[j]);
-        if (round_like_ref) u = rnd<T>(u);
-        if (silu) u = FastMath<T>::value ? __fdividef(u, 1.f + __expf(-u)) : u / (1.f + expf(-u));
-        f[j] = u;
+        for (int j = 0; j < 8; ++j) f[j] = gn_act<T>(fmaf(f[j], rsc[j], rsf[j]), silu, round_like_ref);
+        q0.set(f);
+        q0.store(drow + (int64_t)i * 8);
+        if (has2) {
+          q1.get(f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = gn_act<T>(fmaf(f[j], rsc[j], rsf[j]), silu, round_like_ref);
+          q1.set(f);
+          q1.store(drow + (int64_t)i2 * 8);
+        }
       }
-      q.set(f);
-      q.store(drow + (int64_t)i * 8);
+    } else {
+      for (int i = threadIdx.x; i < row_elems; i += blockDim.x) {
+        const int wp = i / CV;
+        const int cv = i - wp * CV;
+        const int w = min(max(wp - y.pw, 0), y.W - 1);
+        Vec8<T> q; q.load(srow + (int64_t)w * x.sW + cv * 8);
+        float f[8]; q.get(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = gn_act<T>(fmaf(f[j], sh[cv * 8 + j], sh[C + cv * 8 + j]), silu, round_like_ref);
+        q.set(f);
+        q.store(drow + (int64_t)i * 8);
+      }
     }
   }
 }
 
 // Sum per-tile GroupNorm partials (written by the conv epilogue) in a fixed order: grid = (groups, B).
-// part: [B][rows][groups][2] fp32 -> sums: [B][groups][2] fp64.  One block per (group, batch); threads stride
+// part: [B][rows][groups][2] fp64 -> sums: [B][groups][2] fp64.  One block per (group, batch); threads stride
 // over rows, then a fixed-shape tree in shared memory: bit-reproducible.
-__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ part, int64_t rows, int groups,
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const double* __restrict__ part, int64_t rows, int groups,
                                                           double* __restrict__ sums) {
   __shared__ double sa[256], sq[256];
   const int g = blockIdx.x, b = blockIdx.y;
-  const float* p = part + ((int64_t)b * rows * groups + g) * 2;
+  const double* p = part + ((int64_t)b * rows * groups + g) * 2;
   double a = 0.0, q = 0.0;
   for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) {
-    a += (double)p[r * groups * 2];
-    q += (double)p[r * groups * 2 + 1];
+    a += p[r * groups * 2];
+    q += p[r * groups * 2 + 1];
   }
   sa[threadIdx.x] = a; sq[threadIdx.x] = q;
   __syncthreads();
@@ -481,7 +521,7 @@ int hyvae_groupnorm_apply(const hyvae_vol* x, const double* sums, const float* g
   return check_launch("groupnorm_apply");
 }
 
-int hyvae_groupnorm_finalize(const float* partials, int32_t B, int64_t rows, int32_t groups, double* sums, void* stream) {
+int hyvae_groupnorm_finalize(const double* partials, int32_t B, int64_t rows, int32_t groups, double* sums, void* stream) {
   HYVAE_CHECK_ARG(partials && sums && B > 0 && rows > 0 && groups > 0, "bad finalize arguments");
   ProfScope prof(PC_GN_STATS, (double)B * rows * groups * 8, stream);
   gn_finalize_kernel<<<dim3((unsigned)groups, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(partials, rows, groups, sums);

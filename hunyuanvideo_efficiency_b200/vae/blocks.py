@@ -286,7 +286,7 @@ def _gemm_nt(x: Vol, w: torch.Tensor, bias, cout: int, residual: Optional[Vol] =
              out: Optional[Vol] = None) -> Vol:
     """y[m][n] = sum_k x[m][k] * w[n][k] (+bias[n]) (+residual): a 1x1x1 'conv' on either kernel."""
     rl = False
-    if tc_eligible(x.dtype, x.C, cout, (1, 1, 1), 1) and x.pad == (0, 0, 0):
+    if tc_eligible(x.dtype, x.C, cout, (1, 1, 1), 1) and x.pad == (0, 0, 0) and x.C % 8 == 0 and cout % 8 == 0:
         return N.conv3d_tc(x, w, bias, 1, (1, 1, 1), cout, residual, out_dtype, rl, out=out)
     return N.conv3d_direct(x, w, bias, 1, (1, 1, 1), cout, residual, (1, 1, 1), out_dtype, rl, out=out)
 

@@ -74,10 +74,11 @@ int hyvae_conv3d_causal_direct(const hyvae_vol* x, const void* w, const float* b
                                int32_t up_t, int32_t up_h, int32_t up_w, int32_t round_like_ref, void* stream);
 int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
                            const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
-                           int32_t round_like_ref, int32_t variant, float* gn_partials, int32_t gn_groups, void* stream);
-/* rows-per-batch of the gn_partials buffer the call above fills for output volume y:
- * gn_partials is [B][rows][gn_groups][2] fp32 (see hyvae_groupnorm_finalize). */
-int64_t hyvae_conv3d_tc_gn_rows(const hyvae_vol* y, int32_t sh, int32_t sw);
+                           int32_t round_like_ref, int32_t variant, double* gn_partials, int32_t gn_groups, void* stream);
+/* rows-per-batch of the gn_partials buffer: gn_partials is [B][rows][gn_groups][2] fp64, ZEROED by the caller; every
+ * (CTA, warp) of the conv accumulates into its own row, so several launches may add into one buffer (the phases of
+ * an upsampling conv) before hyvae_groupnorm_finalize reduces the rows in a fixed order. */
+int64_t hyvae_conv3d_tc_gn_rows(void);
 
 /* ---- GroupNorm (+SiLU) -------------------------------------------------------------------------
  * Replaces nn.GroupNorm(32,C,eps=1e-6) + SiLU, unet_causal_3d_blocks.py:359-363,401-405 and
@@ -92,10 +93,10 @@ int hyvae_groupnorm_stats(const hyvae_vol* x, int32_t groups, double* sums, void
 int hyvae_groupnorm_apply(const hyvae_vol* x, const double* sums, const float* gamma, const float* beta,
                           int32_t groups, float eps, int32_t silu, int32_t round_like_ref, const hyvae_vol* y,
                           void* stream);
-/* Statistics from the PRODUCER: hyvae_conv3d_causal_tc can emit per-tile partial sums of its own output
- * (gn_partials, [B][rows][groups][2] fp32 with rows = hyvae_conv3d_tc_gn_rows()); _finalize adds them in a fixed
- * order into `sums`, replacing the _stats pass over the tensor. */
-int hyvae_groupnorm_finalize(const float* partials, int32_t B, int64_t rows, int32_t groups, double* sums, void* stream);
+/* Statistics from the PRODUCER: hyvae_conv3d_causal_tc can emit partial sums of its own output (gn_partials,
+ * [B][rows][groups][2] fp64 with rows = hyvae_conv3d_tc_gn_rows()); _finalize adds the rows in a fixed order into
+ * `sums`, replacing the _stats pass over the tensor. */
+int hyvae_groupnorm_finalize(const double* partials, int32_t B, int64_t rows, int32_t groups, double* sums, void* stream);
 
 /* ---- pad / nearest upsample --------------------------------------------------------------------
  * Replaces F.pad(replicate) :74 and F.interpolate(nearest)+cat of UpsampleCausal3D.forward :152-171:

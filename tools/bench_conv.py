@@ -59,5 +59,9 @@ if __name__ == "__main__":
     conv_case(256, 128, 9, 256, 256)
     conv_case(128, 128, 9, 256, 256, stride=(1, 2, 2))
     conv_case(512, 512, 1, 1, 17408, k=1)
+    conv_case(8, 128, 9, 256, 256)      # encoder conv_in (3 -> 128, channels padded to 8)
+    conv_case(128, 8, 9, 256, 256)      # decoder conv_out (128 -> 3, Cout padded to 8)
+    conv_case(128, 128, 65, 256, 256)   # the real canonical-tile size (1.1 GB in, 1.1 GB out)
+    conv_case(256, 128, 65, 256, 256)
     gn_case(128, 17, 256, 256)
     gn_case(512, 17, 32, 32)
