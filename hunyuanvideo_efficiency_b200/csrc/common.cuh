@@ -41,7 +41,7 @@ inline int check_launch(const char* what) {
 // ---- optional per-kernel-class timing (CUDA events on the launching stream; bench.py's roofline leg) ----
 enum ProfClass { PC_CONV_TC = 0, PC_CONV_DIRECT, PC_GN_STATS, PC_GN_APPLY, PC_PAD_UPSAMPLE, PC_SOFTMAX, PC_LAYOUT, PC_BLEND,
                  PC_TEMPORAL, PC_COUNT };
-struct ProfRec { cudaEvent_t a, b; int cls; double work; };
+struct ProfRec { cudaEvent_t a, b; int cls; double work; char tag[56]; };
 extern bool g_prof_on;
 extern std::vector<ProfRec> g_prof;
 extern std::vector<cudaEvent_t> g_prof_pool;
@@ -54,8 +54,12 @@ inline cudaEvent_t prof_event() {
 // RAII: brackets the launches of one C-ABI call with two events.  `work` = algorithmic flops or bytes.
 struct ProfScope {
   bool on; cudaStream_t st; ProfRec r;
-  ProfScope(int cls, double work, void* stream) : on(g_prof_on), st((cudaStream_t)stream) {
-    if (on) { r.cls = cls; r.work = work; r.a = prof_event(); r.b = prof_event(); cudaEventRecord(r.a, st); }
+  ProfScope(int cls, double work, void* stream, const char* tag = "") : on(g_prof_on), st((cudaStream_t)stream) {
+    if (on) {
+      r.cls = cls; r.work = work; r.a = prof_event(); r.b = prof_event();
+      snprintf(r.tag, sizeof(r.tag), "%s", tag);
+      cudaEventRecord(r.a, st);
+    }
   }
   ~ProfScope() { if (on) { cudaEventRecord(r.b, st); g_prof.push_back(r); } }
 };

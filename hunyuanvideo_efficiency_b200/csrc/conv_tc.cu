@@ -191,6 +191,66 @@ __device__ __forceinline__ MTile decode_mtile(const TcArgs& a, int64_t mt) {
   return r;
 }
 
+// Epilogue of one 128-voxel m-tile x BN channels held by this CTA: TMEM -> registers -> +bias (+residual) ->
+// store, plus the optional GroupNorm partial statistics.  Called by the 4 epilogue warps (q = TMEM lane quarter).
+template <typename T, typename OT, int BN>
+__device__ __forceinline__ void epilogue_mtile(const TcArgs& a, const MTile& m, int q, int lane, uint32_t tmem_cols, int n0) {
+  const int row = q * 32 + lane;
+  OT* yd = reinterpret_cast<OT*>(a.y);
+  const T* rs = reinterpret_cast<const T*>(a.res);
+  const int h = m.h0 + row / a.TW, w = m.w0 + row % a.TW;
+  const bool valid = (h < a.Ho) && (w < a.Wo);
+  const int64_t yo = a.yoff + (int64_t)m.b * a.ysB + (int64_t)m.t * a.ysT + (int64_t)h * a.ysH + (int64_t)w * a.ysW;
+  const int64_t ro = a.roff + (int64_t)m.b * a.rsB + (int64_t)m.t * a.rsT + (int64_t)h * a.rsH + (int64_t)w * a.rsW;
+#pragma unroll 1
+  for (int j = 0; j < BN / 32; ++j) {
+    uint32_t v[32];
+    tmem_ld32(tmem_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+    const int nc = n0 + j * 32;
+    if (nc < a.Cout) {  // warp-uniform
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n = nc + g * 8;
+        if (n < a.Cout) {
+          if (a.bias) {
+            const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n);
+            const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n + 4);
+            f[g * 8 + 0] += b0.x; f[g * 8 + 1] += b0.y; f[g * 8 + 2] += b0.z; f[g * 8 + 3] += b0.w;
+            f[g * 8 + 4] += b1.x; f[g * 8 + 5] += b1.y; f[g * 8 + 6] += b1.z; f[g * 8 + 7] += b1.w;
+          }
+          if (rs && valid) {
+            Vec8<T> r; r.load(rs + ro + n);
+            float rf[8]; r.get(rf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[g * 8 + e] = (a.round_like_ref ? rnd<T>(f[g * 8 + e]) : f[g * 8 + e]) + rf[e];
+          }
+          if (valid) {
+            Vec8<OT> o; o.set(&f[g * 8]);
+            o.store(yd + yo + n);
+          }
+        }
+      }
+      if (a.gn_part) {
+        const int64_t prow = (int64_t)m.b * a.gn_rows + blockIdx.x * 4 + q;
+        double* dst = a.gn_part + (prow * a.gn_groups + nc / a.gn_cpg) * 2;
+        const int ng = (a.Cout - nc) / a.gn_cpg;
+        switch (a.gn_cpg) {
+          case 1: gn_chunk_stats<1>(f, valid, dst, lane, ng); break;
+          case 2: gn_chunk_stats<2>(f, valid, dst, lane, ng); break;
+          case 4: gn_chunk_stats<4>(f, valid, dst, lane, ng); break;
+          case 8: gn_chunk_stats<8>(f, valid, dst, lane, ng); break;
+          case 16: gn_chunk_stats<16>(f, valid, dst, lane, ng); break;
+          default: gn_chunk_stats<32>(f, valid, dst, lane, ng); break;
+        }
+      }
+    }
+  }
+}
+
 template <typename T, typename OT, int BN, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -285,9 +345,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ================= epilogue warps =================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    OT* yd = reinterpret_cast<OT*>(a.y);
-    const T* rs = reinterpret_cast<const T*>(a.res);
     int iter = 0;
     for (int64_t tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++iter) {
       const int acc = iter & 1;
@@ -301,57 +358,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int i = 0; i < MT; ++i) {
         const MTile m = decode_mtile(a, mg * MT + i);
         if (!m.valid) continue;  // warp-uniform
-        const int h = m.h0 + row / a.TW, w = m.w0 + row % a.TW;
-        const bool valid = (h < a.Ho) && (w < a.Wo);
-        const int64_t yo = a.yoff + (int64_t)m.b * a.ysB + (int64_t)m.t * a.ysT + (int64_t)h * a.ysH + (int64_t)w * a.ysW;
-        const int64_t ro = a.roff + (int64_t)m.b * a.rsB + (int64_t)m.t * a.rsT + (int64_t)h * a.rsH + (int64_t)w * a.rsW;
-#pragma unroll 1
-        for (int j = 0; j < BN / 32; ++j) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS + i * BN + j * 32), v);
-          tmem_ld_wait();
-          float f[32];
-#pragma unroll
-          for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
-          const int nc = n0 + j * 32;
-          if (nc < a.Cout) {  // warp-uniform
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int n = nc + g * 8;
-              if (n < a.Cout) {
-                if (a.bias) {
-                  const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n);
-                  const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n + 4);
-                  f[g * 8 + 0] += b0.x; f[g * 8 + 1] += b0.y; f[g * 8 + 2] += b0.z; f[g * 8 + 3] += b0.w;
-                  f[g * 8 + 4] += b1.x; f[g * 8 + 5] += b1.y; f[g * 8 + 6] += b1.z; f[g * 8 + 7] += b1.w;
-                }
-                if (rs && valid) {
-                  Vec8<T> r; r.load(rs + ro + n);
-                  float rf[8]; r.get(rf);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[g * 8 + e] = (a.round_like_ref ? rnd<T>(f[g * 8 + e]) : f[g * 8 + e]) + rf[e];
-                }
-                if (valid) {
-                  Vec8<OT> o; o.set(&f[g * 8]);
-                  o.store(yd + yo + n);
-                }
-              }
-            }
-            if (a.gn_part) {
-              const int64_t prow = (int64_t)m.b * a.gn_rows + blockIdx.x * 4 + q;
-              double* dst = a.gn_part + (prow * a.gn_groups + nc / a.gn_cpg) * 2;
-              const int ng = (a.Cout - nc) / a.gn_cpg;
-              switch (a.gn_cpg) {
-                case 1: gn_chunk_stats<1>(f, valid, dst, lane, ng); break;
-                case 2: gn_chunk_stats<2>(f, valid, dst, lane, ng); break;
-                case 4: gn_chunk_stats<4>(f, valid, dst, lane, ng); break;
-                case 8: gn_chunk_stats<8>(f, valid, dst, lane, ng); break;
-                case 16: gn_chunk_stats<16>(f, valid, dst, lane, ng); break;
-                default: gn_chunk_stats<32>(f, valid, dst, lane, ng); break;
-              }
-            }
-          }
-        }
+        epilogue_mtile<T, OT, BN>(a, m, q, lane, tmem_base + (uint32_t)(acc * Cfg::ACC_COLS + i * BN), n0);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar + 8 * acc);
@@ -363,6 +370,190 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------- 2-CTA (cta_group::2) kernel
+// A CTA pair (cluster of 2, the two SMs of a TPC) computes a 256-voxel x BN tile with ONE tcgen05.mma.cta_group::2 per
+// K=16 step, issued by the leader (cluster rank 0).  CTA r stages ITS m-tile (128 voxels, A operand) and rows
+// [r*BN/2, (r+1)*BN/2) of the weight tile (B operand): the weight traffic from L2 and the B reads of the MMA are
+// halved per SM compared to the 1-CTA kernel, and the smaller stage (16 KB + BN/2*128 B) allows a deeper TMA ring.
+// Protocol: every TMA of both CTAs signals the LEADER's full barrier (address with the peer bit cleared); the leader's
+// tcgen05.commit multicasts to the empty / tmem-full barriers of both CTAs; the epilogue warps of both CTAs arrive
+// on the leader's tmem-empty barrier.  Each CTA's epilogue reads its own TMEM (its 128 voxels x BN channels).
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even CTA of the pair
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t local_bar) {  // arrive on the barrier at the same offset in cluster rank 0
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(local_bar)
+      : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {  // arrives on `bar`'s offset in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_m256(int n, int ab_fmt) {
+  return (1u << 4) | ((uint32_t)ab_fmt << 7) | ((uint32_t)ab_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN> struct Tc2Cfg {
+  static constexpr int B_STAGE_BYTES = (BN / 2) * 64 * 2;            // this CTA's half of the weight tile
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // per CTA
+  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 10 ? 10 : STAGES_RAW;
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <typename T, typename OT, int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  using Cfg = Tc2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t bars = sB + STAGES * Cfg::B_STAGE_BYTES;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
+  const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
+  const uint32_t tmem_slot = tempty_bar + 16;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 2); mbar_init(empty_bar + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 256); }
+    fence_barrier_init();
+  }
+  cluster_sync_all();  // both CTAs' barriers exist before anything remote touches them
+  if (warp == 1) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();  // TMEM of BOTH CTAs is allocated before the leader's first MMA can write it
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int taps = a.k * a.k * a.k;
+  const int kchunks = (a.Cin + 63) / 64;
+  const int num_kb = taps * kchunks;
+  const int64_t pair0 = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer (both CTAs) =================
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t tile = pair0; tile < a.total_tiles; tile += npairs) {
+        const int nt = (int)(tile % a.n_tiles);
+        const int64_t mg = tile / a.n_tiles;
+        const int n0 = nt * BN + (int)rank * (BN / 2);
+        const MTile m = decode_mtile(a, mg * 2 + rank);
+        for (int tap = 0; tap < taps; ++tap) {
+          const int kt = tap / (a.k * a.k), kh = (tap / a.k) % a.k, kw = tap % a.k;
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+            if (leader) mbar_expect_tx(full_bar + 8 * stage, 2 * Cfg::STAGE_BYTES);  // bytes of both CTAs land on this barrier
+            tma_load_5d_2sm(sA + stage * A_STAGE_BYTES, &tmA, full_bar + 8 * stage, kc * 64,
+                            m.w0 * a.sw + kw, m.h0 * a.sh + kh, m.t * a.st + kt, m.b);
+            tma_load_3d_2sm(sB + stage * Cfg::B_STAGE_BYTES, &tmB, full_bar + 8 * stage, kc * 64, n0, tap);
+            if (!leader) mbar_arrive_leader(full_bar + 8 * stage);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ================= MMA issuer (leader CTA only) =================
+      constexpr uint32_t idesc = make_idesc_m256(BN, TcFmt<T>::fmt);
+      int stage = 0; uint32_t phase = 0;
+      int iter = 0;
+      for (int64_t tile = pair0; tile < a.total_tiles; tile += npairs, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t adesc = make_kmajor_sw128_desc(sA + stage * A_STAGE_BYTES);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sB + stage * Cfg::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          umma_commit_2sm(empty_bar + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(tfull_bar + 8 * acc);
+      }
+    }
+  } else {
+    // ================= epilogue warps (both CTAs, own TMEM) =================
+    const int q = warp & 3;
+    int iter = 0;
+    for (int64_t tile = pair0; tile < a.total_tiles; tile += npairs, ++iter) {
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      const int nt = (int)(tile % a.n_tiles);
+      const int64_t mg = tile / a.n_tiles;
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      const MTile m = decode_mtile(a, mg * 2 + rank);
+      if (m.valid) epilogue_mtile<T, OT, BN>(a, m, q, lane, tmem_base + (uint32_t)(acc * BN), nt * BN);
+      tc_fence_before();
+      if (leader) mbar_arrive(tempty_bar + 8 * acc);
+      else mbar_arrive_leader(tempty_bar + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // no CTA of the pair exits (or frees TMEM) while the other may still signal it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -394,6 +585,21 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArg
   int64_t grid = a.total_tiles < num_sms() ? a.total_tiles : num_sms();
   conv_tc_kernel<T, OT, BN, MT><<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, a);
   return check_launch("conv3d_causal_tc");
+}
+
+template <typename T, typename OT, int BN>
+static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
+  using Cfg = Tc2Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_tc2_kernel<T, OT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+      return fail(HYVAE_ECUDA, "conv_tc2: cannot opt in to %d bytes of shared memory", Cfg::SMEM_BYTES);
+    attr_set = true;
+  }
+  const int64_t max_pairs = num_sms() / 2;
+  const int64_t pairs = a.total_tiles < max_pairs ? a.total_tiles : max_pairs;
+  conv_tc2_kernel<T, OT, BN><<<(unsigned)(2 * pairs), TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, a);
+  return check_launch("conv3d_causal_tc (2-CTA)");
 }
 
 }  // namespace hyvae
@@ -461,8 +667,10 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
     a.gn_cpg = y->C / gn_groups;
     HYVAE_CHECK_ARG(a.gn_cpg <= 32 && (a.gn_cpg & (a.gn_cpg - 1)) == 0, "fused GroupNorm statistics need Cout/groups in {1,2,4,8,16,32} (got %d)", a.gn_cpg);
   }
-  // two m-tiles per CTA tile for the narrow-N layers once there is enough work to fill the chip (variant 1 forces MT=1)
-  const int MT = (BN <= 128 && a.m_tiles >= 2 * (int64_t)num_sms() && variant != 1) ? 2 : 1;
+  // variant: 0 = auto (CTA-pair kernel whenever there are >= 2 m-tiles), 1 = 1-CTA kernel with MT=1, 2 = 1-CTA kernel
+  const bool two_cta = (variant == 0) && a.m_tiles >= 2 && BN >= 64;
+  // 1-CTA kernel: two m-tiles per CTA tile for the narrow-N layers once there is enough work to fill the chip
+  const int MT = two_cta ? 2 : ((BN <= 128 && a.m_tiles >= 2 * (int64_t)num_sms() && variant != 1) ? 2 : 1);
   a.total_tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;
 
   const CUtensorMapDataType dt = x->dtype == HYVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -479,14 +687,17 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
   {
     cuuint64_t dims[3] = {(cuuint64_t)x->C, (cuuint64_t)y->C, (cuuint64_t)(k * k * k)};
     cuuint64_t strides[2] = {(cuuint64_t)x->C * 2, (cuuint64_t)x->C * y->C * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)(two_cta ? BN / 2 : BN), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&tmB, dt, 3, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(B) failed with %d", (int)r);
   }
   cudaStream_t s = (cudaStream_t)stream;
-  ProfScope prof(PC_CONV_TC, 2.0 * (double)y->B * y->T * y->H * y->W * y->C * x->C * k * k * k, stream);
+  char tag[56];
+  snprintf(tag, sizeof(tag), "k%d %d->%d %dx%dx%dx%d s%d%d%d BN%d %s%d", k, x->C, y->C, y->B, y->T, y->H, y->W, st, sh, sw, BN,
+           two_cta ? "2cta" : "MT", MT);
+  ProfScope prof(PC_CONV_TC, 2.0 * (double)y->B * y->T * y->H * y->W * y->C * x->C * k * k * k, stream, tag);
 #define HYVAE_TC_LAUNCH(T, OT)                                                                              \
   switch (BN) {                                                                                             \
     case 256: return launch_tc<T, OT, 256, 1>(tmA, tmB, a, s);                                              \
@@ -495,6 +706,20 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
     default: return MT == 2 ? launch_tc<T, OT, 32, 2>(tmA, tmB, a, s) : launch_tc<T, OT, 32, 1>(tmA, tmB, a, s);    \
   }
   const bool f32out = (y->dtype == HYVAE_F32);
+#define HYVAE_TC2_LAUNCH(T, OT)                                   \
+  switch (BN) {                                                   \
+    case 256: return launch_tc2<T, OT, 256>(tmA, tmB, a, s);      \
+    case 128: return launch_tc2<T, OT, 128>(tmA, tmB, a, s);      \
+    default: return launch_tc2<T, OT, 64>(tmA, tmB, a, s);        \
+  }
+  if (two_cta) {
+    if (x->dtype == HYVAE_BF16) {
+      if (f32out) { HYVAE_TC2_LAUNCH(__nv_bfloat16, float) } else { HYVAE_TC2_LAUNCH(__nv_bfloat16, __nv_bfloat16) }
+    } else {
+      if (f32out) { HYVAE_TC2_LAUNCH(__half, float) } else { HYVAE_TC2_LAUNCH(__half, __half) }
+    }
+  }
+#undef HYVAE_TC2_LAUNCH
   if (x->dtype == HYVAE_BF16) {
     if (f32out) { HYVAE_TC_LAUNCH(__nv_bfloat16, float) } else { HYVAE_TC_LAUNCH(__nv_bfloat16, __nv_bfloat16) }
   } else {

@@ -3,6 +3,8 @@
 // All are coalesced, 16-byte vectorised along the channel (or W) axis, and written in the "gather"
 // form: one thread per DESTINATION element, source index by clamping — which is what turns the
 // reference's F.pad(replicate) copies (unet_causal_3d_blocks.py:74) into index arithmetic.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hyvae {
@@ -417,13 +419,18 @@ int hyvae_profile_end(double* ms, double* work, int64_t* launches, int32_t n_cla
   HYVAE_CHECK_ARG(ms && work && launches && n_classes >= PC_COUNT, "profile_end needs %d classes", (int)PC_COUNT);
   for (int i = 0; i < n_classes; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }
   if (!g_prof.empty() && cudaEventSynchronize(g_prof.back().b) != cudaSuccess) return fail(HYVAE_ECUDA, "profile: event sync failed");
+  FILE* dump = nullptr;
+  if (const char* path = getenv("HYVAE_PROFILE_DUMP")) dump = fopen(path, "w");
+  if (dump) fprintf(dump, "class,tag,work,ms\n");
   for (auto& r : g_prof) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return fail(HYVAE_ECUDA, "profile: elapsed time failed");
     ms[r.cls] += t; work[r.cls] += r.work; launches[r.cls] += 1;
+    if (dump) fprintf(dump, "%d,%s,%.6g,%.6f\n", r.cls, r.tag, r.work, t);
     g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
   }
   g_prof.clear();
+  if (dump) fclose(dump);
   return HYVAE_OK;
 }
 

@@ -185,6 +185,27 @@ def test_tc_thin_layers_and_fused_gn_stats():
     assert O.rel_err(ref3, y3.to_ncthw().float().cpu()) < 2e-3
 
 
+@pytest.mark.parametrize("Cin,Cout,T,H,W,stride", [(128, 128, 9, 64, 64, (1, 1, 1)), (256, 256, 5, 40, 72, (1, 1, 1)),
+                                                   (512, 512, 3, 18, 32, (1, 1, 1)), (128, 256, 9, 36, 64, (2, 2, 2)),
+                                                   (128, 64, 3, 8, 24, (1, 1, 1))])
+def test_tc_cta_pair_kernel_matches_single_cta_kernel(Cin, Cout, T, H, W, stride):
+    """variant 0 (cta_group::2 pair kernel, many tiles per pair, odd tile counts) vs variant 2 (1-CTA kernel)."""
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    x, w, b = _rand_case(1, Cin, Cout, T, H, W, 21)
+    xv = _vol(x.half(), pad=(2, 1, 1))
+    wp = _pack(w.half(), torch.float16)
+    r = N.Vol(1, *N.conv_out_dims(T, H, W, stride), Cout, torch.float16, _dev())
+    r.t.normal_()
+    ys = [N.conv3d_tc(xv, wp, b.to(_dev()), 3, stride, Cout, residual=r, variant=v, gn_groups=32) for v in (0, 2, 0)]
+    assert torch.equal(ys[0].t, ys[2].t)                                    # reproducible
+    assert O.rel_err(ys[1].t.float().cpu(), ys[0].t.float().cpu()) < 1e-3   # same math, fp16 storage
+    assert torch.allclose(ys[0].gn_sums, ys[1].gn_sums, rtol=1e-5, atol=1e-3)
+    ref = O.causal_conv3d(x.half().float(), w.half().float(), b, stride) + r.to_ncthw().float().cpu()
+    assert O.rel_err(ref, ys[0].to_ncthw().float().cpu()) < 2e-3
+
+
 def test_tc_gemm_k1_residual_and_fp16():
     N = _N()
     if not N.device_supports_tc():
