@@ -433,27 +433,37 @@ __host__ __device__ constexpr uint32_t make_idesc_m256(int n, int ab_fmt) {
   return (1u << 4) | ((uint32_t)ab_fmt << 7) | ((uint32_t)ab_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
-template <int BN> struct Tc2Cfg {
-  static constexpr int B_STAGE_BYTES = (BN / 2) * 64 * 2;            // this CTA's half of the weight tile
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // per CTA
-  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 10 ? 10 : STAGES_RAW;
+// KHT ("kh trick", stride-1 3x3x3 convs): the tile is 16 rows x 8 columns of one frame, and ONE A stage holds the
+// 18-row halo {64 ch, 8 w, 18 h} of a (kt, kw, channel-chunk) group.  Each h-row is 8 voxels = exactly one 1024-byte
+// SWIZZLE_128B atom, so the A operand of tap kh is the same stage at byte offset kh*1024 — still atom aligned.  One
+// A load then feeds the three kh taps (3 B stages): A traffic from L2 drops 2.7x, which is what the Cout=128 layers
+// (half the MACs per A byte) need to leave the L2-bandwidth bound.  A and B run in separate TMA rings.
+template <int BN, bool KHT> struct Tc2Cfg {
+  static constexpr int NSUB = KHT ? 3 : 1;                            // B stages (taps) consumed per A stage
+  static constexpr int A_BYTES = KHT ? 18 * 1024 : A_STAGE_BYTES;
+  static constexpr int B_STAGE_BYTES = (BN / 2) * 64 * 2;             // this CTA's half of the weight tile
+  static constexpr int SA = KHT ? 3 : 0;                              // A ring depth (KHT); non-KHT shares the B ring index
+  static constexpr int BUDGET = 200 * 1024;
+  static constexpr int SB_RAW = KHT ? (BUDGET - SA * A_BYTES) / B_STAGE_BYTES : BUDGET / (A_BYTES + B_STAGE_BYTES);
+  static constexpr int SB = SB_RAW > 12 ? 12 : SB_RAW;
+  static constexpr int NA = KHT ? SA : SB;                            // number of A buffers
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = NA * A_BYTES + SB * B_STAGE_BYTES + 1024 + 512;
 };
 
-template <typename T, typename OT, int BN>
+template <typename T, typename OT, int BN, bool KHT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-  using Cfg = Tc2Cfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  using Cfg = Tc2Cfg<BN, KHT>;
+  constexpr int SB = Cfg::SB, NA = Cfg::NA, NSUB = Cfg::NSUB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
-  const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
-  const uint32_t bars = sB + STAGES * Cfg::B_STAGE_BYTES;
-  const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
-  const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
+  const uint32_t sB = smem_base + NA * Cfg::A_BYTES;
+  const uint32_t bars = sB + SB * Cfg::B_STAGE_BYTES;
+  const uint32_t bfull_bar = bars, bempty_bar = bars + 8 * SB;
+  const uint32_t afull_bar = bars + 16 * SB, aempty_bar = afull_bar + 8 * NA;  // used by KHT only
+  const uint32_t tfull_bar = aempty_bar + 8 * NA, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
@@ -465,7 +475,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 2); mbar_init(empty_bar + 8 * s, 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(bfull_bar + 8 * s, 2); mbar_init(bempty_bar + 8 * s, 1); }
+    for (int s = 0; s < NA; ++s) { mbar_init(afull_bar + 8 * s, 2); mbar_init(aempty_bar + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 256); }
     fence_barrier_init();
   }
@@ -476,30 +487,43 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int taps = a.k * a.k * a.k;
   const int kchunks = (a.Cin + 63) / 64;
-  const int num_kb = taps * kchunks;
+  // groups per tile: KHT -> (kt, kw, chunk) with the 3 kh taps inside; otherwise (tap, chunk)
+  const int ngroups = (KHT ? 9 : a.k * a.k * a.k) * kchunks;
   const int64_t pair0 = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
   if (warp == 0) {
     if (lane == 0) {
       // ================= TMA producer (both CTAs) =================
-      int stage = 0; uint32_t phase = 0;
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       for (int64_t tile = pair0; tile < a.total_tiles; tile += npairs) {
         const int nt = (int)(tile % a.n_tiles);
         const int64_t mg = tile / a.n_tiles;
         const int n0 = nt * BN + (int)rank * (BN / 2);
         const MTile m = decode_mtile(a, mg * 2 + rank);
-        for (int tap = 0; tap < taps; ++tap) {
-          const int kt = tap / (a.k * a.k), kh = (tap / a.k) % a.k, kw = tap % a.k;
-          for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-            if (leader) mbar_expect_tx(full_bar + 8 * stage, 2 * Cfg::STAGE_BYTES);  // bytes of both CTAs land on this barrier
-            tma_load_5d_2sm(sA + stage * A_STAGE_BYTES, &tmA, full_bar + 8 * stage, kc * 64,
-                            m.w0 * a.sw + kw, m.h0 * a.sh + kh, m.t * a.st + kt, m.b);
-            tma_load_3d_2sm(sB + stage * Cfg::B_STAGE_BYTES, &tmB, full_bar + 8 * stage, kc * 64, n0, tap);
-            if (!leader) mbar_arrive_leader(full_bar + 8 * stage);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        for (int g = 0; g < ngroups; ++g) {
+          const int kc = g % kchunks, tg = g / kchunks;
+          int kt, kh0, kw;
+          if (KHT) { kt = tg / 3; kw = tg % 3; kh0 = 0; }
+          else { kt = tg / (a.k * a.k); kh0 = (tg / a.k) % a.k; kw = tg % a.k; }
+          if (KHT) {
+            mbar_wait(aempty_bar + 8 * sa, pa ^ 1);
+            if (leader) mbar_expect_tx(afull_bar + 8 * sa, 2 * Cfg::A_BYTES);
+            tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull_bar + 8 * sa, kc * 64, m.w0 + kw, m.h0, m.t + kt, m.b);
+            if (!leader) mbar_arrive_leader(afull_bar + 8 * sa);
+            if (++sa == NA) { sa = 0; pa ^= 1; }
+          }
+#pragma unroll
+          for (int sub = 0; sub < NSUB; ++sub) {
+            const int kh = kh0 + sub;
+            mbar_wait(bempty_bar + 8 * sb, pb ^ 1);
+            if (leader) mbar_expect_tx(bfull_bar + 8 * sb, 2 * (Cfg::B_STAGE_BYTES + (KHT ? 0 : Cfg::A_BYTES)));
+            if (!KHT)
+              tma_load_5d_2sm(sA + sb * Cfg::A_BYTES, &tmA, bfull_bar + 8 * sb, kc * 64,
+                              m.w0 * a.sw + kw, m.h0 * a.sh + kh, m.t * a.st + kt, m.b);
+            tma_load_3d_2sm(sB + sb * Cfg::B_STAGE_BYTES, &tmB, bfull_bar + 8 * sb, kc * 64, n0, (kt * a.k + kh) * a.k + kw);
+            if (!leader) mbar_arrive_leader(bfull_bar + 8 * sb);
+            if (++sb == SB) { sb = 0; pb ^= 1; }
           }
         }
       }
@@ -508,7 +532,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0 && leader) {
       // ================= MMA issuer (leader CTA only) =================
       constexpr uint32_t idesc = make_idesc_m256(BN, TcFmt<T>::fmt);
-      int stage = 0; uint32_t phase = 0;
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       int iter = 0;
       for (int64_t tile = pair0; tile < a.total_tiles; tile += npairs, ++iter) {
         const int acc = iter & 1;
@@ -516,16 +540,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar + 8 * stage, phase);
-          tc_fence_after();
-          const uint64_t adesc = make_kmajor_sw128_desc(sA + stage * A_STAGE_BYTES);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sB + stage * Cfg::B_STAGE_BYTES);
+        for (int g = 0; g < ngroups; ++g) {
+          if (KHT) { mbar_wait(afull_bar + 8 * sa, pa); }
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-          umma_commit_2sm(empty_bar + 8 * stage);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          for (int sub = 0; sub < NSUB; ++sub) {
+            mbar_wait(bfull_bar + 8 * sb, pb);
+            tc_fence_after();
+            // KHT: tap kh reads the halo stage 8 rows (= 1024 B, one swizzle atom) further down
+            const uint64_t adesc = make_kmajor_sw128_desc(KHT ? sA + sa * Cfg::A_BYTES + sub * 1024 : sA + sb * Cfg::A_BYTES);
+            const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * Cfg::B_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (g | sub | k) != 0);
+            umma_commit_2sm(bempty_bar + 8 * sb);
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+          if (KHT) {
+            umma_commit_2sm(aempty_bar + 8 * sa);
+            if (++sa == NA) { sa = 0; pa ^= 1; }
+          }
         }
         umma_commit_2sm(tfull_bar + 8 * acc);
       }
@@ -587,18 +620,18 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArg
   return check_launch("conv3d_causal_tc");
 }
 
-template <typename T, typename OT, int BN>
+template <typename T, typename OT, int BN, bool KHT>
 static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
-  using Cfg = Tc2Cfg<BN>;
+  using Cfg = Tc2Cfg<BN, KHT>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_tc2_kernel<T, OT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_tc2_kernel<T, OT, BN, KHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
       return fail(HYVAE_ECUDA, "conv_tc2: cannot opt in to %d bytes of shared memory", Cfg::SMEM_BYTES);
     attr_set = true;
   }
   const int64_t max_pairs = num_sms() / 2;
   const int64_t pairs = a.total_tiles < max_pairs ? a.total_tiles : max_pairs;
-  conv_tc2_kernel<T, OT, BN><<<(unsigned)(2 * pairs), TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, a);
+  conv_tc2_kernel<T, OT, BN, KHT><<<(unsigned)(2 * pairs), TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, a);
   return check_launch("conv3d_causal_tc (2-CTA)");
 }
 
@@ -656,8 +689,18 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
   a.k = k; a.st = st; a.sh = sh; a.sw = sw; a.round_like_ref = round_like_ref;
 
   pick_tile(y->H, y->W, sh, sw, &a.TH, &a.TW);
+  // variant: 0 = auto, 1 = 1-CTA kernel with MT=1, 2 = 1-CTA kernel, 3 = CTA-pair kernel without the kh trick
+  const int BN_sel = y->C > 128 ? 256 : (y->C > 64 ? 128 : (y->C > 32 ? 64 : 32));
+  bool kht = false;
+  if ((variant == 0) && k == 3 && st == 1 && sh == 1 && sw == 1 && BN_sel >= 64) {
+    // 16 x 8 tiles: accept up to 15 % more padded area than the best 128-voxel tile shape
+    const int64_t area_best = (int64_t)((y->H + a.TH - 1) / a.TH) * a.TH * ((y->W + a.TW - 1) / a.TW) * a.TW;
+    const int64_t area_kht = (int64_t)((y->H + 15) / 16) * 16 * ((y->W + 7) / 8) * 8;
+    const int64_t mt_kht = (int64_t)y->B * y->T * ((y->H + 15) / 16) * ((y->W + 7) / 8);
+    if (area_kht * 100 <= area_best * 115 && mt_kht >= 2) { kht = true; a.TH = 16; a.TW = 8; }
+  }
   a.tiles_h = (y->H + a.TH - 1) / a.TH; a.tiles_w = (y->W + a.TW - 1) / a.TW;
-  const int BN = y->C > 128 ? 256 : (y->C > 64 ? 128 : (y->C > 32 ? 64 : 32));
+  const int BN = BN_sel;
   a.n_tiles = (y->C + BN - 1) / BN;
   a.m_tiles = (int64_t)y->B * y->T * a.tiles_h * a.tiles_w;
   a.m_tiles_per_b = (int64_t)y->T * a.tiles_h * a.tiles_w;
@@ -668,7 +711,8 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
     HYVAE_CHECK_ARG(a.gn_cpg <= 32 && (a.gn_cpg & (a.gn_cpg - 1)) == 0, "fused GroupNorm statistics need Cout/groups in {1,2,4,8,16,32} (got %d)", a.gn_cpg);
   }
   // variant: 0 = auto (CTA-pair kernel whenever there are >= 2 m-tiles), 1 = 1-CTA kernel with MT=1, 2 = 1-CTA kernel
-  const bool two_cta = (variant == 0) && a.m_tiles >= 2 && BN >= 64;
+  const bool two_cta = (variant == 0 || variant == 3) && a.m_tiles >= 2 && BN >= 64;
+  if (!two_cta && kht) return fail(HYVAE_EINVAL, "internal: kh-trick tile shape chosen without the CTA-pair kernel");
   // 1-CTA kernel: two m-tiles per CTA tile for the narrow-N layers once there is enough work to fill the chip
   const int MT = two_cta ? 2 : ((BN <= 128 && a.m_tiles >= 2 * (int64_t)num_sms() && variant != 1) ? 2 : 1);
   a.total_tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;
@@ -678,7 +722,7 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
   {
     cuuint64_t dims[5] = {(cuuint64_t)x->C, (cuuint64_t)vx.Wp(), (cuuint64_t)vx.Hp(), (cuuint64_t)vx.Tp(), (cuuint64_t)x->B};
     cuuint64_t strides[4] = {(cuuint64_t)vx.sW * 2, (cuuint64_t)vx.sH * 2, (cuuint64_t)vx.sT * 2, (cuuint64_t)vx.sB * 2};
-    cuuint32_t box[5] = {64, (cuuint32_t)(a.TW * sw), (cuuint32_t)(a.TH * sh), 1, 1};
+    cuuint32_t box[5] = {64, (cuuint32_t)(a.TW * sw), (cuuint32_t)(kht ? a.TH + 2 : a.TH * sh), 1, 1};
     cuuint32_t estr[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1, 1};
     CUresult r = encode(&tmA, dt, 5, x->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -696,7 +740,7 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
   cudaStream_t s = (cudaStream_t)stream;
   char tag[56];
   snprintf(tag, sizeof(tag), "k%d %d->%d %dx%dx%dx%d s%d%d%d BN%d %s%d", k, x->C, y->C, y->B, y->T, y->H, y->W, st, sh, sw, BN,
-           two_cta ? "2cta" : "MT", MT);
+           two_cta ? (kht ? "2ctaK" : "2cta") : "MT", MT);
   ProfScope prof(PC_CONV_TC, 2.0 * (double)y->B * y->T * y->H * y->W * y->C * x->C * k * k * k, stream, tag);
 #define HYVAE_TC_LAUNCH(T, OT)                                                                              \
   switch (BN) {                                                                                             \
@@ -706,11 +750,11 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
     default: return MT == 2 ? launch_tc<T, OT, 32, 2>(tmA, tmB, a, s) : launch_tc<T, OT, 32, 1>(tmA, tmB, a, s);    \
   }
   const bool f32out = (y->dtype == HYVAE_F32);
-#define HYVAE_TC2_LAUNCH(T, OT)                                   \
-  switch (BN) {                                                   \
-    case 256: return launch_tc2<T, OT, 256>(tmA, tmB, a, s);      \
-    case 128: return launch_tc2<T, OT, 128>(tmA, tmB, a, s);      \
-    default: return launch_tc2<T, OT, 64>(tmA, tmB, a, s);        \
+#define HYVAE_TC2_LAUNCH(T, OT)                                                                                        \
+  switch (BN) {                                                                                                        \
+    case 256: return kht ? launch_tc2<T, OT, 256, true>(tmA, tmB, a, s) : launch_tc2<T, OT, 256, false>(tmA, tmB, a, s); \
+    case 128: return kht ? launch_tc2<T, OT, 128, true>(tmA, tmB, a, s) : launch_tc2<T, OT, 128, false>(tmA, tmB, a, s); \
+    default: return kht ? launch_tc2<T, OT, 64, true>(tmA, tmB, a, s) : launch_tc2<T, OT, 64, false>(tmA, tmB, a, s);    \
   }
   if (two_cta) {
     if (x->dtype == HYVAE_BF16) {

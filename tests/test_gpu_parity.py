@@ -198,10 +198,11 @@ def test_tc_cta_pair_kernel_matches_single_cta_kernel(Cin, Cout, T, H, W, stride
     wp = _pack(w.half(), torch.float16)
     r = N.Vol(1, *N.conv_out_dims(T, H, W, stride), Cout, torch.float16, _dev())
     r.t.normal_()
-    ys = [N.conv3d_tc(xv, wp, b.to(_dev()), 3, stride, Cout, residual=r, variant=v, gn_groups=32) for v in (0, 2, 0)]
+    ys = [N.conv3d_tc(xv, wp, b.to(_dev()), 3, stride, Cout, residual=r, variant=v, gn_groups=32) for v in (0, 2, 0, 3)]
     assert torch.equal(ys[0].t, ys[2].t)                                    # reproducible
-    assert O.rel_err(ys[1].t.float().cpu(), ys[0].t.float().cpu()) < 1e-3   # same math, fp16 storage
-    assert torch.allclose(ys[0].gn_sums, ys[1].gn_sums, rtol=1e-5, atol=1e-3)
+    for other in (ys[1], ys[3]):                                            # pair+kh-trick vs 1-CTA vs pair without kh-trick
+        assert O.rel_err(other.t.float().cpu(), ys[0].t.float().cpu()) < 1e-3
+        assert torch.allclose(ys[0].gn_sums, other.gn_sums, rtol=1e-5, atol=1e-3)
     ref = O.causal_conv3d(x.half().float(), w.half().float(), b, stride) + r.to_ncthw().float().cpu()
     assert O.rel_err(ref, ys[0].to_ncthw().float().cpu()) < 2e-3
 
