@@ -692,7 +692,11 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
   // variant: 0 = auto, 1 = 1-CTA kernel with MT=1, 2 = 1-CTA kernel, 3 = CTA-pair kernel without the kh trick
   const int BN_sel = y->C > 128 ? 256 : (y->C > 64 ? 128 : (y->C > 32 ? 64 : 32));
   bool kht = false;
-  if ((variant == 0) && k == 3 && st == 1 && sh == 1 && sw == 1 && BN_sel >= 64) {
+  // Cout <= 128: an N=128 MMA keeps the shared-memory port saturated with operand reads (A 4 KB + B per 64 cycles),
+  // and measured faster on the 1-CTA kernel with two m-tiles per weight tile than on the pair kernel (profiles/).
+  const int64_t mt_plain = (int64_t)y->B * y->T * ((y->H + a.TH - 1) / a.TH) * ((y->W + a.TW - 1) / a.TW);
+  const bool prefer_1cta = (variant == 0) && BN_sel <= 128 && mt_plain >= 2 * (int64_t)num_sms();
+  if ((variant == 0) && !prefer_1cta && k == 3 && st == 1 && sh == 1 && sw == 1 && BN_sel >= 64) {
     // 16 x 8 tiles: accept up to 15 % more padded area than the best 128-voxel tile shape
     const int64_t area_best = (int64_t)((y->H + a.TH - 1) / a.TH) * a.TH * ((y->W + a.TW - 1) / a.TW) * a.TW;
     const int64_t area_kht = (int64_t)((y->H + 15) / 16) * 16 * ((y->W + 7) / 8) * 8;
@@ -711,7 +715,7 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
     HYVAE_CHECK_ARG(a.gn_cpg <= 32 && (a.gn_cpg & (a.gn_cpg - 1)) == 0, "fused GroupNorm statistics need Cout/groups in {1,2,4,8,16,32} (got %d)", a.gn_cpg);
   }
   // variant: 0 = auto (CTA-pair kernel whenever there are >= 2 m-tiles), 1 = 1-CTA kernel with MT=1, 2 = 1-CTA kernel
-  const bool two_cta = (variant == 0 || variant == 3) && a.m_tiles >= 2 && BN >= 64;
+  const bool two_cta = ((variant == 0 && !prefer_1cta) || variant == 3) && a.m_tiles >= 2 && BN >= 64;
   if (!two_cta && kht) return fail(HYVAE_EINVAL, "internal: kh-trick tile shape chosen without the CTA-pair kernel");
   // 1-CTA kernel: two m-tiles per CTA tile for the narrow-N layers once there is enough work to fill the chip
   const int MT = two_cta ? 2 : ((BN <= 128 && a.m_tiles >= 2 * (int64_t)num_sms() && variant != 1) ? 2 : 1);
