@@ -200,6 +200,19 @@ def conv3d_direct(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, resi
     return y
 
 
+_GN_PART = {}
+
+
+def _gn_partials(B: int, rows: int, groups: int, device) -> torch.Tensor:
+    """[B][rows][groups][2] fp64 scratch for the conv epilogue's GroupNorm partial sums.  Zeroed once: every
+    hyvae_groupnorm_finalize leaves it zeroed again, and conv + finalize pairs are stream ordered."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream, B, rows, groups)
+    buf = _GN_PART.get(key)
+    if buf is None:
+        buf = _GN_PART[key] = torch.zeros((B, rows, groups, 2), dtype=torch.float64, device=device)
+    return buf
+
+
 def conv3d_tc(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, residual: Optional[Vol] = None,
               out_dtype=None, round_like_ref=True, variant=0, out: Optional[Vol] = None, gn_groups: int = 0) -> Vol:
     """gn_groups > 0: the epilogue also emits GroupNorm partial statistics of y; they are reduced here
@@ -209,7 +222,7 @@ def conv3d_tc(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, residual
     part, rows = None, 0
     if gn_groups > 0 and cout % gn_groups == 0 and (cout // gn_groups) in (1, 2, 4, 8, 16, 32):
         rows = int(lib().hyvae_conv3d_tc_gn_rows())
-        part = torch.zeros((x.B, rows, gn_groups, 2), dtype=torch.float64, device=x.device)
+        part = _gn_partials(x.B, rows, gn_groups, x.device)
     _check(lib().hyvae_conv3d_causal_tc(x.ref(), w.data_ptr(), _ptr(bias), residual.ref() if residual else None, y.ref(),
                                         k, stride[0], stride[1], stride[2], int(round_like_ref), variant,
                                         _ptr(part), gn_groups if part is not None else 0, _stream()),

@@ -1,0 +1,415 @@
+// Stride-1 3x3x3 CausalConv3d for Cout <= 128 on tcgen05/TMEM with a FULL 2-D halo stage in shared memory.
+//
+// Reference semantics: F.pad(replicate) + nn.Conv3d, unet_causal_3d_blocks.py:73-75 (+ residual :415).
+//
+// Why a second kernel: with N = Cout <= 128 an MMA of 128 voxels x 128 channels x K=16 lasts 64 cycles and reads
+// 8 KB of operands from shared memory, i.e. the tensor core already uses the whole shared-memory port; every byte
+// TMA writes into shared memory and every scattered global store of the epilogue competes with it
+// (profiles/r01_probe_conv.txt: 1.60 PFLOP/s with loads and epilogue disabled, 1.04 with them).  So this kernel
+//   * loads the A operand ONCE per (frame tap kt, 64-channel chunk): an 18-row x (8*MT+2)-column halo patch
+//     {64 ch, TWH, 18} that feeds all nine (kh, kw) taps of MT adjacent 16x8-voxel m-tiles.  Tap (kh, kw) of m-tile i
+//     is the same stage at byte offset (kh*PITCH + kw + 8*i)*128 with the 8-row-group stride (SBO) = PITCH*128:
+//     L2 -> SM operand traffic drops from 96 to ~41 B/clk/SM;
+//   * runs the epilogue through shared memory: TMEM -> registers -> (+bias, +residual tile fetched by TMA) ->
+//     swizzled staging rows -> one TMA store per warp and 64-channel half, instead of 32-way scattered 16-byte stores;
+//   * reduces the GroupNorm partial sums with a recursive-halving shuffle tree (16 instead of 80 shuffles per 32
+//     columns) and keeps the per-warp fp64 accumulators in registers until the batch item changes.
+// Roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+#include "conv_internal.h"
+#include "tcgen05.cuh"
+
+namespace hyvae {
+
+constexpr int HALO_THREADS = 192;
+
+template <int BN, int MT> struct HaloCfg {
+  static constexpr int TWH = 8 * MT + 2, THH = 18;                  // halo patch: columns x rows
+  static constexpr int PITCH = TWH;                                  // smem rows (of 128 B) per halo row: dense
+  static constexpr int A_TX = TWH * THH * 128;                      // bytes TMA delivers per A stage
+  static constexpr int A_BYTES = (A_TX + 1023) / 1024 * 1024;
+  static constexpr int TB = BN >= 128 ? 1 : 3;                       // (kh, kw) taps per B stage (9 % TB == 0)
+  static constexpr int B_TAP_BYTES = BN * 128;
+  static constexpr int B_BYTES = TB * B_TAP_BYTES;
+  static constexpr int NA = 2;
+  static constexpr int NH = (BN + 63) / 64;                          // 64-channel halves of the output tile
+  static constexpr int OUT_BYTES = NH * 16384;                       // one m-tile of output staging, reused by the MT m-tiles
+  static constexpr int BUDGET = 227 * 1024 - 2048;                   // minus alignment slack and barrier block
+  static constexpr int NB_RAW = (BUDGET - NA * A_BYTES - OUT_BYTES) / B_BYTES;
+  static constexpr int NB = NB_RAW > 8 ? 8 : NB_RAW;
+  static constexpr int ACC_COLS = MT * BN;
+  static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
+  static constexpr int SMEM_BYTES = NA * A_BYTES + NB * B_BYTES + OUT_BYTES + 2048;
+  static_assert(NB >= 3, "B ring too shallow");
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
+};
+
+// K-major SWIZZLE_128B descriptor with an arbitrary 8-row-group stride (SBO) and a start address that is only
+// 128-byte aligned.  The hardware applies the 128B swizzle to ABSOLUTE shared-memory address bits (measured: results are
+// bit-identical to the aligned kernels with the base-offset field left 0, and wrong with it set), so any row of a
+// TMA-written SWIZZLE_128B region may be row 0 of an operand, and 8-row groups may start at any row.
+__device__ __forceinline__ uint64_t make_halo_desc(uint32_t addr, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Sum V per-lane values over the 32 lanes with recursive halving: afterwards every lane holds the warp total of
+// value index lane * V / 32 (V - 1 + log2(32 / V) shuffles instead of 5 * V).  Fixed tree => bit-reproducible.
+template <int V>
+__device__ __forceinline__ float halving_reduce(float (&v)[V], int lane) {
+  int o = 16;
+#pragma unroll
+  for (int h = V / 2; h >= 1; h >>= 1, o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? v[i] : v[i + h];
+      const float keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+#pragma unroll
+  for (; o >= 1; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+  return v[0];
+}
+
+// GroupNorm partial of one 32-column chunk: per group of CPG channels (sum, sum of squares) over this warp's rows.
+template <int CPG>
+__device__ __forceinline__ float gn_chunk_reduce(const float* f, bool valid, int lane) {
+  constexpr int V = 2 * (32 / CPG);
+  float v[V];
+#pragma unroll
+  for (int g = 0; g < 32 / CPG; ++g) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) { const float u = valid ? f[g * CPG + c] : 0.f; s += u; q = fmaf(u, u, q); }
+    v[2 * g] = s; v[2 * g + 1] = q;
+  }
+  return halving_reduce<V>(v, lane);
+}
+
+struct HGroup { int b, t, h0, w0; };
+__device__ __forceinline__ HGroup decode_group(const HaloArgs& a, int64_t g, int mt_cols) {
+  HGroup r;
+  const int gw = (int)(g % a.groups_w); g /= a.groups_w;
+  const int th = (int)(g % a.tiles_h); g /= a.tiles_h;
+  r.t = (int)(g % a.To); r.b = (int)(g / a.To);
+  r.h0 = th * 16; r.w0 = gw * mt_cols;
+  return r;
+}
+
+template <typename T, int BN, int MT>
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const HaloArgs a) {
+  using Cfg = HaloCfg<BN, MT>;
+  constexpr int NA = Cfg::NA, NB = Cfg::NB, NH = Cfg::NH, PITCH = Cfg::PITCH, TB = Cfg::TB;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + NA * Cfg::A_BYTES;
+  const uint32_t sOut = sB + NB * Cfg::B_BYTES;
+  const uint32_t bars = sOut + Cfg::OUT_BYTES;
+  const uint32_t afull = bars, aempty = afull + 8 * NA;
+  const uint32_t bfull = aempty + 8 * NA, bempty = bfull + 8 * NB;
+  const uint32_t tfull = bempty + 8 * NB, tempty = tfull + 16;
+  const uint32_t rfull = tempty + 16;                       // [4 warps]
+  const uint32_t tmem_slot = rfull + 8 * 4;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY);
+    if (a.has_res) tma_prefetch_desc(&tmR);
+    for (int s = 0; s < NA; ++s) { mbar_init(afull + 8 * s, 1); mbar_init(aempty + 8 * s, 1); }
+    for (int s = 0; s < NB; ++s) { mbar_init(bfull + 8 * s, 1); mbar_init(bempty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + 8 * s, 1); mbar_init(tempty + 8 * s, 128); }
+    for (int s = 0; s < 4; ++s) mbar_init(rfull + 8 * s, 1);
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int kchunks = (a.Cin + 63) / 64;
+  const int steps_per_group = 3 * kchunks;  // (kt, kc)
+
+  if (warp == 0) {
+    {
+      // ================= TMA producer (warp-uniform loops, one elected lane issues) =================
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      int64_t afills = 0, bfills = 0;
+      auto issue_A = [&](int64_t g, int step) {
+        const HGroup m = decode_group(a, g, 8 * MT);
+        const int kt = step / kchunks, kc = step % kchunks;
+        mbar_wait(aempty + 8 * sa, pa ^ 1);
+        if (elect_one()) {
+          if ((a.probe & 1) && afills >= NA) {
+            mbar_arrive(afull + 8 * sa);
+          } else {
+            mbar_expect_tx(afull + 8 * sa, Cfg::A_TX);
+            tma_load_5d(sA + sa * Cfg::A_BYTES, &tmA, afull + 8 * sa, kc * 64, m.w0, m.h0, m.t + kt, m.b);
+          }
+        }
+        __syncwarp();
+        ++afills;
+        if (++sa == NA) { sa = 0; pa ^= 1; }
+      };
+      bool first = true;
+      for (int64_t g = blockIdx.x; g < a.total; g += gridDim.x) {
+        for (int step = 0; step < steps_per_group; ++step) {
+          if (first) { issue_A(g, step); first = false; }
+          const int kt = step / kchunks, kc = step % kchunks;
+#pragma unroll 1
+          for (int tg = 0; tg < 9 / TB; ++tg) {
+            if (tg == (9 / TB) / 2) {  // prefetch the next A halo while the MMA works through this one
+              if (step + 1 < steps_per_group) issue_A(g, step + 1);
+              else if (g + gridDim.x < a.total) issue_A(g + gridDim.x, 0);
+            }
+            mbar_wait(bempty + 8 * sb, pb ^ 1);
+            if (elect_one()) {
+              if ((a.probe & 1) && bfills >= NB) {
+                mbar_arrive(bfull + 8 * sb);
+              } else {
+                mbar_expect_tx(bfull + 8 * sb, Cfg::B_BYTES);
+                tma_load_3d(sB + sb * Cfg::B_BYTES, &tmB, bfull + 8 * sb, kc * 64, 0, kt * 9 + tg * TB);
+              }
+            }
+            __syncwarp();
+            ++bfills;
+            if (++sb == NB) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    {
+      // ================= MMA issuer (warp-uniform loops, one elected lane issues) =================
+      constexpr uint32_t idesc = make_idesc(BN, TcFmt<T>::fmt);
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      int iter = 0;
+      for (int64_t g = blockIdx.x; g < a.total; g += gridDim.x, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait(tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
+        for (int step = 0; step < steps_per_group; ++step) {
+          mbar_wait(afull + 8 * sa, pa);
+          const uint32_t a_stage = sA + sa * Cfg::A_BYTES;
+          // K = 16 slices that hold real channels in this 64-channel chunk (thin layers: conv_in has Cin = 8)
+          const int rem = a.Cin - (step % kchunks) * 64;
+          const int nk = rem >= 64 ? 4 : (rem + 15) / 16;
+#pragma unroll 1
+          for (int tg = 0; tg < 9 / TB; ++tg) {
+            mbar_wait(bfull + 8 * sb, pb);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int tt = 0; tt < TB; ++tt) {
+                const int tap9 = tg * TB + tt;
+                const int kh = tap9 / 3, kw = tap9 - 3 * kh;
+                const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * Cfg::B_BYTES + tt * Cfg::B_TAP_BYTES);
+#pragma unroll
+                for (int i = 0; i < MT; ++i) {
+                  const uint64_t adesc = make_halo_desc(a_stage + (uint32_t)((kh * PITCH + kw + 8 * i) * 128), PITCH * 128);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (k < nk) umma_f16(d_tmem + i * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (step | tap9 | k) != 0);
+                }
+              }
+              umma_commit(bempty + 8 * sb);
+            }
+            __syncwarp();
+            if (++sb == NB) { sb = 0; pb ^= 1; }
+          }
+          if (elect_one()) umma_commit(aempty + 8 * sa);
+          __syncwarp();
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+        }
+        if (elect_one()) umma_commit(tfull + 8 * acc);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp & 3;  // TMEM lane quarter = rows 32q .. 32q+31 of every m-tile = tile rows 4q .. 4q+3
+    const int hh = 4 * q + (lane >> 3), ww = lane & 7;
+    double gacc[BN / 32];
+#pragma unroll
+    for (int j = 0; j < BN / 32; ++j) gacc[j] = 0.0;
+    int gb = -1;       // batch item the accumulators belong to
+    uint32_t rph = 0;  // phase of this warp's residual barrier
+    const uint32_t rbar = rfull + 8 * q;
+    const uint32_t stage_w = sOut + q * 4096;  // this warp's 32 rows of the staging tile (per 64-channel half: + hf * 16384)
+    auto gn_flush = [&]() {
+      if (a.gn_part == nullptr || gb < 0) return;
+      const int V = 2 * (32 / a.gn_cpg);
+      const int per = 32 / V;  // lanes holding the same value
+      if (lane % per == 0) {
+        const int idx = lane / per;
+        double* row = a.gn_part + ((int64_t)gb * a.gn_rows + blockIdx.x * 4 + q) * a.gn_groups * 2;
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          const int grp = (32 * j) / a.gn_cpg + (idx >> 1);
+          if (grp < a.gn_groups) row[grp * 2 + (idx & 1)] += gacc[j];  // private slot: plain RMW
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < BN / 32; ++j) gacc[j] = 0.0;
+    };
+    int iter = 0;
+    for (int64_t g = blockIdx.x; g < a.total; g += gridDim.x, ++iter) {
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      const HGroup m = decode_group(a, g, 8 * MT);
+      if (m.b != gb) { gn_flush(); gb = m.b; }
+      // The staging rows of this warp are reused by every m-tile: they are free once the previous TMA stores have read
+      // them.  The residual tile of the first m-tile is fetched while the MMAs of this group are still running.
+      auto stage_acquire = [&](int i) {
+        if (lane == 0) {
+          bulk_wait_read0();
+          if (a.has_res) {
+            mbar_expect_tx(rbar, NH * 4096);
+#pragma unroll
+            for (int hf = 0; hf < NH; ++hf)
+              tma_load_5d(stage_w + hf * 16384, &tmR, rbar, hf * 64, m.w0 + 8 * i, m.h0 + 4 * q, m.t, m.b);
+          }
+        }
+        __syncwarp();
+      };
+      stage_acquire(0);
+      mbar_wait(tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const bool row_ok = (m.h0 + hh) < a.Ho;
+#pragma unroll 1
+      for (int i = 0; i < MT; ++i) {
+        if (m.w0 + 8 * i >= a.Wo || (a.probe & 4)) continue;  // warp-uniform
+        if (i > 0) stage_acquire(i);
+        const bool valid = row_ok && (m.w0 + 8 * i + ww) < a.Wo;
+        if (a.has_res) { mbar_wait(rbar, rph); rph ^= 1u; }
+        const uint32_t t_cols = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS + i * BN);
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          uint32_t v[32];
+          tmem_ld32(t_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+          const int nc = j * 32;
+          if (nc < a.Cout) {  // warp-uniform
+            const uint32_t srow = stage_w + (j >> 1) * 16384 + lane * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int n = nc + c * 8;
+              if (a.bias && n < a.Cout) {
+                const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n);
+                const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n + 4);
+                f[c * 8 + 0] += b0.x; f[c * 8 + 1] += b0.y; f[c * 8 + 2] += b0.z; f[c * 8 + 3] += b0.w;
+                f[c * 8 + 4] += b1.x; f[c * 8 + 5] += b1.y; f[c * 8 + 6] += b1.z; f[c * 8 + 7] += b1.w;
+              }
+              const uint32_t sa16 = srow + ((uint32_t)((((j & 1) * 4 + c) ^ (lane & 7))) << 4);
+              if (a.has_res) {
+                Vec8<T> r; r.v = lds128(sa16);
+                float rf[8]; r.get(rf);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[c * 8 + e] += rf[e];
+              }
+              Vec8<T> o; o.set(&f[c * 8]);
+              sts128(sa16, o.v);
+            }
+            if (a.gn_part) {
+              float r;
+              switch (a.gn_cpg) {
+                case 2: r = gn_chunk_reduce<2>(f, valid, lane); break;
+                case 4: r = gn_chunk_reduce<4>(f, valid, lane); break;
+                case 8: r = gn_chunk_reduce<8>(f, valid, lane); break;
+                case 16: r = gn_chunk_reduce<16>(f, valid, lane); break;
+                default: r = gn_chunk_reduce<32>(f, valid, lane); break;
+              }
+              gacc[j] += (double)r;
+            }
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int hf = 0; hf < NH; ++hf)
+            if (hf * 64 < a.Cout)
+              tma_store_5d(&tmY, stage_w + hf * 16384, hf * 64, m.w0 + 8 * i, m.h0 + 4 * q, m.t, m.b);
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty + 8 * acc);
+    }
+    gn_flush();
+    if (lane == 0) bulk_wait0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <typename T, int BN, int MT>
+static int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
+                         const HaloArgs& a, cudaStream_t stream) {
+  using Cfg = HaloCfg<BN, MT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_halo_kernel<T, BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+      return fail(HYVAE_ECUDA, "conv_halo: cannot opt in to %d bytes of shared memory", Cfg::SMEM_BYTES);
+    attr_set = true;
+  }
+  const int64_t grid = a.total < num_sms() ? a.total : num_sms();
+  conv_halo_kernel<T, BN, MT><<<(unsigned)grid, HALO_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, a);
+  return check_launch("conv3d_causal_tc (halo)");
+}
+
+void halo_geometry(int bn, int mt, int* twh, int* thh, int* taps_per_b) {
+  *twh = 8 * mt + 2; *thh = 18; *taps_per_b = bn >= 128 ? 1 : 3;
+}
+
+int launch_halo(int dtype, int bn, int mt, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+                const CUtensorMap& tmR, const HaloArgs& a, cudaStream_t stream) {
+#define HYVAE_HALO_CASE(T)                                                                          \
+  if (bn == 128 && mt == 2) return launch_halo_t<T, 128, 2>(tmA, tmB, tmY, tmR, a, stream);          \
+  if (bn == 64 && mt == 2) return launch_halo_t<T, 64, 2>(tmA, tmB, tmY, tmR, a, stream);            \
+  if (bn == 32 && mt == 2) return launch_halo_t<T, 32, 2>(tmA, tmB, tmY, tmR, a, stream);
+  if (dtype == HYVAE_BF16) { HYVAE_HALO_CASE(__nv_bfloat16) } else { HYVAE_HALO_CASE(__half) }
+#undef HYVAE_HALO_CASE
+  return fail(HYVAE_EUNSUPPORTED, "conv_halo: no instantiation for BN=%d MT=%d", bn, mt);
+}
+
+}  // namespace hyvae

@@ -1,0 +1,30 @@
+// Internal (non-ABI) declarations shared by the tensor-core convolution translation units.
+#pragma once
+
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace hyvae {
+
+template <typename T> struct TcFmt;
+template <> struct TcFmt<__nv_bfloat16> { static constexpr int fmt = 1; };
+template <> struct TcFmt<__half> { static constexpr int fmt = 0; };
+
+// conv_halo.cu: stride-1 3x3x3 conv, Cout <= 128, full 2-D halo stage (see the header of that file)
+struct HaloArgs {
+  const float* bias;
+  int B, To, Ho, Wo, Cin, Cout;
+  int tiles_h, groups_w;   // 16-row tiles, groups of MT 8-column m-tiles
+  int64_t total;           // B * To * tiles_h * groups_w
+  int has_res;
+  double* gn_part;         // optional [B][gn_rows][gn_groups][2]
+  int gn_groups, gn_cpg, gn_rows;
+  int probe;
+};
+
+void halo_geometry(int bn, int mt, int* twh, int* thh, int* taps_per_b);  // A box {64, twh, thh}; B box {64, bn, taps_per_b}
+int launch_halo(int dtype, int bn, int mt, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+                const CUtensorMap& tmR, const HaloArgs& a, cudaStream_t stream);
+
+}  // namespace hyvae

@@ -19,111 +19,13 @@
 //   with the n-tile fastest so concurrent CTAs share the A halo in L2.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
+#include "conv_internal.h"
+#include "tcgen05.cuh"
 
 namespace hyvae {
-
-// ---------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must trap, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("hyvae conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-template <int NCOLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(NCOLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int NCOLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
-//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) | [32,46) SBO >> 4 = 1024 B
-//   between 8-row core-matrix groups | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-// kind::f16 instruction descriptor: fp32 accumulate, A/B both K-major, M = 128.
-//   [4,6) D fmt (1 = f32) | [7,10) A fmt | [10,13) B fmt (0 = f16, 1 = bf16) | [17,23) N >> 3 | [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc(int n, int ab_fmt) {
-  return (1u << 4) | ((uint32_t)ab_fmt << 7) | ((uint32_t)ab_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
 
 // ---------------------------------------------------------------------------------- kernel
 struct TcArgs {
@@ -141,6 +43,7 @@ struct TcArgs {
   double* gn_part;      // optional [B][gn_rows][gn_groups][2] (sum, sum of squares) of the output; row = CTA * 4 + warp
   int gn_groups, gn_cpg, gn_rows;
   int64_t m_tiles_per_b;
+  int probe;            // measurement only (HYVAE_TC_PROBE): bit 0 = stop issuing TMA once the ring is primed, bit 1 = all loads hit tile 0, bit 2 = skip the epilogue
 };
 
 constexpr int TC_THREADS = 192;
@@ -160,9 +63,6 @@ template <int BN, int MT> struct TcCfg {
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
 };
 
-template <typename T> struct TcFmt;
-template <> struct TcFmt<__nv_bfloat16> { static constexpr int fmt = 1; };
-template <> struct TcFmt<__half> { static constexpr int fmt = 0; };
 
 // GroupNorm partial statistics of one 32-column chunk of the epilogue: per group of CPG channels, the sum and sum of
 // squares over this warp's 32 rows (fixed shuffle tree); lane 0 adds them to the fp64 slot that this (CTA, warp)
@@ -288,34 +188,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_kb = taps * kchunks;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================= TMA producer =================
+    {
+      // ================= TMA producer (warp-uniform loops, one elected lane issues; see elect_one) =================
       int stage = 0; uint32_t phase = 0;
+      int64_t fills = 0;
       for (int64_t tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int nt = (int)(tile % a.n_tiles);
         const int64_t mg = tile / a.n_tiles;
-        const int n0 = nt * BN;
+        const int n0 = (a.probe & 2) ? 0 : nt * BN;
         MTile m[MT];
 #pragma unroll
-        for (int i = 0; i < MT; ++i) m[i] = decode_mtile(a, mg * MT + i);
+        for (int i = 0; i < MT; ++i) m[i] = decode_mtile(a, (a.probe & 2) ? (int64_t)i : mg * MT + i);
         for (int tap = 0; tap < taps; ++tap) {
           const int kt = tap / (a.k * a.k), kh = (tap / a.k) % a.k, kw = tap % a.k;
-          for (int kc = 0; kc < kchunks; ++kc) {
+          for (int kc = 0; kc < kchunks; ++kc, ++fills) {
             mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-            mbar_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
+            if (elect_one()) {
+              if ((a.probe & 1) && fills >= STAGES) {
+                mbar_arrive(full_bar + 8 * stage);
+              } else {
+                mbar_expect_tx(full_bar + 8 * stage, Cfg::STAGE_BYTES);
 #pragma unroll
-            for (int i = 0; i < MT; ++i)
-              tma_load_5d(sA + stage * Cfg::A_BYTES + i * A_STAGE_BYTES, &tmA, full_bar + 8 * stage, kc * 64,
-                          m[i].w0 * a.sw + kw, m[i].h0 * a.sh + kh, m[i].t * a.st + kt, m[i].b);
-            tma_load_3d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, full_bar + 8 * stage, kc * 64, n0, tap);
+                for (int i = 0; i < MT; ++i)
+                  tma_load_5d(sA + stage * Cfg::A_BYTES + i * A_STAGE_BYTES, &tmA, full_bar + 8 * stage, kc * 64,
+                              m[i].w0 * a.sw + kw, m[i].h0 * a.sh + kh, m[i].t * a.st + kt, m[i].b);
+                tma_load_3d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, full_bar + 8 * stage, kc * 64, n0, tap);
+              }
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer =================
+    {
+      // ================= MMA issuer (warp-uniform loops, one elected lane issues) =================
       constexpr uint32_t idesc = make_idesc(BN, TcFmt<T>::fmt);
       int stage = 0; uint32_t phase = 0;
       int iter = 0;
@@ -328,18 +236,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
-          const uint64_t bdesc = make_kmajor_sw128_desc(sB + stage * Cfg::B_STAGE_BYTES);
+          if (elect_one()) {
+            const uint64_t bdesc = make_kmajor_sw128_desc(sB + stage * Cfg::B_STAGE_BYTES);
 #pragma unroll
-          for (int i = 0; i < MT; ++i) {
-            const uint64_t adesc = make_kmajor_sw128_desc(sA + stage * Cfg::A_BYTES + i * A_STAGE_BYTES);
+            for (int i = 0; i < MT; ++i) {
+              const uint64_t adesc = make_kmajor_sw128_desc(sA + stage * Cfg::A_BYTES + i * A_STAGE_BYTES);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)  // 4 x (K = 16) per 64-channel chunk: +32 B along K inside the swizzle atom
-              umma_f16(d_tmem + i * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+              for (int k = 0; k < 4; ++k)  // 4 x (K = 16) per 64-channel chunk: +32 B along K inside the swizzle atom
+                umma_f16(d_tmem + i * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            }
+            umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs have read it
           }
-          umma_commit(empty_bar + 8 * stage);  // frees the smem slot once these MMAs have read it
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else {
@@ -357,7 +269,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int i = 0; i < MT; ++i) {
         const MTile m = decode_mtile(a, mg * MT + i);
-        if (!m.valid) continue;  // warp-uniform
+        if (!m.valid || (a.probe & 4)) continue;  // warp-uniform
         epilogue_mtile<T, OT, BN>(a, m, q, lane, tmem_base + (uint32_t)(acc * Cfg::ACC_COLS + i * BN), n0);
       }
       tc_fence_before();
@@ -382,57 +294,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // Protocol: every TMA of both CTAs signals the LEADER's full barrier (address with the peer bit cleared); the leader's
 // tcgen05.commit multicasts to the empty / tmem-full barriers of both CTAs; the epilogue warps of both CTAs arrive
 // on the leader's tmem-empty barrier.  Each CTA's epilogue reads its own TMEM (its 128 voxels x BN channels).
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even CTA of the pair
-__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t local_bar) {  // arrive on the barrier at the same offset in cluster rank 0
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(local_bar)
-      : "memory");
-}
-template <int NCOLS>
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(NCOLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-template <int NCOLS>
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
-}
-__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {  // arrives on `bar`'s offset in both CTAs of the pair
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-__host__ __device__ constexpr uint32_t make_idesc_m256(int n, int ab_fmt) {
-  return (1u << 4) | ((uint32_t)ab_fmt << 7) | ((uint32_t)ab_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-}
-
 // KHT ("kh trick", stride-1 3x3x3 convs): the tile is 16 rows x 8 columns of one frame, and ONE A stage holds the
 // 18-row halo {64 ch, 8 w, 18 h} of a (kt, kw, channel-chunk) group.  Each h-row is 8 voxels = exactly one 1024-byte
 // SWIZZLE_128B atom, so the A operand of tap kh is the same stage at byte offset kh*1024 — still atom aligned.  One
@@ -493,14 +354,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int64_t pair0 = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================= TMA producer (both CTAs) =================
+    {
+      // ================= TMA producer (both CTAs; warp-uniform loops, one elected lane issues) =================
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      int64_t afills = 0, bfills = 0;
       for (int64_t tile = pair0; tile < a.total_tiles; tile += npairs) {
         const int nt = (int)(tile % a.n_tiles);
         const int64_t mg = tile / a.n_tiles;
-        const int n0 = nt * BN + (int)rank * (BN / 2);
-        const MTile m = decode_mtile(a, mg * 2 + rank);
+        const int n0 = ((a.probe & 2) ? 0 : nt * BN) + (int)rank * (BN / 2);
+        const MTile m = decode_mtile(a, (a.probe & 2) ? (int64_t)rank : mg * 2 + rank);
         for (int g = 0; g < ngroups; ++g) {
           const int kc = g % kchunks, tg = g / kchunks;
           int kt, kh0, kw;
@@ -508,29 +370,42 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           else { kt = tg / (a.k * a.k); kh0 = (tg / a.k) % a.k; kw = tg % a.k; }
           if (KHT) {
             mbar_wait(aempty_bar + 8 * sa, pa ^ 1);
-            if (leader) mbar_expect_tx(afull_bar + 8 * sa, 2 * Cfg::A_BYTES);
-            tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull_bar + 8 * sa, kc * 64, m.w0 + kw, m.h0, m.t + kt, m.b);
-            if (!leader) mbar_arrive_leader(afull_bar + 8 * sa);
+            const bool skip = (a.probe & 1) && afills >= NA;
+            ++afills;
+            if (elect_one()) {
+              if (leader) { if (skip) mbar_arrive(afull_bar + 8 * sa); else mbar_expect_tx(afull_bar + 8 * sa, 2 * Cfg::A_BYTES); }
+              if (!skip) tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull_bar + 8 * sa, kc * 64, m.w0 + kw, m.h0, m.t + kt, m.b);
+              if (!leader) mbar_arrive_leader(afull_bar + 8 * sa);
+            }
+            __syncwarp();
             if (++sa == NA) { sa = 0; pa ^= 1; }
           }
 #pragma unroll
           for (int sub = 0; sub < NSUB; ++sub) {
             const int kh = kh0 + sub;
             mbar_wait(bempty_bar + 8 * sb, pb ^ 1);
-            if (leader) mbar_expect_tx(bfull_bar + 8 * sb, 2 * (Cfg::B_STAGE_BYTES + (KHT ? 0 : Cfg::A_BYTES)));
-            if (!KHT)
-              tma_load_5d_2sm(sA + sb * Cfg::A_BYTES, &tmA, bfull_bar + 8 * sb, kc * 64,
-                              m.w0 * a.sw + kw, m.h0 * a.sh + kh, m.t * a.st + kt, m.b);
-            tma_load_3d_2sm(sB + sb * Cfg::B_STAGE_BYTES, &tmB, bfull_bar + 8 * sb, kc * 64, n0, (kt * a.k + kh) * a.k + kw);
-            if (!leader) mbar_arrive_leader(bfull_bar + 8 * sb);
+            const bool skipb = (a.probe & 1) && bfills >= SB;
+            ++bfills;
+            if (elect_one()) {
+              if (leader) {
+                if (skipb) mbar_arrive(bfull_bar + 8 * sb);
+                else mbar_expect_tx(bfull_bar + 8 * sb, 2 * (Cfg::B_STAGE_BYTES + (KHT ? 0 : Cfg::A_BYTES)));
+              }
+              if (!KHT && !skipb)
+                tma_load_5d_2sm(sA + sb * Cfg::A_BYTES, &tmA, bfull_bar + 8 * sb, kc * 64,
+                                m.w0 * a.sw + kw, m.h0 * a.sh + kh, m.t * a.st + kt, m.b);
+              if (!skipb) tma_load_3d_2sm(sB + sb * Cfg::B_STAGE_BYTES, &tmB, bfull_bar + 8 * sb, kc * 64, n0, (kt * a.k + kh) * a.k + kw);
+              if (!leader) mbar_arrive_leader(bfull_bar + 8 * sb);
+            }
+            __syncwarp();
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ================= MMA issuer (leader CTA only) =================
+    if (leader) {
+      // ================= MMA issuer (leader CTA only; warp-uniform loops, one elected lane issues) =================
       constexpr uint32_t idesc = make_idesc_m256(BN, TcFmt<T>::fmt);
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       int iter = 0;
@@ -546,21 +421,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int sub = 0; sub < NSUB; ++sub) {
             mbar_wait(bfull_bar + 8 * sb, pb);
             tc_fence_after();
-            // KHT: tap kh reads the halo stage 8 rows (= 1024 B, one swizzle atom) further down
-            const uint64_t adesc = make_kmajor_sw128_desc(KHT ? sA + sa * Cfg::A_BYTES + sub * 1024 : sA + sb * Cfg::A_BYTES);
-            const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * Cfg::B_STAGE_BYTES);
+            if (elect_one()) {
+              // KHT: tap kh reads the halo stage 8 rows (= 1024 B, one swizzle atom) further down
+              const uint64_t adesc = make_kmajor_sw128_desc(KHT ? sA + sa * Cfg::A_BYTES + sub * 1024 : sA + sb * Cfg::A_BYTES);
+              const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * Cfg::B_STAGE_BYTES);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (g | sub | k) != 0);
-            umma_commit_2sm(bempty_bar + 8 * sb);
+              for (int k = 0; k < 4; ++k)
+                umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (g | sub | k) != 0);
+              umma_commit_2sm(bempty_bar + 8 * sb);
+            }
+            __syncwarp();
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
           if (KHT) {
-            umma_commit_2sm(aempty_bar + 8 * sa);
+            if (elect_one()) umma_commit_2sm(aempty_bar + 8 * sa);
+            __syncwarp();
             if (++sa == NA) { sa = 0; pa ^= 1; }
           }
         }
-        umma_commit_2sm(tfull_bar + 8 * acc);
+        if (elect_one()) umma_commit_2sm(tfull_bar + 8 * acc);
+        __syncwarp();
       }
     }
   } else {
@@ -575,7 +455,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       const MTile m = decode_mtile(a, mg * 2 + rank);
-      if (m.valid) epilogue_mtile<T, OT, BN>(a, m, q, lane, tmem_base + (uint32_t)(acc * BN), nt * BN);
+      if (m.valid && !(a.probe & 4)) epilogue_mtile<T, OT, BN>(a, m, q, lane, tmem_base + (uint32_t)(acc * BN), nt * BN);
       tc_fence_before();
       if (leader) mbar_arrive(tempty_bar + 8 * acc);
       else mbar_arrive_leader(tempty_bar + 8 * acc);
@@ -687,6 +567,69 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
   }
   a.B = y->B; a.To = y->T; a.Ho = y->H; a.Wo = y->W; a.Cin = x->C; a.Cout = y->C;
   a.k = k; a.st = st; a.sh = sh; a.sw = sw; a.round_like_ref = round_like_ref;
+  { const char* pe = getenv("HYVAE_TC_PROBE"); a.probe = pe ? atoi(pe) : 0; }  // measurement only: results are garbage when set
+
+  // ---- halo kernel (conv_halo.cu): every stride-1 3x3x3 conv with Cout <= 128 and a 16-bit output (variant 5 forces it)
+  const bool halo_ok = k == 3 && st == 1 && sh == 1 && sw == 1 && y->C <= 128 && y->dtype == x->dtype &&
+                       (gn_partials == nullptr || (gn_groups > 0 && y->C % gn_groups == 0 && y->C / gn_groups >= 2));
+  if (variant == 5 || (variant == 0 && halo_ok)) {
+    HYVAE_CHECK_ARG(k == 3 && st == 1 && sh == 1 && sw == 1 && y->C <= 128 && y->dtype == x->dtype, "halo kernel: needs k=3, stride 1, Cout <= 128, 16-bit output");
+    const int bn = y->C > 64 ? 128 : (y->C > 32 ? 64 : 32), mt = 2;
+    int twh, thh, taps_per_b;
+    halo_geometry(bn, mt, &twh, &thh, &taps_per_b);
+    HaloArgs h;
+    h.bias = bias; h.B = y->B; h.To = y->T; h.Ho = y->H; h.Wo = y->W; h.Cin = x->C; h.Cout = y->C;
+    h.tiles_h = (y->H + 15) / 16; h.groups_w = (y->W + 8 * mt - 1) / (8 * mt);
+    h.total = (int64_t)y->B * y->T * h.tiles_h * h.groups_w;
+    h.has_res = residual != nullptr;
+    h.gn_part = gn_partials; h.gn_groups = gn_groups; h.gn_cpg = 0; h.gn_rows = num_sms() * 4; h.probe = a.probe;
+    if (gn_partials) {
+      HYVAE_CHECK_ARG(gn_groups > 0 && y->C % gn_groups == 0, "gn_groups=%d does not divide Cout=%d", gn_groups, y->C);
+      h.gn_cpg = y->C / gn_groups;
+      HYVAE_CHECK_ARG(h.gn_cpg >= 2 && h.gn_cpg <= 32 && (h.gn_cpg & (h.gn_cpg - 1)) == 0, "halo kernel: fused GroupNorm statistics need Cout/groups in {2,...,32} (got %d)", h.gn_cpg);
+    }
+    const CUtensorMapDataType dt = x->dtype == HYVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUtensorMap tmA, tmB, tmY, tmR;
+    {
+      cuuint64_t dims[5] = {(cuuint64_t)x->C, (cuuint64_t)vx.Wp(), (cuuint64_t)vx.Hp(), (cuuint64_t)vx.Tp(), (cuuint64_t)x->B};
+      cuuint64_t strides[4] = {(cuuint64_t)vx.sW * 2, (cuuint64_t)vx.sH * 2, (cuuint64_t)vx.sT * 2, (cuuint64_t)vx.sB * 2};
+      cuuint32_t box[5] = {64, (cuuint32_t)twh, (cuuint32_t)thh, 1, 1};
+      cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+      CUresult r = encode(&tmA, dt, 5, x->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(A halo) failed with %d", (int)r);
+    }
+    {
+      cuuint64_t dims[3] = {(cuuint64_t)x->C, (cuuint64_t)y->C, 27};
+      cuuint64_t strides[2] = {(cuuint64_t)x->C * 2, (cuuint64_t)x->C * y->C * 2};
+      cuuint32_t box[3] = {64, (cuuint32_t)bn, (cuuint32_t)taps_per_b};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = encode(&tmB, dt, 3, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+    }
+    auto out_map = [&](CUtensorMap* tm, const hyvae_vol* v, const Vol& vv) -> int {
+      cuuint64_t dims[5] = {(cuuint64_t)v->C, (cuuint64_t)v->W, (cuuint64_t)v->H, (cuuint64_t)v->T, (cuuint64_t)v->B};
+      cuuint64_t strides[4] = {(cuuint64_t)vv.sW * 2, (cuuint64_t)vv.sH * 2, (cuuint64_t)vv.sT * 2, (cuuint64_t)vv.sB * 2};
+      cuuint32_t box[5] = {64, 8, 4, 1, 1};
+      cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+      void* base = (char*)v->data + vv.at(0, 0, 0, 0) * 2;
+      CUresult r = encode(tm, dt, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      return r == CUDA_SUCCESS ? 0 : fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(out) failed with %d", (int)r);
+    };
+    if (int e = out_map(&tmY, y, vy)) return e;
+    if (residual) {
+      Vol vr = make_vol(residual);
+      if (int e = out_map(&tmR, residual, vr)) return e;
+    } else {
+      tmR = tmY;
+    }
+    char tag[56];
+    snprintf(tag, sizeof(tag), "k3 %d->%d %dx%dx%dx%d s111 BN%d halo", x->C, y->C, y->B, y->T, y->H, y->W, bn);
+    ProfScope prof(PC_CONV_TC, 2.0 * (double)y->B * y->T * y->H * y->W * y->C * x->C * 27, stream, tag);
+    return launch_halo(x->dtype, bn, mt, tmA, tmB, tmY, tmR, h, (cudaStream_t)stream);
+  }
 
   pick_tile(y->H, y->W, sh, sw, &a.TH, &a.TW);
   // variant: 0 = auto, 1 = 1-CTA kernel with MT=1, 2 = 1-CTA kernel, 3 = CTA-pair kernel without the kh trick
@@ -696,7 +639,7 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
   // and measured faster on the 1-CTA kernel with two m-tiles per weight tile than on the pair kernel (profiles/).
   const int64_t mt_plain = (int64_t)y->B * y->T * ((y->H + a.TH - 1) / a.TH) * ((y->W + a.TW - 1) / a.TW);
   const bool prefer_1cta = (variant == 0) && BN_sel <= 128 && mt_plain >= 2 * (int64_t)num_sms();
-  if ((variant == 0) && !prefer_1cta && k == 3 && st == 1 && sh == 1 && sw == 1 && BN_sel >= 64) {
+  if (((variant == 0 && !prefer_1cta) || variant == 4) && k == 3 && st == 1 && sh == 1 && sw == 1 && BN_sel >= 64) {
     // 16 x 8 tiles: accept up to 15 % more padded area than the best 128-voxel tile shape
     const int64_t area_best = (int64_t)((y->H + a.TH - 1) / a.TH) * a.TH * ((y->W + a.TW - 1) / a.TW) * a.TW;
     const int64_t area_kht = (int64_t)((y->H + 15) / 16) * 16 * ((y->W + 7) / 8) * 8;
@@ -715,7 +658,7 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
     HYVAE_CHECK_ARG(a.gn_cpg <= 32 && (a.gn_cpg & (a.gn_cpg - 1)) == 0, "fused GroupNorm statistics need Cout/groups in {1,2,4,8,16,32} (got %d)", a.gn_cpg);
   }
   // variant: 0 = auto (CTA-pair kernel whenever there are >= 2 m-tiles), 1 = 1-CTA kernel with MT=1, 2 = 1-CTA kernel
-  const bool two_cta = ((variant == 0 && !prefer_1cta) || variant == 3) && a.m_tiles >= 2 && BN >= 64;
+  const bool two_cta = ((variant == 0 && !prefer_1cta) || variant == 3 || variant == 4) && a.m_tiles >= 2 && BN >= 64;
   if (!two_cta && kht) return fail(HYVAE_EINVAL, "internal: kh-trick tile shape chosen without the CTA-pair kernel");
   // 1-CTA kernel: two m-tiles per CTA tile for the narrow-N layers once there is enough work to fill the chip
   const int MT = two_cta ? 2 : ((BN <= 128 && a.m_tiles >= 2 * (int64_t)num_sms() && variant != 1) ? 2 : 1);

@@ -141,20 +141,14 @@ __global__ void gn_stats_kernel(Vol x, int groups, int vox_per_block, double* __
 template <typename T> struct FastMath { static constexpr bool value = true; };
 template <> struct FastMath<float> { static constexpr bool value = false; };
 
-// y = silu(u) with one MUFU (ex2) per element on the 16-bit paths: the reciprocal is two Newton steps on the FMA pipe
-// (MUFU rate, 16/clk/SM, is what bounds this kernel otherwise).  fp32 keeps expf and a true division.
+// y = silu(u).  16-bit paths: u * rcp(1 + ex2(-u * log2 e)) = FMUL + MUFU.EX2 + FADD + MUFU.RCP + FMUL.  Two MUFU per
+// element is 8 elements/clk/SM, ~2.2 T elements/s chip-wide, above what HBM can feed (1.6 T/s); the previous Newton
+// reciprocal made the kernel issue bound (ncu: 80 % issue slots busy at 48 % DRAM).  fp32 keeps expf and a division.
 template <typename T>
 __device__ __forceinline__ float gn_act(float u, int silu, int round_like_ref) {
   if (round_like_ref) u = rnd<T>(u);
   if (!silu) return u;
-  if (FastMath<T>::value) {
-    const float d = 1.f + __expf(-u);                 // d in [1, inf)
-    float r = __int_as_float(0x7EF311C7 - __float_as_int(d));  // fast reciprocal seed (~12 % error)
-    r = r * fmaf(-d, r, 2.f);
-    r = r * fmaf(-d, r, 2.f);
-    r = r * fmaf(-d, r, 2.f);                         // 3 Newton steps: < 1e-6 relative
-    return (d > 1e30f) ? 0.f : u * r;
-  }
+  if (FastMath<T>::value) return __fdividef(u, 1.f + __expf(-u));  // u -> -inf: d = inf, rcp = 0, result -0
   return u / (1.f + expf(-u));
 }
 
@@ -239,15 +233,17 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Vol x, Vol y, const doubl
 // Sum per-tile GroupNorm partials (written by the conv epilogue) in a fixed order: grid = (groups, B).
 // part: [B][rows][groups][2] fp64 -> sums: [B][groups][2] fp64.  One block per (group, batch); threads stride
 // over rows, then a fixed-shape tree in shared memory: bit-reproducible.
-__global__ void __launch_bounds__(256) gn_finalize_kernel(const double* __restrict__ part, int64_t rows, int groups,
+__global__ void __launch_bounds__(256) gn_finalize_kernel(double* __restrict__ part, int64_t rows, int groups,
                                                           double* __restrict__ sums) {
   __shared__ double sa[256], sq[256];
   const int g = blockIdx.x, b = blockIdx.y;
-  const double* p = part + ((int64_t)b * rows * groups + g) * 2;
+  double* p = part + ((int64_t)b * rows * groups + g) * 2;
   double a = 0.0, q = 0.0;
   for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) {
-    a += p[r * groups * 2];
-    q += p[r * groups * 2 + 1];
+    double2* e = reinterpret_cast<double2*>(p + r * groups * 2);
+    const double2 v = *e;
+    a += v.x; q += v.y;
+    *e = make_double2(0.0, 0.0);  // leave the buffer zeroed for the next conv that accumulates into it
   }
   sa[threadIdx.x] = a; sq[threadIdx.x] = q;
   __syncthreads();
@@ -528,7 +524,7 @@ int hyvae_groupnorm_apply(const hyvae_vol* x, const double* sums, const float* g
   return check_launch("groupnorm_apply");
 }
 
-int hyvae_groupnorm_finalize(const double* partials, int32_t B, int64_t rows, int32_t groups, double* sums, void* stream) {
+int hyvae_groupnorm_finalize(double* partials, int32_t B, int64_t rows, int32_t groups, double* sums, void* stream) {
   HYVAE_CHECK_ARG(partials && sums && B > 0 && rows > 0 && groups > 0, "bad finalize arguments");
   ProfScope prof(PC_GN_STATS, (double)B * rows * groups * 8, stream);
   gn_finalize_kernel<<<dim3((unsigned)groups, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(partials, rows, groups, sums);

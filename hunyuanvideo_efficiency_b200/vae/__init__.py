@@ -18,24 +18,25 @@ MODEL_BASE = os.getenv("MODEL_BASE", "./ckpts")
 VAE_PATH = {"884-16c-hy": f"{MODEL_BASE}/hunyuan-video-t2v-720p/vae"}
 
 
+def _route_block_records(records, blocks, what: str):
+    """Hand every JSON record to the block its `block_index` names (out-of-range indices only warn, like
+    hyvideo/vae/__init__.py:27-31,47-51)."""
+    for rec in records:
+        i = rec["block_index"]
+        if 0 <= i < len(blocks):
+            blocks[i].apply_t_ops_config(rec)
+        else:
+            print(f"[Warning] {what} index {i} out of range of {what}s.")
+
+
 def _apply_t_ops_config_to_vae(vae: AutoencoderKLCausal3D, t_ops_config: dict):
-    """hyvideo/vae/__init__.py:15-63: push the JSON's per-block records into the block objects."""
-    enc_cfg = t_ops_config.get("encoder", {})
-    for block_cfg in enc_cfg.get("down_blocks", []):
-        idx = block_cfg["block_index"]
-        if 0 <= idx < len(vae.encoder.down_blocks):
-            vae.encoder.down_blocks[idx].apply_t_ops_config(block_cfg)
-        else:
-            print(f"[Warning] down_block index {idx} out of range of encoder.down_blocks.")
-    vae.encoder.mid_block.apply_t_ops_config_midblock(enc_cfg.get("mid_block", {}))
-    dec_cfg = t_ops_config.get("decoder", {})
-    for block_cfg in dec_cfg.get("up_blocks", []):
-        idx = block_cfg["block_index"]
-        if 0 <= idx < len(vae.decoder.up_blocks):
-            vae.decoder.up_blocks[idx].apply_t_ops_config(block_cfg)
-        else:
-            print(f"[Warning] up_block index {idx} out of range of decoder.up_blocks.")
-    vae.decoder.mid_block.apply_t_ops_config_midblock(dec_cfg.get("mid_block", {}))
+    """hyvideo/vae/__init__.py:15-63: the temporal pool / stride / interp experiment description is pushed into
+    the encoder's down blocks, the decoder's up blocks and both mid blocks."""
+    enc, dec = t_ops_config.get("encoder", {}), t_ops_config.get("decoder", {})
+    _route_block_records(enc.get("down_blocks", []), vae.encoder.down_blocks, "encoder.down_block")
+    vae.encoder.mid_block.apply_t_ops_config_midblock(enc.get("mid_block", {}))
+    _route_block_records(dec.get("up_blocks", []), vae.decoder.up_blocks, "decoder.up_block")
+    vae.decoder.mid_block.apply_t_ops_config_midblock(dec.get("mid_block", {}))
 
 
 def load_t_ops_config(json_path: str) -> dict:
@@ -43,38 +44,38 @@ def load_t_ops_config(json_path: str) -> dict:
         return json.load(f)
 
 
+def _read_state_dict(vae_path: str, map_location):
+    """`<vae_path>/pytorch_model.pt`, optionally wrapped in {"state_dict": ...} and / or prefixed "vae."
+    (hyvideo/vae/__init__.py:94-101).  A missing file is an AssertionError, as in the reference."""
+    f = Path(vae_path) / "pytorch_model.pt"
+    assert f.exists(), f"VAE checkpoint not found: {f}"
+    sd = torch.load(f, map_location=map_location, weights_only=False)
+    sd = sd.get("state_dict", sd)
+    if any(k.startswith("vae.") for k in sd):
+        sd = {k.replace("vae.", ""): v for k, v in sd.items() if k.startswith("vae.")}
+    return sd
+
+
 def load_vae(vae_type: str = "884-16c-hy", vae_precision: str = None, sample_size: tuple = None, vae_path: str = None,
              logger=None, device=None, t_ops_config_path: str = None, test: bool = False):
-    """Load the 3D VAE (config.json + pytorch_model.pt under `vae_path`), exactly like the reference:
-    returns (vae, vae_path, spatial_compression_ratio, time_compression_ratio)."""
-    if vae_path is None:
-        vae_path = VAE_PATH[vae_type]
-    if logger is not None:
-        logger.info(f"Loading 3D VAE model ({vae_type}) from: {vae_path}")
-    config = AutoencoderKLCausal3D.load_config(vae_path)
-    vae = AutoencoderKLCausal3D.from_config(config, sample_size=sample_size) if sample_size else AutoencoderKLCausal3D.from_config(config)
-
-    vae_ckpt = Path(vae_path) / "pytorch_model.pt"
-    assert vae_ckpt.exists(), f"VAE checkpoint not found: {vae_ckpt}"
-    ckpt = torch.load(vae_ckpt, map_location=vae.device, weights_only=False)
-    if "state_dict" in ckpt:
-        ckpt = ckpt["state_dict"]
-    if any(k.startswith("vae.") for k in ckpt.keys()):
-        ckpt = {k.replace("vae.", ""): v for k, v in ckpt.items() if k.startswith("vae.")}
-    vae.load_state_dict(ckpt)
-
-    spatial_compression_ratio = vae.config.spatial_compression_ratio
-    time_compression_ratio = vae.config.time_compression_ratio
+    """Same signature, checkpoint format, ordering of side effects and return tuple as the reference's
+    load_vae (hyvideo/vae/__init__.py:70-127):
+    -> (vae, vae_path, spatial_compression_ratio, time_compression_ratio)."""
+    log = logger.info if logger is not None else (lambda *_: None)
+    vae_path = vae_path if vae_path is not None else VAE_PATH[vae_type]
+    log(f"Loading 3D VAE model ({vae_type}) from: {vae_path}")
+    overrides = {"sample_size": sample_size} if sample_size else {}
+    vae = AutoencoderKLCausal3D.from_config(AutoencoderKLCausal3D.load_config(vae_path), **overrides)
+    vae.load_state_dict(_read_state_dict(vae_path, vae.device))
+    ratios = (vae.config.spatial_compression_ratio, vae.config.time_compression_ratio)
     if vae_precision is not None:
         vae = vae.to(dtype=PRECISION_TO_TYPE[vae_precision])
     vae.requires_grad_(False)
-    if logger is not None:
-        logger.info(f"VAE to dtype: {vae.dtype}")
+    log(f"VAE to dtype: {vae.dtype}")
     if device is not None:
         vae = vae.to(device)
     vae.eval()
-    if t_ops_config_path is not None and test:
-        if logger is not None:
-            logger.info("Applying T-pool/pad configs to the loaded VAE.")
+    if t_ops_config_path is not None and test:  # the experiment hooks are only armed in test mode (:121)
+        log("Applying T-pool/pad configs to the loaded VAE.")
         _apply_t_ops_config_to_vae(vae, load_t_ops_config(t_ops_config_path))
-    return vae, vae_path, spatial_compression_ratio, time_compression_ratio
+    return (vae, vae_path) + ratios

@@ -95,8 +95,9 @@ int hyvae_groupnorm_apply(const hyvae_vol* x, const double* sums, const float* g
                           void* stream);
 /* Statistics from the PRODUCER: hyvae_conv3d_causal_tc can emit partial sums of its own output (gn_partials,
  * [B][rows][groups][2] fp64 with rows = hyvae_conv3d_tc_gn_rows()); _finalize adds the rows in a fixed order into
- * `sums`, replacing the _stats pass over the tensor. */
-int hyvae_groupnorm_finalize(const double* partials, int32_t B, int64_t rows, int32_t groups, double* sums, void* stream);
+ * `sums`, replacing the _stats pass over the tensor, and ZEROES `partials` again, so one buffer zeroed once can
+ * serve every conv enqueued on the same stream. */
+int hyvae_groupnorm_finalize(double* partials, int32_t B, int64_t rows, int32_t groups, double* sums, void* stream);
 
 /* ---- pad / nearest upsample --------------------------------------------------------------------
  * Replaces F.pad(replicate) :74 and F.interpolate(nearest)+cat of UpsampleCausal3D.forward :152-171:

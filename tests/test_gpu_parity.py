@@ -189,7 +189,7 @@ def test_tc_thin_layers_and_fused_gn_stats():
                                                    (512, 512, 3, 18, 32, (1, 1, 1)), (128, 256, 9, 36, 64, (2, 2, 2)),
                                                    (128, 64, 3, 8, 24, (1, 1, 1))])
 def test_tc_cta_pair_kernel_matches_single_cta_kernel(Cin, Cout, T, H, W, stride):
-    """variant 0 (cta_group::2 pair kernel, many tiles per pair, odd tile counts) vs variant 2 (1-CTA kernel)."""
+    """variant 4 (cta_group::2 pair kernel, many tiles per pair, odd tile counts) vs variant 2 (1-CTA kernel)."""
     N = _N()
     if not N.device_supports_tc():
         pytest.skip("needs sm_100")
@@ -198,13 +198,53 @@ def test_tc_cta_pair_kernel_matches_single_cta_kernel(Cin, Cout, T, H, W, stride
     wp = _pack(w.half(), torch.float16)
     r = N.Vol(1, *N.conv_out_dims(T, H, W, stride), Cout, torch.float16, _dev())
     r.t.normal_()
-    ys = [N.conv3d_tc(xv, wp, b.to(_dev()), 3, stride, Cout, residual=r, variant=v, gn_groups=32) for v in (0, 2, 0, 3)]
+    # variant 4 = CTA-pair kernel with the kh trick where it applies (auto would pick the halo kernel for Cout <= 128)
+    ys = [N.conv3d_tc(xv, wp, b.to(_dev()), 3, stride, Cout, residual=r, variant=v, gn_groups=32) for v in (4, 2, 4, 3)]
     assert torch.equal(ys[0].t, ys[2].t)                                    # reproducible
     for other in (ys[1], ys[3]):                                            # pair+kh-trick vs 1-CTA vs pair without kh-trick
         assert O.rel_err(other.t.float().cpu(), ys[0].t.float().cpu()) < 1e-3
         assert torch.allclose(ys[0].gn_sums, other.gn_sums, rtol=1e-5, atol=1e-3)
     ref = O.causal_conv3d(x.half().float(), w.half().float(), b, stride) + r.to_ncthw().float().cpu()
     assert O.rel_err(ref, ys[0].to_ncthw().float().cpu()) < 2e-3
+
+
+@pytest.mark.parametrize("B,Cin,Cout,T,H,W,res,gn", [
+    (2, 128, 128, 3, 40, 24, True, 32),    # two 16x16 groups in W (second m-tile of the last group half empty), batch 2
+    (2, 64, 128, 2, 21, 19, False, 32),    # ragged H and W, Cin = one chunk
+    (1, 256, 128, 3, 32, 48, True, 32),    # four K chunks (decoder 256 -> 128)
+    (1, 128, 8, 3, 40, 40, False, 0),      # conv_out: Cout padded 3 -> 8, BN = 32, three taps per weight stage
+    (1, 8, 128, 3, 40, 40, False, 32),     # conv_in: Cin padded 3 -> 8, one K = 16 slice per tap
+    (1, 64, 64, 3, 32, 32, True, 32),      # BN = 64
+    (1, 128, 128, 5, 6, 5, True, 32),      # smaller than one tile
+])
+def test_tc_halo_kernel_matches_oracle_and_single_cta_kernel(B, Cin, Cout, T, H, W, res, gn):
+    """conv_halo.cu (variant 5 / auto for stride-1 3x3x3, Cout <= 128): full 2-D halo stage read at unaligned
+    row offsets, TMA-store epilogue with the residual tile fetched by TMA, halving-tree GroupNorm statistics."""
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    x, w, b = _rand_case(B, Cin, Cout, T, H, W, 31)
+    xv = _vol(x.half(), pad=(2, 1, 1))
+    wp = _pack(w.half(), torch.float16)
+    r = None
+    if res:
+        r = N.Vol(B, T, H, W, Cout, torch.float16, _dev())
+        r.t.normal_()
+    ys = [N.conv3d_tc(xv, wp, b.to(_dev()), 3, (1, 1, 1), Cout, residual=r, variant=v, gn_groups=gn) for v in (5, 2, 5, 0)]
+    assert torch.equal(ys[0].t, ys[2].t) and torch.equal(ys[0].t, ys[3].t)      # reproducible; auto picks the halo kernel
+    assert O.rel_err(ys[1].t.float().cpu(), ys[0].t.float().cpu()) < 1e-3
+    if gn:
+        assert torch.equal(ys[0].gn_sums, ys[2].gn_sums)
+        assert torch.allclose(ys[0].gn_sums, ys[1].gn_sums, rtol=1e-5, atol=5e-2)   # different fp32 summation trees
+    ref = O.causal_conv3d(x.half().float(), w.half().float(), b)
+    if res:
+        ref = ref + r.to_ncthw().float().cpu()
+    assert O.rel_err(ref, ys[0].to_ncthw().float().cpu()) < 2e-3
+    if gn:   # statistics of the fp32 result, per (batch, group)
+        n = (Cout // gn) * T * H * W
+        g_ref = ref.reshape(B, gn, -1).double()
+        assert torch.allclose(ys[0].gn_sums[:, :, 0].cpu() / n, g_ref.mean(-1), atol=5e-4)
+        assert torch.allclose(ys[0].gn_sums[:, :, 1].cpu() / n, (g_ref ** 2).mean(-1), rtol=2e-3)
 
 
 def test_tc_gemm_k1_residual_and_fp16():
