@@ -37,6 +37,7 @@ _SIGNATURES = {
     "hyvae_vol_to_ncthw": [_VP, _vp, _i32, _i32, _vp],
     "hyvae_conv3d_causal_direct": [_VP, _vp, _vp, _VP, _VP, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "hyvae_conv3d_causal_tc": [_VP, _vp, _vp, _VP, _VP, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
+    "hyvae_conv3d_upphase_tc": [_VP, _vp, _vp, _VP, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "hyvae_groupnorm_finalize": [_vp, _i32, _i64, _i32, _vp, _vp],
     "hyvae_groupnorm_stats": [_VP, _i32, _vp, _vp, _i64, _vp],
     "hyvae_groupnorm_apply": [_VP, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _VP, _vp],
@@ -227,6 +228,27 @@ def conv3d_tc(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, residual
                                         k, stride[0], stride[1], stride[2], int(round_like_ref), variant,
                                         _ptr(part), gn_groups if part is not None else 0, _stream()),
            "conv3d_causal_tc")
+    if part is not None:
+        sums = torch.empty((x.B, gn_groups, 2), dtype=torch.float64, device=x.device)
+        _check(lib().hyvae_groupnorm_finalize(part.data_ptr(), x.B, rows, gn_groups, sums.data_ptr(), _stream()), "groupnorm_finalize")
+        y.gn_sums, y.gn_groups = sums, gn_groups
+    return y
+
+
+def conv3d_upsample_phases(x: Vol, phase_w, bias, up, cout: int, gn_groups: int = 0) -> Vol:
+    """UpsampleCausal3D's nearest upsample + 3x3x3 conv as 4 (up[0] == 1) or 8 phase convolutions over the LOW-res
+    volume `x`, which must carry the halo (nkt-1, 1, 1).  phase_w: {(pt, ph, pw): [nkt*4][Cout][Cin] tensor}."""
+    assert up[1] == 2 and up[2] == 2 and up[0] in (1, 2)
+    T = 2 * x.T - 1 if up[0] == 2 else x.T
+    y = Vol(x.B, T, 2 * x.H, 2 * x.W, cout, x.dtype, x.device)
+    part, rows = None, 0
+    if gn_groups > 0 and cout % gn_groups == 0 and (cout // gn_groups) in (1, 2, 4, 8, 16, 32):
+        rows = int(lib().hyvae_conv3d_tc_gn_rows())
+        part = _gn_partials(x.B, rows, gn_groups, x.device)
+    for (pt, ph, pw), w in phase_w.items():
+        _check(lib().hyvae_conv3d_upphase_tc(x.ref(), w.data_ptr(), _ptr(bias), y.ref(), up[0], pt, ph, pw,
+                                             _ptr(part), gn_groups if part is not None else 0, _stream()),
+               "conv3d_upphase_tc")
     if part is not None:
         sums = torch.empty((x.B, gn_groups, 2), dtype=torch.float64, device=x.device)
         _check(lib().hyvae_groupnorm_finalize(part.data_ptr(), x.B, rows, gn_groups, sums.data_ptr(), _stream()), "groupnorm_finalize")

@@ -237,7 +237,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * Cfg::B_BYTES + tt * Cfg::B_TAP_BYTES);
 #pragma unroll
                 for (int i = 0; i < MT; ++i) {
-                  const uint64_t adesc = make_halo_desc(a_stage + (uint32_t)((kh * PITCH + kw + 8 * i) * 128), PITCH * 128);
+                  const uint64_t adesc = (a.probe & 16) ? make_halo_desc(a_stage + (uint32_t)(i * 16384), 1024)  // aligned-operand timing probe
+                                                        : make_halo_desc(a_stage + (uint32_t)((kh * PITCH + kw + 8 * i) * 128), PITCH * 128);
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
                     if (k < nk) umma_f16(d_tmem + i * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (step | tap9 | k) != 0);
@@ -339,7 +340,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 Vec8<T> r; r.v = lds128(sa16);
                 float rf[8]; r.get(rf);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[c * 8 + e] += rf[e];
+                for (int e = 0; e < 8; ++e) f[c * 8 + e] = (a.round_like_ref ? rnd<T>(f[c * 8 + e]) : f[c * 8 + e]) + rf[e];
               }
               Vec8<T> o; o.set(&f[c * 8]);
               sts128(sa16, o.v);

@@ -18,6 +18,7 @@ struct HaloArgs {
   int tiles_h, groups_w;   // 16-row tiles, groups of MT 8-column m-tiles
   int64_t total;           // B * To * tiles_h * groups_w
   int has_res;
+  int round_like_ref;      // round conv + bias to the storage type before adding the residual
   double* gn_part;         // optional [B][gn_rows][gn_groups][2]
   int gn_groups, gn_cpg, gn_rows;
   int probe;

@@ -44,6 +44,10 @@ struct TcArgs {
   int gn_groups, gn_cpg, gn_rows;
   int64_t m_tiles_per_b;
   int probe;            // measurement only (HYVAE_TC_PROBE): bit 0 = stop issuing TMA once the ring is primed, bit 1 = all loads hit tile 0, bit 2 = skip the epilogue
+  // kh-trick pair kernel: tap geometry.  The standard conv is nkt = nkw = nsub = 3 with origin (0,0,0); one phase of
+  // the sub-pixel decomposition of nearest-upsample + conv (hyvae_conv3d_upphase_tc) has 2 (or 3) x 2 x 2 taps and a
+  // box origin shifted by the phase.  Weight tap index = (kt * nsub + kh) * nkw + kw.
+  int nkt, nkw, nsub, ot, oh, ow, a_tx;
 };
 
 constexpr int TC_THREADS = 192;
@@ -349,8 +353,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int kchunks = (a.Cin + 63) / 64;
-  // groups per tile: KHT -> (kt, kw, chunk) with the 3 kh taps inside; otherwise (tap, chunk)
-  const int ngroups = (KHT ? 9 : a.k * a.k * a.k) * kchunks;
+  // groups per tile: KHT -> (kt, kw, chunk) with the kh taps inside; otherwise (tap, chunk)
+  const int ngroups = (KHT ? a.nkt * a.nkw : a.k * a.k * a.k) * kchunks;
+  const int nsub = KHT ? a.nsub : 1;
   const int64_t pair0 = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
   if (warp == 0) {
@@ -366,15 +371,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int g = 0; g < ngroups; ++g) {
           const int kc = g % kchunks, tg = g / kchunks;
           int kt, kh0, kw;
-          if (KHT) { kt = tg / 3; kw = tg % 3; kh0 = 0; }
+          if (KHT) { kt = tg / a.nkw; kw = tg % a.nkw; kh0 = 0; }
           else { kt = tg / (a.k * a.k); kh0 = (tg / a.k) % a.k; kw = tg % a.k; }
           if (KHT) {
             mbar_wait(aempty_bar + 8 * sa, pa ^ 1);
             const bool skip = (a.probe & 1) && afills >= NA;
             ++afills;
             if (elect_one()) {
-              if (leader) { if (skip) mbar_arrive(afull_bar + 8 * sa); else mbar_expect_tx(afull_bar + 8 * sa, 2 * Cfg::A_BYTES); }
-              if (!skip) tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull_bar + 8 * sa, kc * 64, m.w0 + kw, m.h0, m.t + kt, m.b);
+              if (leader) { if (skip) mbar_arrive(afull_bar + 8 * sa); else mbar_expect_tx(afull_bar + 8 * sa, 2 * a.a_tx); }
+              if (!skip) tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull_bar + 8 * sa, kc * 64, m.w0 + a.ow + kw, m.h0 + a.oh, m.t + a.ot + kt, m.b);
               if (!leader) mbar_arrive_leader(afull_bar + 8 * sa);
             }
             __syncwarp();
@@ -382,6 +387,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
 #pragma unroll
           for (int sub = 0; sub < NSUB; ++sub) {
+            if (sub >= nsub) break;
             const int kh = kh0 + sub;
             mbar_wait(bempty_bar + 8 * sb, pb ^ 1);
             const bool skipb = (a.probe & 1) && bfills >= SB;
@@ -394,7 +400,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (!KHT && !skipb)
                 tma_load_5d_2sm(sA + sb * Cfg::A_BYTES, &tmA, bfull_bar + 8 * sb, kc * 64,
                                 m.w0 * a.sw + kw, m.h0 * a.sh + kh, m.t * a.st + kt, m.b);
-              if (!skipb) tma_load_3d_2sm(sB + sb * Cfg::B_STAGE_BYTES, &tmB, bfull_bar + 8 * sb, kc * 64, n0, (kt * a.k + kh) * a.k + kw);
+              if (!skipb) tma_load_3d_2sm(sB + sb * Cfg::B_STAGE_BYTES, &tmB, bfull_bar + 8 * sb, kc * 64, n0,
+                                          KHT ? (kt * a.nsub + kh) * a.nkw + kw : (kt * a.k + kh) * a.k + kw);
               if (!leader) mbar_arrive_leader(bfull_bar + 8 * sb);
             }
             __syncwarp();
@@ -419,6 +426,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (KHT) { mbar_wait(afull_bar + 8 * sa, pa); }
 #pragma unroll
           for (int sub = 0; sub < NSUB; ++sub) {
+            if (sub >= nsub) break;
             mbar_wait(bfull_bar + 8 * sb, pb);
             tc_fence_after();
             if (elect_one()) {
@@ -568,6 +576,7 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
   a.B = y->B; a.To = y->T; a.Ho = y->H; a.Wo = y->W; a.Cin = x->C; a.Cout = y->C;
   a.k = k; a.st = st; a.sh = sh; a.sw = sw; a.round_like_ref = round_like_ref;
   { const char* pe = getenv("HYVAE_TC_PROBE"); a.probe = pe ? atoi(pe) : 0; }  // measurement only: results are garbage when set
+  a.nkt = a.nkw = a.nsub = 3; a.ot = a.oh = a.ow = 0; a.a_tx = 18 * 1024;
 
   // ---- halo kernel (conv_halo.cu): every stride-1 3x3x3 conv with Cout <= 128 and a 16-bit output (variant 5 forces it)
   const bool halo_ok = k == 3 && st == 1 && sh == 1 && sw == 1 && y->C <= 128 && y->dtype == x->dtype &&
@@ -581,7 +590,7 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
     h.bias = bias; h.B = y->B; h.To = y->T; h.Ho = y->H; h.Wo = y->W; h.Cin = x->C; h.Cout = y->C;
     h.tiles_h = (y->H + 15) / 16; h.groups_w = (y->W + 8 * mt - 1) / (8 * mt);
     h.total = (int64_t)y->B * y->T * h.tiles_h * h.groups_w;
-    h.has_res = residual != nullptr;
+    h.has_res = residual != nullptr; h.round_like_ref = round_like_ref;
     h.gn_part = gn_partials; h.gn_groups = gn_groups; h.gn_cpg = 0; h.gn_rows = num_sms() * 4; h.probe = a.probe;
     if (gn_partials) {
       HYVAE_CHECK_ARG(gn_groups > 0 && y->C % gn_groups == 0, "gn_groups=%d does not divide Cout=%d", gn_groups, y->C);
@@ -717,4 +726,91 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
     if (f32out) { HYVAE_TC_LAUNCH(__half, float) } else { HYVAE_TC_LAUNCH(__half, __half) }
   }
 #undef HYVAE_TC_LAUNCH
+}
+
+// ---------------------------------------------------------------------------------- sub-pixel phases of upsample + conv
+// UpsampleCausal3D.forward (unet_causal_3d_blocks.py:152-175) = nearest x2 (frame 0 not duplicated in T) followed by a
+// 3x3x3 CausalConv3d.  Every high-res tap of output voxel (t', h', w') reads low-res voxel x[f(t')][h'>>1][w'>>1]-ish, so
+// per output parity ("phase") the 27 taps collapse onto 2x2x2 (T upsampled) or 3x2x2 (T not upsampled) low-res taps
+// whose weights are sums of the original taps:
+//   H (same for W): h' = 2i   -> x[i-1]*W0 + x[i]*(W1+W2);      h' = 2i+1 -> x[i]*(W0+W1) + x[i+1]*W2
+//   T (up_t == 2):  t' = 2j   -> x[j-1]*W0 + x[j]*(W1+W2);      t' = 2j-1 -> x[j-1]*(W0+W1) + x[j]*W2   (j >= 1)
+// with x[-1] = x[0], x[H] = x[H-1] (the replicate halo of the LOW-res volume reproduces the replicate padding of the
+// upsampled one).  One call computes one phase: a 2(3)x2x2-tap conv over the low-res volume whose output rows are
+// scattered with stride 2 into y.  3.4x (2.25x) fewer MACs than convolving the upsampled tensor, and the 8x larger
+// upsampled tensor is never materialised.  Runs on the kh-trick CTA-pair kernel.
+extern "C" int hyvae_conv3d_upphase_tc(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* y,
+                                       int32_t up_t, int32_t pt, int32_t ph, int32_t pw, double* gn_partials,
+                                       int32_t gn_groups, void* stream) {
+  if (int e = check_vol(x, "x")) return e;
+  if (int e = check_vol(y, "y")) return e;
+  HYVAE_CHECK_ARG(w != nullptr, "w is null");
+  HYVAE_CHECK_ARG((up_t == 1 || up_t == 2) && (pt == 0 || (pt == 1 && up_t == 2)) && (ph == 0 || ph == 1) && (pw == 0 || pw == 1),
+                  "bad phase (up_t=%d pt=%d ph=%d pw=%d)", up_t, pt, ph, pw);
+  HYVAE_CHECK_ARG((x->dtype == HYVAE_BF16 || x->dtype == HYVAE_F16) && x->dtype == y->dtype && x->B == y->B, "needs 16-bit x and y of one dtype");
+  const int nkt = up_t == 2 ? 2 : 3;
+  HYVAE_CHECK_ARG(x->pt == nkt - 1 && x->ph == 1 && x->pw == 1, "x must carry the halo (%d,1,1), has (%d,%d,%d)", nkt - 1, x->pt, x->ph, x->pw);
+  HYVAE_CHECK_ARG(y->T == (up_t == 2 ? 2 * x->T - 1 : x->T) && y->H == 2 * x->H && y->W == 2 * x->W, "y dims do not match the upsampled conv output");
+  HYVAE_CHECK_ARG(x->C % 8 == 0 && y->C % 8 == 0 && y->C >= 64, "Cin %% 8, Cout %% 8 and Cout >= 64 required (Cin=%d Cout=%d)", x->C, y->C);
+  HYVAE_CHECK_ARG(((uintptr_t)x->data & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)y->data & 15) == 0, "pointers must be 16-byte aligned");
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const int To = (up_t == 2 && pt == 1) ? x->T - 1 : x->T;
+  if (To <= 0) return HYVAE_OK;  // a single frame has no odd output frames
+
+  Vol vx = make_vol(x), vy = make_vol(y);
+  TcArgs a;
+  a.y = y->data; a.bias = bias; a.res = nullptr; a.rsB = a.rsT = a.rsH = a.rsW = a.roff = 0;
+  a.ysB = vy.sB; a.ysT = vy.sT * (up_t == 2 ? 2 : 1); a.ysH = vy.sH * 2; a.ysW = vy.sW * 2;
+  a.yoff = vy.at(0, (up_t == 2 && pt == 1) ? 1 : 0, ph, pw);
+  a.B = y->B; a.To = To; a.Ho = x->H; a.Wo = x->W; a.Cin = x->C; a.Cout = y->C;
+  a.k = 3; a.st = a.sh = a.sw = 1; a.round_like_ref = 0;
+  { const char* pe = getenv("HYVAE_TC_PROBE"); a.probe = pe ? atoi(pe) : 0; }
+  a.nkt = nkt; a.nkw = 2; a.nsub = 2; a.ot = (up_t == 2 && pt == 1) ? 1 : 0; a.oh = ph; a.ow = pw; a.a_tx = 17 * 1024;
+  a.TH = 16; a.TW = 8;
+  a.tiles_h = (x->H + 15) / 16; a.tiles_w = (x->W + 7) / 8;
+  const int BN = y->C > 128 ? 256 : (y->C > 64 ? 128 : 64);
+  a.n_tiles = (y->C + BN - 1) / BN;
+  a.m_tiles = (int64_t)y->B * To * a.tiles_h * a.tiles_w;
+  a.m_tiles_per_b = (int64_t)To * a.tiles_h * a.tiles_w;
+  a.total_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
+  a.gn_part = gn_partials; a.gn_groups = gn_groups; a.gn_cpg = 0; a.gn_rows = num_sms() * 4;
+  if (gn_partials) {
+    HYVAE_CHECK_ARG(gn_groups > 0 && y->C % gn_groups == 0, "gn_groups=%d does not divide Cout=%d", gn_groups, y->C);
+    a.gn_cpg = y->C / gn_groups;
+    HYVAE_CHECK_ARG(a.gn_cpg <= 32 && (a.gn_cpg & (a.gn_cpg - 1)) == 0, "fused GroupNorm statistics need Cout/groups in {1,2,4,8,16,32} (got %d)", a.gn_cpg);
+  }
+  const CUtensorMapDataType dt = x->dtype == HYVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)x->C, (cuuint64_t)vx.Wp(), (cuuint64_t)vx.Hp(), (cuuint64_t)vx.Tp(), (cuuint64_t)x->B};
+    cuuint64_t strides[4] = {(cuuint64_t)vx.sW * 2, (cuuint64_t)vx.sH * 2, (cuuint64_t)vx.sT * 2, (cuuint64_t)vx.sB * 2};
+    cuuint32_t box[5] = {64, 8, 17, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmA, dt, 5, x->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(A phase) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)x->C, (cuuint64_t)y->C, (cuuint64_t)(nkt * 4)};
+    cuuint64_t strides[2] = {(cuuint64_t)x->C * 2, (cuuint64_t)x->C * y->C * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)(BN / 2), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&tmB, dt, 3, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(B phase) failed with %d", (int)r);
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  char tag[56];
+  snprintf(tag, sizeof(tag), "up%d22 p%d%d%d %d->%d lo %dx%dx%dx%d BN%d", up_t, pt, ph, pw, x->C, y->C, y->B, To, x->H, x->W, BN);
+  // algorithmic work = what the reference executes for these output voxels: 27 taps at high resolution
+  ProfScope prof(PC_CONV_TC, 2.0 * (double)y->B * To * x->H * x->W * y->C * x->C * 27, stream, tag);
+#define HYVAE_UP_LAUNCH(T)                                                           \
+  switch (BN) {                                                                      \
+    case 256: return launch_tc2<T, T, 256, true>(tmA, tmB, a, s);                    \
+    case 128: return launch_tc2<T, T, 128, true>(tmA, tmB, a, s);                    \
+    default: return launch_tc2<T, T, 64, true>(tmA, tmB, a, s);                      \
+  }
+  if (x->dtype == HYVAE_BF16) { HYVAE_UP_LAUNCH(__nv_bfloat16) } else { HYVAE_UP_LAUNCH(__half) }
+#undef HYVAE_UP_LAUNCH
 }

@@ -153,7 +153,7 @@ __device__ __forceinline__ float gn_act(float u, int silu, int round_like_ref) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) gn_apply_kernel(Vol x, Vol y, const double* __restrict__ sums, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(Vol x, Vol y, const double* __restrict__ sums, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int groups, float eps, int silu, int round_like_ref,
                                 int rows_per_block) {
   extern __shared__ float sh[];  // scale[C], shift[C]
@@ -190,28 +190,32 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Vol x, Vol y, const doubl
     const T* srow = xs + x.at(b, t, h, 0);
     T* drow = yd + (int64_t)r * Wp * C;
     if (fixed_cv) {
-      // blockDim % CV == 0: this thread always lands on the same 8 channels -> scale/shift live in registers;
-      // two 16-byte vectors in flight per thread
-      for (int i = threadIdx.x; i < row_elems; i += 2 * blockDim.x) {
-        const int i2 = i + blockDim.x;
-        const bool has2 = i2 < row_elems;
-        const int wp0 = pow2 ? (i >> shift) : (i / CV), wp1 = pow2 ? (i2 >> shift) : (i2 / CV);
-        const int w0 = min(max(wp0 - y.pw, 0), y.W - 1), w1 = min(max(wp1 - y.pw, 0), y.W - 1);
-        Vec8<T> q0, q1;
-        q0.load(srow + (int64_t)w0 * x.sW + mycv * 8);
-        if (has2) q1.load(srow + (int64_t)w1 * x.sW + mycv * 8);
-        float f[8];
-        q0.get(f);
+      // blockDim % CV == 0: this thread always lands on the same 8 channels -> scale/shift live in registers.
+      // Four 16-byte loads are issued before the first use (the kernel was latency bound with two: ncu showed 42 % of
+      // the stall samples on the first consumer of the load at 45 % occupancy).
+      constexpr int U = 4;
+      for (int i = threadIdx.x; i < row_elems; i += U * blockDim.x) {
+        Vec8<T> q[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = gn_act<T>(fmaf(f[j], rsc[j], rsf[j]), silu, round_like_ref);
-        q0.set(f);
-        q0.store(drow + (int64_t)i * 8);
-        if (has2) {
-          q1.get(f);
+        for (int u = 0; u < U; ++u) {
+          const int iu = i + u * blockDim.x;
+          if (iu < row_elems) {
+            const int wp = pow2 ? (iu >> shift) : (iu / CV);
+            const int w = min(max(wp - y.pw, 0), y.W - 1);
+            q[u].load(srow + (int64_t)w * x.sW + mycv * 8);
+          }
+        }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = gn_act<T>(fmaf(f[j], rsc[j], rsf[j]), silu, round_like_ref);
-          q1.set(f);
-          q1.store(drow + (int64_t)i2 * 8);
+        for (int u = 0; u < U; ++u) {
+          const int iu = i + u * blockDim.x;
+          if (iu < row_elems) {
+            float f[8];
+            q[u].get(f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = gn_act<T>(fmaf(f[j], rsc[j], rsf[j]), silu, round_like_ref);
+            q[u].set(f);
+            q[u].store(drow + (int64_t)iu * 8);
+          }
         }
       }
     } else {

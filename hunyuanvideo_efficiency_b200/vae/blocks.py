@@ -81,6 +81,28 @@ class _Conv3dParams(nn.Module):
             self._packed = (key, pw.contiguous(), None if pb is None else pb.contiguous())
         return self._packed[1], self._packed[2]
 
+    def phase_packed(self, dtype, up):
+        """Weights of the sub-pixel phases of `nearest-upsample(up) -> this 3x3x3 conv` (hyvae_conv3d_upphase_tc):
+        {(pt, ph, pw): [nkt*2*2][Cout][Cin]}.  Along an upsampled axis the three taps fold onto two low-res taps,
+        even outputs use (W0, W1+W2), odd outputs (W0+W1, W2); sums are formed in fp32 and rounded once."""
+        w = self.weight
+        key = ("phase", w._version, w.data_ptr(), dtype, w.device, tuple(up), None if self.bias is None else self.bias._version)
+        cached = getattr(self, "_phase_packed", None)
+        if cached is None or cached[0] != key:
+            w32 = w.detach().float()
+            fold = (torch.tensor([[1., 0., 0.], [0., 1., 1.]], device=w.device), torch.tensor([[1., 1., 0.], [0., 0., 1.]], device=w.device))
+            eye = torch.eye(3, device=w.device)
+            out = {}
+            for pt in range(2 if up[0] == 2 else 1):
+                mt = fold[pt] if up[0] == 2 else eye
+                for ph in range(2):
+                    for pw in range(2):
+                        wp = torch.einsum("at,bh,cw,oithw->abcoi", mt, fold[ph], fold[pw], w32)
+                        out[(pt, ph, pw)] = wp.reshape(-1, self.out_channels, self.in_channels).to(dtype).contiguous()
+            pb = None if self.bias is None else self.bias.detach().float().contiguous()
+            self._phase_packed = cached = (key, out, pb)
+        return cached[1], cached[2]
+
 
 class CausalConv3d(nn.Module):
     """unet_causal_3d_blocks.py:49-75.  `time_causal_padding` is kept as an attribute; the padding
@@ -173,6 +195,8 @@ class UpsampleCausal3D(nn.Module):
         self.channels, self.out_channels = channels, out_channels or channels
         self.use_conv, self.name, self.interpolate = use_conv, name, interpolate
         self.upsample_factor = tuple(upsample_factor)
+        # fp16 activations only: the folded weights (W0+W1, ...) need fp16's mantissa; bf16 operands keep the plain path
+        self.phase_decomposition = os.environ.get("HYVAE_UPSAMPLE_PHASES", "1") == "1"
         if any(f not in (1, 2) for f in self.upsample_factor):
             raise NotImplementedError(f"upsample_factor {upsample_factor}")
         conv = CausalConv3d(self.channels, self.out_channels, kernel_size=kernel_size or 3, bias=bias) if use_conv else None
@@ -189,6 +213,15 @@ class UpsampleCausal3D(nn.Module):
         conv = self.conv if self.name == "conv" else self.Conv2d_0
         if conv is None:
             return N.pad_upsample(x, up)
+        c = conv.conv
+        if (self.phase_decomposition and x.dtype == torch.float16 and up[1:] == (2, 2) and c.kernel_size[0] == 3
+                and tuple(int(v) for v in c.stride) == (1, 1, 1) and c.in_channels % 8 == 0 and c.out_channels % 8 == 0
+                and c.out_channels >= 64 and tc_eligible(x.dtype, c.in_channels, c.out_channels, (1, 1, 1), 3)):
+            # sub-pixel phases over the low-res tensor: 3.4x (2.25x) fewer MACs, no 8x upsampled intermediate
+            pw, pb = c.phase_packed(x.dtype, up)
+            halo = (1 if up[0] == 2 else 2, 1, 1)
+            xp = x if x.pad == halo else N.pad_upsample(x, (1, 1, 1), halo)
+            return N.conv3d_upsample_phases(xp, pw, pb, up, c.out_channels, gn_groups=conv.emit_gn_groups)
         return conv.forward_vol(x, up=up)
 
     def forward(self, hidden_states, output_size=None, scale: float = 1.0):

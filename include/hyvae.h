@@ -75,6 +75,16 @@ int hyvae_conv3d_causal_direct(const hyvae_vol* x, const void* w, const float* b
 int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
                            const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
                            int32_t round_like_ref, int32_t variant, double* gn_partials, int32_t gn_groups, void* stream);
+/* One output-parity phase of UpsampleCausal3D.forward (nearest x2 + 3x3x3 CausalConv3d, unet_causal_3d_blocks.py:
+ * 152-175) computed directly from the LOW-resolution volume: the 27 high-res taps collapse onto nkt x 2 x 2 low-res taps
+ * (nkt = 2 if up_t == 2, else 3) whose weights are sums of the original ones.
+ *   x:  low-res volume carrying the halo (nkt-1, 1, 1);  y: high-res volume (T' = 2T-1 if up_t == 2 else T, 2H, 2W).
+ *   w:  [nkt*2*2][Cout][Cin] combined taps of THIS phase, tap = (kt*2 + kh)*2 + kw, in x's dtype.
+ *   pt/ph/pw: output parity (t' = 2j - pt, h' = 2i + ph, w' = 2i' + pw); pt must be 0 when up_t == 1.
+ *   gn_partials: as for hyvae_conv3d_causal_tc; the phases of one conv accumulate into the same buffer.
+ * The caller issues 4 (up_t == 1) or 8 calls per conv. */
+int hyvae_conv3d_upphase_tc(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* y, int32_t up_t,
+                            int32_t pt, int32_t ph, int32_t pw, double* gn_partials, int32_t gn_groups, void* stream);
 /* rows-per-batch of the gn_partials buffer: gn_partials is [B][rows][gn_groups][2] fp64, ZEROED by the caller; every
  * (CTA, warp) of the conv accumulates into its own row, so several launches may add into one buffer (the phases of
  * an upsampling conv) before hyvae_groupnorm_finalize reduces the rows in a fixed order. */

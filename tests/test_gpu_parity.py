@@ -230,7 +230,8 @@ def test_tc_halo_kernel_matches_oracle_and_single_cta_kernel(B, Cin, Cout, T, H,
     if res:
         r = N.Vol(B, T, H, W, Cout, torch.float16, _dev())
         r.t.normal_()
-    ys = [N.conv3d_tc(xv, wp, b.to(_dev()), 3, (1, 1, 1), Cout, residual=r, variant=v, gn_groups=gn) for v in (5, 2, 5, 0)]
+    ys = [N.conv3d_tc(xv, wp, b.to(_dev()), 3, (1, 1, 1), Cout, residual=r, variant=v, gn_groups=gn, round_like_ref=False)
+          for v in (5, 2, 5, 0)]
     assert torch.equal(ys[0].t, ys[2].t) and torch.equal(ys[0].t, ys[3].t)      # reproducible; auto picks the halo kernel
     assert O.rel_err(ys[1].t.float().cpu(), ys[0].t.float().cpu()) < 1e-3
     if gn:
@@ -245,6 +246,37 @@ def test_tc_halo_kernel_matches_oracle_and_single_cta_kernel(B, Cin, Cout, T, H,
         g_ref = ref.reshape(B, gn, -1).double()
         assert torch.allclose(ys[0].gn_sums[:, :, 0].cpu() / n, g_ref.mean(-1), atol=5e-4)
         assert torch.allclose(ys[0].gn_sums[:, :, 1].cpu() / n, (g_ref ** 2).mean(-1), rtol=2e-3)
+
+
+@pytest.mark.parametrize("B,Cin,Cout,T,H,W,up", [
+    (1, 128, 128, 3, 10, 12, (2, 2, 2)),   # ragged low-res tile (10 x 12 < 16 x 8 grid), BN = 128
+    (2, 64, 256, 2, 16, 8, (1, 2, 2)),     # T not upsampled: 3 x 2 x 2 taps, batch 2, BN = 256
+    (1, 256, 256, 1, 20, 24, (2, 2, 2)),   # single frame: the odd temporal phase is empty
+    (1, 512, 512, 5, 18, 32, (2, 2, 2)),   # two n-tiles, deep K, the decoder's ragged 18 x 32 tile
+])
+def test_tc_upsample_phase_decomposition_matches_reference(B, Cin, Cout, T, H, W, up):
+    """UpsampleCausal3D (unet_causal_3d_blocks.py:130-183) as sub-pixel phase convolutions over the low-res tensor
+    (hyvae_conv3d_upphase_tc) vs the reference order of operations (upsample, then 27-tap conv) in fp32."""
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    from hunyuanvideo_efficiency_b200.vae.blocks import UpsampleCausal3D
+    torch.manual_seed(5)
+    m = UpsampleCausal3D(Cin, use_conv=True, out_channels=Cout, upsample_factor=up).to(_dev())
+    x = torch.randn(B, Cin, T, H, W).half()
+    w, b = m.conv.conv.weight.detach().half().float().cpu(), m.conv.conv.bias.detach().float().cpu()
+    ref = O.causal_conv3d(O.upsample_nearest_causal(x.float(), up), w, b)
+    assert m.phase_decomposition
+    y = m.forward_vol(_vol(x))
+    assert O.rel_err(ref, y.to_ncthw().float().cpu()) < 2e-3
+    m.phase_decomposition = False
+    y2 = m.forward_vol(_vol(x))
+    assert O.rel_err(y2.to_ncthw().float().cpu(), y.to_ncthw().float().cpu()) < 2e-3
+    assert y.gn_sums is not None and y2.gn_sums is not None
+    n = (Cout // 32) * ref.shape[2] * ref.shape[3] * ref.shape[4]
+    g_ref = ref.reshape(B, 32, -1).double()
+    assert torch.allclose(y.gn_sums[:, :, 0].cpu() / n, g_ref.mean(-1), atol=1e-3)
+    assert torch.allclose(y.gn_sums[:, :, 1].cpu() / n, (g_ref ** 2).mean(-1), rtol=3e-3)
 
 
 def test_tc_gemm_k1_residual_and_fp16():

@@ -53,7 +53,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         run_case(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]))
     else:
-        cases = [(n, 5, 0) for n in ("small", "rag", "c256", "thin", "c8", "c64", "big", "bignr", "big256", "bigthin", "bigc8")] + [("big", 5, 5), ("big", 5, 4), ("big", 5, 1), ("big", 2, 5), ("bigthin", 5, 5)]
+        cases = [("bignr", 5, 5), ("bignr", 5, 21), ("bignr", 2, 5), ("bignr", 5, 5), ("bignr", 5, 21), ("bignr", 2, 5), ("bignr", 5, 0), ("bignr", 5, 16), ("bignr", 2, 0)]
         for c in cases:
             p = subprocess.run([sys.executable, __file__, c[0], str(c[1]), str(c[2])], capture_output=True, text=True, timeout=120)
             print((p.stdout.strip() or "(no output)") + ("" if p.returncode == 0 else f"  [rc={p.returncode}] {p.stderr.strip()[-300:]}"), flush=True)
