@@ -242,7 +242,7 @@ def conv3d_upsample_phases(x: Vol, phase_w, bias, up, cout: int, gn_groups: int 
     T = 2 * x.T - 1 if up[0] == 2 else x.T
     y = Vol(x.B, T, 2 * x.H, 2 * x.W, cout, x.dtype, x.device)
     part, rows = None, 0
-    if gn_groups > 0 and cout % gn_groups == 0 and (cout // gn_groups) in (1, 2, 4, 8, 16, 32):
+    if gn_groups > 0 and cout % gn_groups == 0 and (cout // gn_groups) in (2, 4, 8, 16, 32):
         rows = int(lib().hyvae_conv3d_tc_gn_rows())
         part = _gn_partials(x.B, rows, gn_groups, x.device)
     for (pt, ph, pw), w in phase_w.items():

@@ -56,58 +56,6 @@ __device__ __forceinline__ uint64_t make_halo_desc(uint32_t addr, uint32_t sbo_b
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-// Sum V per-lane values over the 32 lanes with recursive halving: afterwards every lane holds the warp total of
-// value index lane * V / 32 (V - 1 + log2(32 / V) shuffles instead of 5 * V).  Fixed tree => bit-reproducible.
-template <int V>
-__device__ __forceinline__ float halving_reduce(float (&v)[V], int lane) {
-  int o = 16;
-#pragma unroll
-  for (int h = V / 2; h >= 1; h >>= 1, o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < h; ++i) {
-      const float send = up ? v[i] : v[i + h];
-      const float keep = up ? v[i + h] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-  }
-#pragma unroll
-  for (; o >= 1; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
-  return v[0];
-}
-
-// GroupNorm partial of one 32-column chunk: per group of CPG channels (sum, sum of squares) over this warp's rows.
-template <int CPG>
-__device__ __forceinline__ float gn_chunk_reduce(const float* f, bool valid, int lane) {
-  constexpr int V = 2 * (32 / CPG);
-  float v[V];
-#pragma unroll
-  for (int g = 0; g < 32 / CPG; ++g) {
-    float s = 0.f, q = 0.f;
-#pragma unroll
-    for (int c = 0; c < CPG; ++c) { const float u = valid ? f[g * CPG + c] : 0.f; s += u; q = fmaf(u, u, q); }
-    v[2 * g] = s; v[2 * g + 1] = q;
-  }
-  return halving_reduce<V>(v, lane);
-}
-
 struct HGroup { int b, t, h0, w0; };
 __device__ __forceinline__ HGroup decode_group(const HaloArgs& a, int64_t g, int mt_cols) {
   HGroup r;

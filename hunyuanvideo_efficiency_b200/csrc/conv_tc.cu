@@ -308,28 +308,37 @@ template <int BN, bool KHT> struct Tc2Cfg {
   static constexpr int A_BYTES = KHT ? 18 * 1024 : A_STAGE_BYTES;
   static constexpr int B_STAGE_BYTES = (BN / 2) * 64 * 2;             // this CTA's half of the weight tile
   static constexpr int SA = KHT ? 3 : 0;                              // A ring depth (KHT); non-KHT shares the B ring index
-  static constexpr int BUDGET = 200 * 1024;
+  // KHT kernels with a 16-bit output run the epilogue through shared memory and TMA stores (see conv_halo.cu): one
+  // 128-row x 64-channel SWIZZLE_128B staging block per 64-channel half of the tile
+  static constexpr int NH = (BN + 63) / 64;
+  static constexpr int OUT_BYTES = KHT ? NH * 16384 : 0;
+  static constexpr int BUDGET = (KHT ? 225 : 200) * 1024 - OUT_BYTES;
   static constexpr int SB_RAW = KHT ? (BUDGET - SA * A_BYTES) / B_STAGE_BYTES : BUDGET / (A_BYTES + B_STAGE_BYTES);
   static constexpr int SB = SB_RAW > 12 ? 12 : SB_RAW;
   static constexpr int NA = KHT ? SA : SB;                            // number of A buffers
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = NA * A_BYTES + SB * B_STAGE_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = NA * A_BYTES + SB * B_STAGE_BYTES + OUT_BYTES + 1024 + 512;
+  static_assert(SB >= 4, "B ring too shallow");
 };
 
 template <typename T, typename OT, int BN, bool KHT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const TcArgs a) {
   using Cfg = Tc2Cfg<BN, KHT>;
   constexpr int SB = Cfg::SB, NA = Cfg::NA, NSUB = Cfg::NSUB;
+  constexpr bool TMA_EPI = KHT && sizeof(OT) == 2;  // staged TMA-store epilogue (16-bit output, 16 x 8 tiles)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + NA * Cfg::A_BYTES;
-  const uint32_t bars = sB + SB * Cfg::B_STAGE_BYTES;
+  const uint32_t sOut = sB + SB * Cfg::B_STAGE_BYTES;
+  const uint32_t bars = sOut + Cfg::OUT_BYTES;
   const uint32_t bfull_bar = bars, bempty_bar = bars + 8 * SB;
   const uint32_t afull_bar = bars + 16 * SB, aempty_bar = afull_bar + 8 * NA;  // used by KHT only
   const uint32_t tfull_bar = aempty_bar + 8 * NA, tempty_bar = tfull_bar + 16;
-  const uint32_t tmem_slot = tempty_bar + 16;
+  const uint32_t rfull_bar = tempty_bar + 16;  // [4 epilogue warps]: residual tile landed (TMA_EPI only)
+  const uint32_t tmem_slot = rfull_bar + 32;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
 
@@ -343,6 +352,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int s = 0; s < SB; ++s) { mbar_init(bfull_bar + 8 * s, 2); mbar_init(bempty_bar + 8 * s, 1); }
     for (int s = 0; s < NA; ++s) { mbar_init(afull_bar + 8 * s, 2); mbar_init(aempty_bar + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 256); }
+    for (int s = 0; s < 4; ++s) mbar_init(rfull_bar + 8 * s, 1);
     fence_barrier_init();
   }
   cluster_sync_all();  // both CTAs' barriers exist before anything remote touches them
@@ -455,18 +465,135 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ================= epilogue warps (both CTAs, own TMEM) =================
     const int q = warp & 3;
     int iter = 0;
-    for (int64_t tile = pair0; tile < a.total_tiles; tile += npairs, ++iter) {
-      const int acc = iter & 1;
-      const uint32_t acc_phase = (iter >> 1) & 1;
-      const int nt = (int)(tile % a.n_tiles);
-      const int64_t mg = tile / a.n_tiles;
-      mbar_wait(tfull_bar + 8 * acc, acc_phase);
-      tc_fence_after();
-      const MTile m = decode_mtile(a, mg * 2 + rank);
-      if (m.valid && !(a.probe & 4)) epilogue_mtile<T, OT, BN>(a, m, q, lane, tmem_base + (uint32_t)(acc * BN), nt * BN);
-      tc_fence_before();
-      if (leader) mbar_arrive(tempty_bar + 8 * acc);
-      else mbar_arrive_leader(tempty_bar + 8 * acc);
+    if constexpr (TMA_EPI) {
+      // TMEM -> registers -> (+bias, +residual tile fetched by TMA) -> swizzled staging rows -> one TMA store per warp
+      // and 64-channel half; GroupNorm partials by the halving tree into per-warp fp64 register accumulators that are
+      // flushed when the (batch item, n-tile) changes.  Same scheme as conv_halo.cu.
+      constexpr int NH = Cfg::NH;
+      const int hh = 4 * q + (lane >> 3), ww = lane & 7;
+      const uint32_t rbar = rfull_bar + 8 * q;
+      const uint32_t stage_w = sOut + q * 4096;
+      uint32_t rph = 0;
+      double gacc[BN / 32];
+#pragma unroll
+      for (int j = 0; j < BN / 32; ++j) gacc[j] = 0.0;
+      int gb = -1, gnt = 0;
+      auto gn_flush = [&]() {
+        if (a.gn_part == nullptr || gb < 0) return;
+        const int V = 2 * (32 / a.gn_cpg);
+        const int per = 32 / V;
+        if (lane % per == 0) {
+          const int idx = lane / per;
+          double* row = a.gn_part + ((int64_t)gb * a.gn_rows + blockIdx.x * 4 + q) * a.gn_groups * 2;
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) {
+            const int grp = (gnt * BN + 32 * j) / a.gn_cpg + (idx >> 1);
+            if (grp < a.gn_groups) row[grp * 2 + (idx & 1)] += gacc[j];  // private slot: plain RMW
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) gacc[j] = 0.0;
+      };
+      for (int64_t tile = pair0; tile < a.total_tiles; tile += npairs, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        const int nt = (int)(tile % a.n_tiles);
+        const int64_t mg = tile / a.n_tiles;
+        const int n0 = nt * BN;
+        const MTile m = decode_mtile(a, mg * 2 + rank);
+        const bool live = m.valid && !(a.probe & 4);
+        if (live) {
+          if (m.b != gb || nt != gnt) { gn_flush(); gb = m.b; gnt = nt; }
+          if (lane == 0) {  // staging rows are free once the previous TMA stores have read them
+            bulk_wait_read0();
+            if (a.res) {
+              mbar_expect_tx(rbar, NH * 4096);
+#pragma unroll
+              for (int hf = 0; hf < NH; ++hf)
+                tma_load_5d(stage_w + hf * 16384, &tmR, rbar, n0 + hf * 64, m.w0, m.h0 + 4 * q, m.t, m.b);
+            }
+          }
+          __syncwarp();
+        }
+        mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        tc_fence_after();
+        if (live) {
+          const bool valid = (m.h0 + hh) < a.Ho && (m.w0 + ww) < a.Wo;
+          if (a.res) { mbar_wait(rbar, rph); rph ^= 1u; }
+          const uint32_t t_cols = tmem_base + (uint32_t)(acc * BN);
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) {
+            uint32_t v[32];
+            tmem_ld32(t_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+            const int nc = n0 + j * 32;
+            if (nc < a.Cout) {  // warp-uniform
+              const uint32_t srow = stage_w + (j >> 1) * 16384 + lane * 128;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int n = nc + c * 8;
+                if (a.bias && n < a.Cout) {
+                  const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n);
+                  const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n + 4);
+                  f[c * 8 + 0] += b0.x; f[c * 8 + 1] += b0.y; f[c * 8 + 2] += b0.z; f[c * 8 + 3] += b0.w;
+                  f[c * 8 + 4] += b1.x; f[c * 8 + 5] += b1.y; f[c * 8 + 6] += b1.z; f[c * 8 + 7] += b1.w;
+                }
+                const uint32_t sa16 = srow + ((uint32_t)((((j & 1) * 4 + c) ^ (lane & 7))) << 4);
+                if (a.res) {
+                  Vec8<T> r; r.v = lds128(sa16);
+                  float rf[8]; r.get(rf);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) f[c * 8 + e] = (a.round_like_ref ? rnd<T>(f[c * 8 + e]) : f[c * 8 + e]) + rf[e];
+                }
+                Vec8<T> o; o.set(&f[c * 8]);
+                sts128(sa16, o.v);
+              }
+              if (a.gn_part) {
+                float r;
+                switch (a.gn_cpg) {
+                  case 2: r = gn_chunk_reduce<2>(f, valid, lane); break;
+                  case 4: r = gn_chunk_reduce<4>(f, valid, lane); break;
+                  case 8: r = gn_chunk_reduce<8>(f, valid, lane); break;
+                  case 16: r = gn_chunk_reduce<16>(f, valid, lane); break;
+                  default: r = gn_chunk_reduce<32>(f, valid, lane); break;
+                }
+                gacc[j] += (double)r;
+              }
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int hf = 0; hf < NH; ++hf)
+              if (n0 + hf * 64 < a.Cout)
+                tma_store_5d(&tmY, stage_w + hf * 16384, n0 + hf * 64, m.w0, m.h0 + 4 * q, m.t, m.b);
+            bulk_commit();
+          }
+        }
+        tc_fence_before();
+        if (leader) mbar_arrive(tempty_bar + 8 * acc);
+        else mbar_arrive_leader(tempty_bar + 8 * acc);
+      }
+      gn_flush();
+      if (lane == 0) bulk_wait0();
+    } else {
+      for (int64_t tile = pair0; tile < a.total_tiles; tile += npairs, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        const int nt = (int)(tile % a.n_tiles);
+        const int64_t mg = tile / a.n_tiles;
+        mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        tc_fence_after();
+        const MTile m = decode_mtile(a, mg * 2 + rank);
+        if (m.valid && !(a.probe & 4)) epilogue_mtile<T, OT, BN>(a, m, q, lane, tmem_base + (uint32_t)(acc * BN), nt * BN);
+        tc_fence_before();
+        if (leader) mbar_arrive(tempty_bar + 8 * acc);
+        else mbar_arrive_leader(tempty_bar + 8 * acc);
+      }
     }
   }
 
@@ -508,6 +635,20 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArg
   return check_launch("conv3d_causal_tc");
 }
 
+// Tensor map of the OUTPUT lattice of a conv (or of its residual): logical dims (C, W, H, T, B) with the element strides
+// of TcArgs, so a phase of the upsample decomposition (stride-2 scatter into y) is a dense box over a strided view.
+static int encode_out_map(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, int64_t off, int C, int W, int H, int T, int B,
+                          int64_t sW, int64_t sH, int64_t sT, int64_t sB) {
+  EncodeTiledFn encode = get_encode_fn();
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sT * 2, (cuuint64_t)sB * 2};
+  cuuint32_t box[5] = {64, 8, 4, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(tm, dt, 5, (char*)const_cast<void*>(base) + off * 2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(out lattice) failed with %d", (int)r);
+}
+
 template <typename T, typename OT, int BN, bool KHT>
 static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
   using Cfg = Tc2Cfg<BN, KHT>;
@@ -519,7 +660,15 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
   }
   const int64_t max_pairs = num_sms() / 2;
   const int64_t pairs = a.total_tiles < max_pairs ? a.total_tiles : max_pairs;
-  conv_tc2_kernel<T, OT, BN, KHT><<<(unsigned)(2 * pairs), TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, a);
+  CUtensorMap tmY = tmA, tmR = tmA;  // placeholders unless the staged TMA-store epilogue is compiled in
+  if (KHT && sizeof(OT) == 2) {
+    const CUtensorMapDataType dt = TcFmt<T>::fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    if (int e = encode_out_map(&tmY, dt, a.y, a.yoff, a.Cout, a.Wo, a.Ho, a.To, a.B, a.ysW, a.ysH, a.ysT, a.ysB)) return e;
+    tmR = tmY;
+    if (a.res)
+      if (int e = encode_out_map(&tmR, dt, a.res, a.roff, a.Cout, a.Wo, a.Ho, a.To, a.B, a.rsW, a.rsH, a.rsT, a.rsB)) return e;
+  }
+  conv_tc2_kernel<T, OT, BN, KHT><<<(unsigned)(2 * pairs), TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, a);
   return check_launch("conv3d_causal_tc (2-CTA)");
 }
 
@@ -653,7 +802,9 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
     const int64_t area_best = (int64_t)((y->H + a.TH - 1) / a.TH) * a.TH * ((y->W + a.TW - 1) / a.TW) * a.TW;
     const int64_t area_kht = (int64_t)((y->H + 15) / 16) * 16 * ((y->W + 7) / 8) * 8;
     const int64_t mt_kht = (int64_t)y->B * y->T * ((y->H + 15) / 16) * ((y->W + 7) / 8);
-    if (area_kht * 100 <= area_best * 115 && mt_kht >= 2) { kht = true; a.TH = 16; a.TW = 8; }
+    // (the staged epilogue of the kh-trick kernel reduces GroupNorm partials for >= 2 channels per group)
+    const bool gn_ok = gn_partials == nullptr || (gn_groups > 0 && y->C % gn_groups == 0 && y->C / gn_groups >= 2);
+    if (area_kht * 100 <= area_best * 115 && mt_kht >= 2 && gn_ok) { kht = true; a.TH = 16; a.TW = 8; }
   }
   a.tiles_h = (y->H + a.TH - 1) / a.TH; a.tiles_w = (y->W + a.TW - 1) / a.TW;
   const int BN = BN_sel;
@@ -778,7 +929,7 @@ extern "C" int hyvae_conv3d_upphase_tc(const hyvae_vol* x, const void* w, const 
   if (gn_partials) {
     HYVAE_CHECK_ARG(gn_groups > 0 && y->C % gn_groups == 0, "gn_groups=%d does not divide Cout=%d", gn_groups, y->C);
     a.gn_cpg = y->C / gn_groups;
-    HYVAE_CHECK_ARG(a.gn_cpg <= 32 && (a.gn_cpg & (a.gn_cpg - 1)) == 0, "fused GroupNorm statistics need Cout/groups in {1,2,4,8,16,32} (got %d)", a.gn_cpg);
+    HYVAE_CHECK_ARG(a.gn_cpg >= 2 && a.gn_cpg <= 32 && (a.gn_cpg & (a.gn_cpg - 1)) == 0, "fused GroupNorm statistics need Cout/groups in {2,4,8,16,32} (got %d)", a.gn_cpg);
   }
   const CUtensorMapDataType dt = x->dtype == HYVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap tmA, tmB;
