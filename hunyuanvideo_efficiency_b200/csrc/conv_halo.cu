@@ -3,9 +3,9 @@
 // Reference semantics: F.pad(replicate) + nn.Conv3d, unet_causal_3d_blocks.py:73-75 (+ residual :415).
 //
 // Why a second kernel: with N = Cout <= 128 an MMA of 128 voxels x 128 channels x K=16 lasts 64 cycles and reads
-// 8 KB of operands from shared memory, i.e. the tensor core already uses the whole shared-memory port; every byte
-// TMA writes into shared memory and every scattered global store of the epilogue competes with it
-// (profiles/r01_probe_conv.txt: 1.60 PFLOP/s with loads and epilogue disabled, 1.04 with them).  So this kernel
+// 8 KB of operands from shared memory, i.e. the tensor core already uses the whole 128 B/clk shared-memory port; every
+// byte TMA writes into shared memory and every scattered global store of the epilogue competes with it
+// (profiles/r01_probe_conv_a.txt: 1.60 PFLOP/s with loads and epilogue disabled, 1.04 with them).  So this kernel
 //   * loads the A operand ONCE per (frame tap kt, 64-channel chunk): an 18-row x (8*MT+2)-column halo patch
 //     {64 ch, TWH, 18} that feeds all nine (kh, kw) taps of MT adjacent 16x8-voxel m-tiles.  Tap (kh, kw) of m-tile i
 //     is the same stage at byte offset (kh*PITCH + kw + 8*i)*128 with the 8-row-group stride (SBO) = PITCH*128:
@@ -13,8 +13,13 @@
 //   * runs the epilogue through shared memory: TMEM -> registers -> (+bias, +residual tile fetched by TMA) ->
 //     swizzled staging rows -> one TMA store per warp and 64-channel half, instead of 32-way scattered 16-byte stores;
 //   * reduces the GroupNorm partial sums with a recursive-halving shuffle tree (16 instead of 80 shuffles per 32
-//     columns) and keeps the per-warp fp64 accumulators in registers until the batch item changes.
-// Roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue.
+//     columns) and keeps the per-warp fp64 accumulators in registers until the batch item changes;
+//   * PAIR = true (Cout = 128): two CTAs of a cluster issue ONE tcgen05.mma.cta_group::2 (M = 256) per K = 16 step and
+//     m-tile slot; each CTA stages its own halo patch and only HALF of the weight tile, so the operand reads of the
+//     tensor core drop from 128 to 96 B/clk/SM and the weight writes from 32 to 16 B/clk/SM — the sum of all
+//     shared-memory traffic (121 B/clk) then fits under the port (it is 168 B/clk for the 1-CTA form).
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue; the producer and
+// MMA loops are warp-uniform with one elected lane issuing.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -27,20 +32,21 @@ namespace hyvae {
 
 constexpr int HALO_THREADS = 192;
 
-template <int BN, int MT> struct HaloCfg {
+template <int BN, int MT, bool PAIR> struct HaloCfg {
   static constexpr int TWH = 8 * MT + 2, THH = 18;                  // halo patch: columns x rows
   static constexpr int PITCH = TWH;                                  // smem rows (of 128 B) per halo row: dense
   static constexpr int A_TX = TWH * THH * 128;                      // bytes TMA delivers per A stage
   static constexpr int A_BYTES = (A_TX + 1023) / 1024 * 1024;
   static constexpr int TB = BN >= 128 ? 1 : 3;                       // (kh, kw) taps per B stage (9 % TB == 0)
-  static constexpr int B_TAP_BYTES = BN * 128;
+  static constexpr int BROWS = PAIR ? BN / 2 : BN;                   // weight rows this CTA stages
+  static constexpr int B_TAP_BYTES = BROWS * 128;
   static constexpr int B_BYTES = TB * B_TAP_BYTES;
   static constexpr int NA = 2;
   static constexpr int NH = (BN + 63) / 64;                          // 64-channel halves of the output tile
   static constexpr int OUT_BYTES = NH * 16384;                       // one m-tile of output staging, reused by the MT m-tiles
   static constexpr int BUDGET = 227 * 1024 - 2048;                   // minus alignment slack and barrier block
   static constexpr int NB_RAW = (BUDGET - NA * A_BYTES - OUT_BYTES) / B_BYTES;
-  static constexpr int NB = NB_RAW > 8 ? 8 : NB_RAW;
+  static constexpr int NB = NB_RAW > 12 ? 12 : NB_RAW;
   static constexpr int ACC_COLS = MT * BN;
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   static constexpr int SMEM_BYTES = NA * A_BYTES + NB * B_BYTES + OUT_BYTES + 2048;
@@ -57,6 +63,7 @@ __device__ __forceinline__ uint64_t make_halo_desc(uint32_t addr, uint32_t sbo_b
 }
 
 struct HGroup { int b, t, h0, w0; };
+// A group index >= a.total decodes to b >= B: TMA zero-fills its loads and the epilogue skips it (odd group count, PAIR)
 __device__ __forceinline__ HGroup decode_group(const HaloArgs& a, int64_t g, int mt_cols) {
   HGroup r;
   const int gw = (int)(g % a.groups_w); g /= a.groups_w;
@@ -66,11 +73,11 @@ __device__ __forceinline__ HGroup decode_group(const HaloArgs& a, int64_t g, int
   return r;
 }
 
-template <typename T, int BN, int MT>
+template <typename T, int BN, int MT, bool PAIR>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const HaloArgs a) {
-  using Cfg = HaloCfg<BN, MT>;
+  using Cfg = HaloCfg<BN, MT, PAIR>;
   constexpr int NA = Cfg::NA, NB = Cfg::NB, NH = Cfg::NH, PITCH = Cfg::PITCH, TB = Cfg::TB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -87,81 +94,98 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  constexpr uint32_t NCTA = PAIR ? 2 : 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY);
     if (a.has_res) tma_prefetch_desc(&tmR);
-    for (int s = 0; s < NA; ++s) { mbar_init(afull + 8 * s, 1); mbar_init(aempty + 8 * s, 1); }
-    for (int s = 0; s < NB; ++s) { mbar_init(bfull + 8 * s, 1); mbar_init(bempty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull + 8 * s, 1); mbar_init(tempty + 8 * s, 128); }
+    for (int s = 0; s < NA; ++s) { mbar_init(afull + 8 * s, NCTA); mbar_init(aempty + 8 * s, 1); }
+    for (int s = 0; s < NB; ++s) { mbar_init(bfull + 8 * s, NCTA); mbar_init(bempty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + 8 * s, 1); mbar_init(tempty + 8 * s, 128 * NCTA); }
     for (int s = 0; s < 4; ++s) mbar_init(rfull + 8 * s, 1);
     fence_barrier_init();
-  } else if (warp == 1) {
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   }
-  tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) {
+    cluster_sync_all();  // both CTAs' barriers exist before anything remote touches them
+    if (warp == 1) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();  // TMEM of BOTH CTAs is allocated before the leader's first MMA can write it
+  } else {
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int kchunks = (a.Cin + 63) / 64;
   const int steps_per_group = 3 * kchunks;  // (kt, kc)
+  // work units: a group of MT m-tiles per CTA; a CTA pair walks two consecutive groups (2u, 2u+1) per unit
+  const int64_t unit0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const int64_t ustride = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const int64_t units = PAIR ? (a.total + 1) / 2 : a.total;
+  auto group_of = [&](int64_t u) -> int64_t { return PAIR ? 2 * u + rank : u; };
 
   if (warp == 0) {
-    {
-      // ================= TMA producer (warp-uniform loops, one elected lane issues) =================
-      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-      int64_t afills = 0, bfills = 0;
-      auto issue_A = [&](int64_t g, int step) {
-        const HGroup m = decode_group(a, g, 8 * MT);
-        const int kt = step / kchunks, kc = step % kchunks;
-        mbar_wait(aempty + 8 * sa, pa ^ 1);
-        if (elect_one()) {
-          if ((a.probe & 1) && afills >= NA) {
-            mbar_arrive(afull + 8 * sa);
-          } else {
-            mbar_expect_tx(afull + 8 * sa, Cfg::A_TX);
-            tma_load_5d(sA + sa * Cfg::A_BYTES, &tmA, afull + 8 * sa, kc * 64, m.w0, m.h0, m.t + kt, m.b);
-          }
+    // ================= TMA producer (warp-uniform loops, one elected lane issues) =================
+    int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+    auto issue_A = [&](int64_t u, int step) {
+      const HGroup m = decode_group(a, group_of(u), 8 * MT);
+      const int kt = step / kchunks, kc = step % kchunks;
+      mbar_wait(aempty + 8 * sa, pa ^ 1);
+      if (elect_one()) {
+        if constexpr (PAIR) {
+          if (leader) mbar_expect_tx(afull + 8 * sa, 2 * Cfg::A_TX);
+          tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull + 8 * sa, kc * 64, m.w0, m.h0, m.t + kt, m.b);
+          if (!leader) mbar_arrive_leader(afull + 8 * sa);
+        } else {
+          mbar_expect_tx(afull + 8 * sa, Cfg::A_TX);
+          tma_load_5d(sA + sa * Cfg::A_BYTES, &tmA, afull + 8 * sa, kc * 64, m.w0, m.h0, m.t + kt, m.b);
         }
-        __syncwarp();
-        ++afills;
-        if (++sa == NA) { sa = 0; pa ^= 1; }
-      };
-      bool first = true;
-      for (int64_t g = blockIdx.x; g < a.total; g += gridDim.x) {
-        for (int step = 0; step < steps_per_group; ++step) {
-          if (first) { issue_A(g, step); first = false; }
-          const int kt = step / kchunks, kc = step % kchunks;
+      }
+      __syncwarp();
+      if (++sa == NA) { sa = 0; pa ^= 1; }
+    };
+    bool first = true;
+    for (int64_t u = unit0; u < units; u += ustride) {
+      for (int step = 0; step < steps_per_group; ++step) {
+        if (first) { issue_A(u, step); first = false; }
+        const int kt = step / kchunks, kc = step % kchunks;
 #pragma unroll 1
-          for (int tg = 0; tg < 9 / TB; ++tg) {
-            if (tg == (9 / TB) / 2) {  // prefetch the next A halo while the MMA works through this one
-              if (step + 1 < steps_per_group) issue_A(g, step + 1);
-              else if (g + gridDim.x < a.total) issue_A(g + gridDim.x, 0);
-            }
-            mbar_wait(bempty + 8 * sb, pb ^ 1);
-            if (elect_one()) {
-              if ((a.probe & 1) && bfills >= NB) {
-                mbar_arrive(bfull + 8 * sb);
-              } else {
-                mbar_expect_tx(bfull + 8 * sb, Cfg::B_BYTES);
-                tma_load_3d(sB + sb * Cfg::B_BYTES, &tmB, bfull + 8 * sb, kc * 64, 0, kt * 9 + tg * TB);
-              }
-            }
-            __syncwarp();
-            ++bfills;
-            if (++sb == NB) { sb = 0; pb ^= 1; }
+        for (int tg = 0; tg < 9 / TB; ++tg) {
+          if (tg == (9 / TB) / 2) {  // prefetch the next A halo while the MMA works through this one
+            if (step + 1 < steps_per_group) issue_A(u, step + 1);
+            else if (u + ustride < units) issue_A(u + ustride, 0);
           }
+          mbar_wait(bempty + 8 * sb, pb ^ 1);
+          if (elect_one()) {
+            if constexpr (PAIR) {
+              if (leader) mbar_expect_tx(bfull + 8 * sb, 2 * Cfg::B_BYTES);
+              tma_load_3d_2sm(sB + sb * Cfg::B_BYTES, &tmB, bfull + 8 * sb, kc * 64, (int)rank * Cfg::BROWS, kt * 9 + tg * TB);
+              if (!leader) mbar_arrive_leader(bfull + 8 * sb);
+            } else {
+              mbar_expect_tx(bfull + 8 * sb, Cfg::B_BYTES);
+              tma_load_3d(sB + sb * Cfg::B_BYTES, &tmB, bfull + 8 * sb, kc * 64, 0, kt * 9 + tg * TB);
+            }
+          }
+          __syncwarp();
+          if (++sb == NB) { sb = 0; pb ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    {
-      // ================= MMA issuer (warp-uniform loops, one elected lane issues) =================
-      constexpr uint32_t idesc = make_idesc(BN, TcFmt<T>::fmt);
+    if (leader) {
+      // ================= MMA issuer (leader CTA; warp-uniform loops, one elected lane issues) =================
+      constexpr uint32_t idesc = PAIR ? make_idesc_m256(BN, TcFmt<T>::fmt) : make_idesc(BN, TcFmt<T>::fmt);
+      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t accum) {
+        if constexpr (PAIR) umma_f16_2sm(d, ad, bd, idesc, accum); else umma_f16(d, ad, bd, idesc, accum);
+      };
+      auto commit = [&](uint32_t bar) { if constexpr (PAIR) umma_commit_2sm(bar); else umma_commit(bar); };
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       int iter = 0;
-      for (int64_t g = blockIdx.x; g < a.total; g += gridDim.x, ++iter) {
+      for (int64_t u = unit0; u < units; u += ustride, ++iter) {
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
         mbar_wait(tempty + 8 * acc, acc_phase ^ 1);
@@ -185,28 +209,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * Cfg::B_BYTES + tt * Cfg::B_TAP_BYTES);
 #pragma unroll
                 for (int i = 0; i < MT; ++i) {
-                  const uint64_t adesc = (a.probe & 16) ? make_halo_desc(a_stage + (uint32_t)(i * 16384), 1024)  // aligned-operand timing probe
-                                                        : make_halo_desc(a_stage + (uint32_t)((kh * PITCH + kw + 8 * i) * 128), PITCH * 128);
+                  const uint64_t adesc = make_halo_desc(a_stage + (uint32_t)((kh * PITCH + kw + 8 * i) * 128), PITCH * 128);
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    if (k < nk) umma_f16(d_tmem + i * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (step | tap9 | k) != 0);
+                    if (k < nk) mma(d_tmem + i * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (step | tap9 | k) != 0);
                 }
               }
-              umma_commit(bempty + 8 * sb);
+              commit(bempty + 8 * sb);
             }
             __syncwarp();
             if (++sb == NB) { sb = 0; pb ^= 1; }
           }
-          if (elect_one()) umma_commit(aempty + 8 * sa);
+          if (elect_one()) commit(aempty + 8 * sa);
           __syncwarp();
           if (++sa == NA) { sa = 0; pa ^= 1; }
         }
-        if (elect_one()) umma_commit(tfull + 8 * acc);
+        if (elect_one()) commit(tfull + 8 * acc);
         __syncwarp();
       }
     }
   } else {
-    // ================= epilogue warps =================
+    // ================= epilogue warps (every CTA: its own MT m-tiles, its own TMEM) =================
     const int q = warp & 3;  // TMEM lane quarter = rows 32q .. 32q+31 of every m-tile = tile rows 4q .. 4q+3
     const int hh = 4 * q + (lane >> 3), ww = lane & 7;
     double gacc[BN / 32];
@@ -233,11 +256,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int j = 0; j < BN / 32; ++j) gacc[j] = 0.0;
     };
     int iter = 0;
-    for (int64_t g = blockIdx.x; g < a.total; g += gridDim.x, ++iter) {
+    for (int64_t u = unit0; u < units; u += ustride, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
-      const HGroup m = decode_group(a, g, 8 * MT);
-      if (m.b != gb) { gn_flush(); gb = m.b; }
+      const HGroup m = decode_group(a, group_of(u), 8 * MT);
+      const bool live = m.b < a.B && !(a.probe & 4);
+      if (live && m.b != gb) { gn_flush(); gb = m.b; }
       // The staging rows of this warp are reused by every m-tile: they are free once the previous TMA stores have read
       // them.  The residual tile of the first m-tile is fetched while the MMAs of this group are still running.
       auto stage_acquire = [&](int i) {
@@ -252,13 +276,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         __syncwarp();
       };
-      stage_acquire(0);
+      if (live) stage_acquire(0);
       mbar_wait(tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const bool row_ok = (m.h0 + hh) < a.Ho;
 #pragma unroll 1
       for (int i = 0; i < MT; ++i) {
-        if (m.w0 + 8 * i >= a.Wo || (a.probe & 4)) continue;  // warp-uniform
+        if (!live || m.w0 + 8 * i >= a.Wo) continue;  // warp-uniform
         if (i > 0) stage_acquire(i);
         const bool valid = row_ok && (m.w0 + 8 * i + ww) < a.Wo;
         if (a.has_res) { mbar_wait(rbar, rph); rph ^= 1u; }
@@ -317,48 +341,70 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty + 8 * acc);
+      if constexpr (PAIR) {
+        if (leader) mbar_arrive(tempty + 8 * acc); else mbar_arrive_leader(tempty + 8 * acc);
+      } else {
+        mbar_arrive(tempty + 8 * acc);
+      }
     }
     gn_flush();
     if (lane == 0) bulk_wait0();
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  if constexpr (PAIR) {
+    cluster_sync_all();  // no CTA of the pair exits (or frees TMEM) while the other may still signal it
+    if (warp == 1) { tc_fence_after(); tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base); }
+  } else {
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
   }
 }
 
-template <typename T, int BN, int MT>
+template <typename T, int BN, int MT, bool PAIR>
 static int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
                          const HaloArgs& a, cudaStream_t stream) {
-  using Cfg = HaloCfg<BN, MT>;
+  using Cfg = HaloCfg<BN, MT, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_halo_kernel<T, BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_halo_kernel<T, BN, MT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
       return fail(HYVAE_ECUDA, "conv_halo: cannot opt in to %d bytes of shared memory", Cfg::SMEM_BYTES);
     attr_set = true;
   }
-  const int64_t grid = a.total < num_sms() ? a.total : num_sms();
-  conv_halo_kernel<T, BN, MT><<<(unsigned)grid, HALO_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, a);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  if (PAIR) {
+    const int64_t units = (a.total + 1) / 2, max_pairs = num_sms() / 2;
+    cfg.gridDim = dim3((unsigned)(2 * (units < max_pairs ? units : max_pairs)));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3((unsigned)(a.total < num_sms() ? a.total : num_sms()));
+  }
+  cfg.blockDim = dim3(HALO_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  if (cudaLaunchKernelEx(&cfg, conv_halo_kernel<T, BN, MT, PAIR>, tmA, tmB, tmY, tmR, a) != cudaSuccess)
+    return fail(HYVAE_ECUDA, "conv_halo: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return check_launch("conv3d_causal_tc (halo)");
 }
 
-void halo_geometry(int bn, int mt, int* twh, int* thh, int* taps_per_b) {
-  *twh = 8 * mt + 2; *thh = 18; *taps_per_b = bn >= 128 ? 1 : 3;
+// geometry the host needs for the tensor maps: A box {64, twh, thh}; B box {64, brows, taps_per_b}
+void halo_geometry(int bn, int mt, bool pair, int* twh, int* thh, int* taps_per_b, int* brows) {
+  *twh = 8 * mt + 2; *thh = 18; *taps_per_b = bn >= 128 ? 1 : 3; *brows = pair ? bn / 2 : bn;
 }
 
-int launch_halo(int dtype, int bn, int mt, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+int launch_halo(int dtype, int bn, int mt, bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
                 const CUtensorMap& tmR, const HaloArgs& a, cudaStream_t stream) {
-#define HYVAE_HALO_CASE(T)                                                                          \
-  if (bn == 128 && mt == 2) return launch_halo_t<T, 128, 2>(tmA, tmB, tmY, tmR, a, stream);          \
-  if (bn == 64 && mt == 2) return launch_halo_t<T, 64, 2>(tmA, tmB, tmY, tmR, a, stream);            \
-  if (bn == 32 && mt == 2) return launch_halo_t<T, 32, 2>(tmA, tmB, tmY, tmR, a, stream);
+#define HYVAE_HALO_CASE(T)                                                                                       \
+  if (bn == 128 && mt == 2) return pair ? launch_halo_t<T, 128, 2, true>(tmA, tmB, tmY, tmR, a, stream)           \
+                                        : launch_halo_t<T, 128, 2, false>(tmA, tmB, tmY, tmR, a, stream);         \
+  if (bn == 64 && mt == 2 && !pair) return launch_halo_t<T, 64, 2, false>(tmA, tmB, tmY, tmR, a, stream);         \
+  if (bn == 32 && mt == 2 && !pair) return launch_halo_t<T, 32, 2, false>(tmA, tmB, tmY, tmR, a, stream);
   if (dtype == HYVAE_BF16) { HYVAE_HALO_CASE(__nv_bfloat16) } else { HYVAE_HALO_CASE(__half) }
 #undef HYVAE_HALO_CASE
-  return fail(HYVAE_EUNSUPPORTED, "conv_halo: no instantiation for BN=%d MT=%d", bn, mt);
+  return fail(HYVAE_EUNSUPPORTED, "conv_halo: no instantiation for BN=%d MT=%d pair=%d", bn, mt, (int)pair);
 }
 
 }  // namespace hyvae

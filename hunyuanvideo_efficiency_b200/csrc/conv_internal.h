@@ -24,8 +24,8 @@ struct HaloArgs {
   int probe;
 };
 
-void halo_geometry(int bn, int mt, int* twh, int* thh, int* taps_per_b);  // A box {64, twh, thh}; B box {64, bn, taps_per_b}
-int launch_halo(int dtype, int bn, int mt, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+void halo_geometry(int bn, int mt, bool pair, int* twh, int* thh, int* taps_per_b, int* brows);
+int launch_halo(int dtype, int bn, int mt, bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
                 const CUtensorMap& tmR, const HaloArgs& a, cudaStream_t stream);
 
 }  // namespace hyvae

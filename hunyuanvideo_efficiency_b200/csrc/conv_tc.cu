@@ -730,15 +730,17 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
   // ---- halo kernel (conv_halo.cu): every stride-1 3x3x3 conv with Cout <= 128 and a 16-bit output (variant 5 forces it)
   const bool halo_ok = k == 3 && st == 1 && sh == 1 && sw == 1 && y->C <= 128 && y->dtype == x->dtype &&
                        (gn_partials == nullptr || (gn_groups > 0 && y->C % gn_groups == 0 && y->C / gn_groups >= 2));
-  if (variant == 5 || (variant == 0 && halo_ok)) {
+  if (variant == 5 || variant == 6 || (variant == 0 && halo_ok)) {  // 5 = force the 1-CTA form, 6 = force the CTA-pair form
     HYVAE_CHECK_ARG(k == 3 && st == 1 && sh == 1 && sw == 1 && y->C <= 128 && y->dtype == x->dtype, "halo kernel: needs k=3, stride 1, Cout <= 128, 16-bit output");
     const int bn = y->C > 64 ? 128 : (y->C > 32 ? 64 : 32), mt = 2;
-    int twh, thh, taps_per_b;
-    halo_geometry(bn, mt, &twh, &thh, &taps_per_b);
     HaloArgs h;
-    h.bias = bias; h.B = y->B; h.To = y->T; h.Ho = y->H; h.Wo = y->W; h.Cin = x->C; h.Cout = y->C;
     h.tiles_h = (y->H + 15) / 16; h.groups_w = (y->W + 8 * mt - 1) / (8 * mt);
     h.total = (int64_t)y->B * y->T * h.tiles_h * h.groups_w;
+    // CTA pairs (M = 256 MMAs, half of the weight tile per CTA) for the wide tile once there is work for every pair
+    const bool pair = bn == 128 && (variant == 6 || (variant == 0 && h.total >= num_sms()));
+    int twh, thh, taps_per_b, brows;
+    halo_geometry(bn, mt, pair, &twh, &thh, &taps_per_b, &brows);
+    h.bias = bias; h.B = y->B; h.To = y->T; h.Ho = y->H; h.Wo = y->W; h.Cin = x->C; h.Cout = y->C;
     h.has_res = residual != nullptr; h.round_like_ref = round_like_ref;
     h.gn_part = gn_partials; h.gn_groups = gn_groups; h.gn_cpg = 0; h.gn_rows = num_sms() * 4; h.probe = a.probe;
     if (gn_partials) {
@@ -760,7 +762,7 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
     {
       cuuint64_t dims[3] = {(cuuint64_t)x->C, (cuuint64_t)y->C, 27};
       cuuint64_t strides[2] = {(cuuint64_t)x->C * 2, (cuuint64_t)x->C * y->C * 2};
-      cuuint32_t box[3] = {64, (cuuint32_t)bn, (cuuint32_t)taps_per_b};
+      cuuint32_t box[3] = {64, (cuuint32_t)brows, (cuuint32_t)taps_per_b};
       cuuint32_t estr[3] = {1, 1, 1};
       CUresult r = encode(&tmB, dt, 3, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -784,9 +786,9 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
       tmR = tmY;
     }
     char tag[56];
-    snprintf(tag, sizeof(tag), "k3 %d->%d %dx%dx%dx%d s111 BN%d halo", x->C, y->C, y->B, y->T, y->H, y->W, bn);
+    snprintf(tag, sizeof(tag), "k3 %d->%d %dx%dx%dx%d s111 BN%d halo%s", x->C, y->C, y->B, y->T, y->H, y->W, bn, pair ? "2" : "");
     ProfScope prof(PC_CONV_TC, 2.0 * (double)y->B * y->T * y->H * y->W * y->C * x->C * 27, stream, tag);
-    return launch_halo(x->dtype, bn, mt, tmA, tmB, tmY, tmR, h, (cudaStream_t)stream);
+    return launch_halo(x->dtype, bn, mt, pair, tmA, tmB, tmY, tmR, h, (cudaStream_t)stream);
   }
 
   pick_tile(y->H, y->W, sh, sw, &a.TH, &a.TW);

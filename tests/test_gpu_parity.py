@@ -233,6 +233,11 @@ def test_tc_halo_kernel_matches_oracle_and_single_cta_kernel(B, Cin, Cout, T, H,
     ys = [N.conv3d_tc(xv, wp, b.to(_dev()), 3, (1, 1, 1), Cout, residual=r, variant=v, gn_groups=gn, round_like_ref=False)
           for v in (5, 2, 5, 0)]
     assert torch.equal(ys[0].t, ys[2].t) and torch.equal(ys[0].t, ys[3].t)      # reproducible; auto picks the halo kernel
+    if Cout > 64:   # CTA-pair form (cta_group::2, half of the weight tile per CTA): same MMA order, same result
+        yp = N.conv3d_tc(xv, wp, b.to(_dev()), 3, (1, 1, 1), Cout, residual=r, variant=6, gn_groups=gn, round_like_ref=False)
+        assert torch.equal(ys[0].t, yp.t)
+        if gn:
+            assert torch.allclose(ys[0].gn_sums, yp.gn_sums, rtol=1e-9, atol=1e-6)
     assert O.rel_err(ys[1].t.float().cpu(), ys[0].t.float().cpu()) < 1e-3
     if gn:
         assert torch.equal(ys[0].gn_sums, ys[2].gn_sums)

@@ -53,7 +53,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         run_case(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]))
     else:
-        cases = [("bignr", 5, 5), ("bignr", 5, 21), ("bignr", 2, 5), ("bignr", 5, 5), ("bignr", 5, 21), ("bignr", 2, 5), ("bignr", 5, 0), ("bignr", 5, 16), ("bignr", 2, 0)]
+        cases = [(n, 6, 0) for n in ("small", "rag", "c256", "big", "bignr", "big256")] + [("big", 5, 0), ("bignr", 5, 0), ("big", 6, 4), ("big", 5, 4)]
         for c in cases:
             p = subprocess.run([sys.executable, __file__, c[0], str(c[1]), str(c[2])], capture_output=True, text=True, timeout=120)
             print((p.stdout.strip() or "(no output)") + ("" if p.returncode == 0 else f"  [rc={p.returncode}] {p.stderr.strip()[-300:]}"), flush=True)
