@@ -144,18 +144,28 @@ template <> struct FastMath<float> { static constexpr bool value = false; };
 // y = silu(u).  16-bit paths: u * rcp(1 + ex2(-u * log2 e)) = FMUL + MUFU.EX2 + FADD + MUFU.RCP + FMUL.  Two MUFU per
 // element is 8 elements/clk/SM, ~2.2 T elements/s chip-wide, above what HBM can feed (1.6 T/s); the previous Newton
 // reciprocal made the kernel issue bound (ncu: 80 % issue slots busy at 48 % DRAM).  fp32 keeps expf and a division.
-template <typename T>
-__device__ __forceinline__ float gn_act(float u, int silu, int round_like_ref) {
-  if (round_like_ref) u = rnd<T>(u);
-  if (!silu) return u;
-  if (FastMath<T>::value) return __fdividef(u, 1.f + __expf(-u));  // u -> -inf: d = inf, rcp = 0, result -0
+// SILU / RLR are template flags: as run-time flags the compiler predicated the rounding instructions, which still
+// occupied issue slots (ncu: 21 warp instructions per element instead of ~10).
+// 16-bit paths: silu(u) = h + h * tanh(h) with h = u / 2 and ONE MUFU (tanh.approx.f32, max relative error 2^-11) per
+// element.  With ex2 + rcp the kernel was MUFU bound: 2 x 1.6e8 ops / (148 SMs x 16 per clk) = 72 us of a 128 us launch.
+// The absolute error, <= 2.4e-4 * |u|, is that of rounding a value of size |u| / 2 to fp16, i.e. it is of the size of the
+// storage rounding the result receives anyway.  fp32 keeps expf and a true division.
+template <typename T, bool SILU, bool RLR>
+__device__ __forceinline__ float gn_act(float u) {
+  if (RLR) u = rnd<T>(u);
+  if (!SILU) return u;
+  if (FastMath<T>::value) {
+    const float h = 0.5f * u;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+  }
   return u / (1.f + expf(-u));
 }
 
-template <typename T>
+template <typename T, bool SILU, bool RLR>
 __global__ void __launch_bounds__(256, 4) gn_apply_kernel(Vol x, Vol y, const double* __restrict__ sums, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, int groups, float eps, int silu, int round_like_ref,
-                                int rows_per_block) {
+                                const float* __restrict__ beta, int groups, float eps, int rows_per_block) {
   extern __shared__ float sh[];  // scale[C], shift[C]
   const int C = x.C, CV = C / 8, b = blockIdx.y;
   const int cpg = C / groups;
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(Vol x, Vol y, const do
             float f[8];
             q[u].get(f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = gn_act<T>(fmaf(f[j], rsc[j], rsf[j]), silu, round_like_ref);
+            for (int j = 0; j < 8; ++j) f[j] = gn_act<T, SILU, RLR>(fmaf(f[j], rsc[j], rsf[j]));
             q[u].set(f);
             q[u].store(drow + (int64_t)iu * 8);
           }
@@ -226,7 +236,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(Vol x, Vol y, const do
         Vec8<T> q; q.load(srow + (int64_t)w * x.sW + cv * 8);
         float f[8]; q.get(f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = gn_act<T>(fmaf(f[j], sh[cv * 8 + j], sh[C + cv * 8 + j]), silu, round_like_ref);
+        for (int j = 0; j < 8; ++j) f[j] = gn_act<T, SILU, RLR>(fmaf(f[j], sh[cv * 8 + j], sh[C + cv * 8 + j]));
         q.set(f);
         q.store(drow + (int64_t)i * 8);
       }
@@ -264,29 +274,34 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(double* __restrict__ p
 // ------------------------------------------------------------------------------------------------
 // replicate pad / nearest upsample (first frame not upsampled in T)
 // ------------------------------------------------------------------------------------------------
+// grid = (row chunks, B): a block walks destination rows (tp, hp) of Wp voxels, so the per-vector index math is 32-bit
+// shifts / one small division instead of 64-bit div/mod chains, and consecutive threads copy consecutive 16-byte vectors.
 template <typename T, int VEC>
-__global__ void pad_upsample_kernel(Vol x, Vol y, int up_t, int up_h, int up_w) {
+__global__ void __launch_bounds__(256) pad_upsample_kernel(Vol x, Vol y, int up_t, int up_h, int up_w, int rows_per_block) {
   const int CV = y.C / VEC;  // y.C == x.C on the vector path; y.C >= x.C (zero channel padding) on the scalar path
-  const int64_t nvp = (int64_t)y.B * y.Tp() * y.Hp() * y.Wp();
-  const int64_t total = nvp * CV;
+  const int b = blockIdx.y;
+  const int Wp = y.Wp(), Hp = y.Hp();
+  const int nrows = y.Tp() * Hp;
+  const int row_elems = Wp * CV;
   const T* xs = reinterpret_cast<const T*>(x.p);
-  T* yd = reinterpret_cast<T*>(y.p);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(i % CV);
-    int64_t v = i / CV;
-    int wp = (int)(v % y.Wp()); int64_t r = v / y.Wp();
-    int hp = (int)(r % y.Hp()); r /= y.Hp();
-    int tp = (int)(r % y.Tp()); int b = (int)(r / y.Tp());
-    int t = max(tp - y.pt, 0);
-    int h = min(max(hp - y.ph, 0), y.H - 1);
-    int w = min(max(wp - y.pw, 0), y.W - 1);
-    int ts = (up_t == 2) ? (t == 0 ? 0 : 1 + ((t - 1) >> 1)) : t;
-    int hs = (up_h == 2) ? (h >> 1) : h;
-    int ws = (up_w == 2) ? (w >> 1) : w;
-    const T* s = xs + x.at(b, ts, hs, ws) + cv * VEC;
-    T* o = yd + v * y.C + cv * VEC;
-    if (VEC == 8) { Vec8<T> q; q.load(s); q.store(o); }
-    else { o[0] = (cv < x.C) ? s[0] : from_f<T>(0.f); }
+  T* yd = reinterpret_cast<T*>(y.p) + (int64_t)b * y.sB;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, nrows);
+  for (int r = r0; r < r1; ++r) {
+    const int tp = r / Hp, hp = r - tp * Hp;
+    const int t = max(tp - y.pt, 0), h = min(max(hp - y.ph, 0), y.H - 1);
+    const int ts = (up_t == 2) ? (t == 0 ? 0 : 1 + ((t - 1) >> 1)) : t;
+    const int hs = (up_h == 2) ? (h >> 1) : h;
+    const T* srow = xs + x.at(b, ts, hs, 0);
+    T* drow = yd + (int64_t)r * Wp * y.C;
+    for (int i = threadIdx.x; i < row_elems; i += blockDim.x) {
+      const int wp = i / CV, cv = i - wp * CV;
+      const int w = min(max(wp - y.pw, 0), y.W - 1);
+      const int ws = (up_w == 2) ? (w >> 1) : w;
+      const T* sp = srow + (int64_t)ws * x.sW + cv * VEC;
+      T* o = drow + (int64_t)i * VEC;
+      if (VEC == 8) { Vec8<T> q; q.load(sp); q.store(o); }
+      else { o[0] = (cv < x.C) ? sp[0] : from_f<T>(0.f); }
+    }
   }
 }
 
@@ -523,8 +538,11 @@ int hyvae_groupnorm_apply(const hyvae_vol* x, const double* sums, const float* g
   while (rpb > 1 && (int64_t)((nrows + rpb - 1) / rpb) * x->B < 8 * num_sms()) rpb >>= 1;
   dim3 grid((unsigned)((nrows + rpb - 1) / rpb), (unsigned)x->B);
   size_t smem = sizeof(float) * 2 * x->C;
-  HYVAE_DISPATCH_DTYPE(x->dtype, T, (gn_apply_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
-      vx, vy, sums, gamma, beta, groups, eps, silu, round_like_ref, rpb)));
+#define HYVAE_GN_LAUNCH(S, R) \
+  HYVAE_DISPATCH_DTYPE(x->dtype, T, (gn_apply_kernel<T, S, R><<<grid, 256, smem, (cudaStream_t)stream>>>(vx, vy, sums, gamma, beta, groups, eps, rpb)))
+  if (silu) { if (round_like_ref) { HYVAE_GN_LAUNCH(true, true); } else { HYVAE_GN_LAUNCH(true, false); } }
+  else { if (round_like_ref) { HYVAE_GN_LAUNCH(false, true); } else { HYVAE_GN_LAUNCH(false, false); } }
+#undef HYVAE_GN_LAUNCH
   return check_launch("groupnorm_apply");
 }
 
@@ -545,10 +563,16 @@ int hyvae_pad_upsample(const hyvae_vol* x, const hyvae_vol* y, int32_t up_t, int
   Vol vx = make_vol(x), vy = make_vol(y);
   int64_t nvp = (int64_t)vy.B * vy.Tp() * vy.Hp() * vy.Wp();
   ProfScope prof(PC_PAD_UPSAMPLE, (double)nvp * x->C * dtype_size(x->dtype) + (double)x->B * x->T * x->H * x->W * x->C * dtype_size(x->dtype), stream);
+  // rows of Wp*C contiguous elements; >= ~32 KB of output per block and >= ~8 blocks per SM when possible
+  const int nrows = vy.Tp() * vy.Hp();
+  const int64_t row_bytes = (int64_t)vy.Wp() * y->C * dtype_size(x->dtype);
+  int rpb = (int)((32768 + row_bytes - 1) / row_bytes);
+  while (rpb > 1 && (int64_t)((nrows + rpb - 1) / rpb) * x->B < 8 * num_sms()) rpb >>= 1;
+  dim3 grid((unsigned)((nrows + rpb - 1) / rpb), (unsigned)x->B);
   if (x->C % 8 == 0 && x->C == y->C) {
-    HYVAE_DISPATCH_DTYPE(x->dtype, T, (pad_upsample_kernel<T, 8><<<grid_for(nvp * (x->C / 8), 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, up_t, up_h, up_w)));
+    HYVAE_DISPATCH_DTYPE(x->dtype, T, (pad_upsample_kernel<T, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(vx, vy, up_t, up_h, up_w, rpb)));
   } else {
-    HYVAE_DISPATCH_DTYPE(x->dtype, T, (pad_upsample_kernel<T, 1><<<grid_for(nvp * y->C, 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, up_t, up_h, up_w)));
+    HYVAE_DISPATCH_DTYPE(x->dtype, T, (pad_upsample_kernel<T, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(vx, vy, up_t, up_h, up_w, rpb)));
   }
   return check_launch("pad_upsample");
 }

@@ -21,6 +21,19 @@ if what in CASES:
         r = N.Vol(1, T, H, W, Cout, torch.float16, dev); r.t.normal_()
     for _ in range(4):
         N.conv3d_tc(x, w, b, 3, (1, 1, 1), Cout, residual=r, out=y, gn_groups=32 if Cout >= 64 else 0, variant=variant)
+elif what == "phase":   # decoder up_block2 upsampler: 256 -> 256, low-res 9 x 128 x 128 -> 17 x 256 x 256
+    from hunyuanvideo_efficiency_b200.vae.blocks import UpsampleCausal3D
+    m = UpsampleCausal3D(256, use_conv=True, out_channels=256, upsample_factor=(2, 2, 2)).to(dev)
+    x = N.Vol(1, 9, 128, 128, 256, torch.float16, dev); x.t.normal_()
+    for _ in range(3):
+        m.forward_vol(x)
+elif what == "conv512s":  # mid-block conv at the canonical tile: 512 -> 512, 17 x 32 x 32
+    x = N.Vol(1, 17, 32, 32, 512, torch.float16, dev, (2, 1, 1)); x.t.normal_()
+    w = (torch.randn(27, 512, 512, device=dev) / (27 * 512) ** 0.5).half()
+    b = torch.randn(512, device=dev)
+    r = N.Vol(1, 17, 32, 32, 512, torch.float16, dev); r.t.normal_()
+    for _ in range(6):
+        N.conv3d_tc(x, w, b, 3, (1, 1, 1), 512, residual=r, gn_groups=32)
 else:
     x = N.Vol(1, 17, 256, 256, 128, torch.float16, dev); x.t.normal_()
     g, b = torch.ones(128, device=dev), torch.zeros(128, device=dev)
