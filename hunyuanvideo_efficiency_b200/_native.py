@@ -49,7 +49,7 @@ _SIGNATURES = {
                                  _i32, _i32, _i32, _i32, C.POINTER(_i64), _vp],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["hyvae_version", "hyvae_last_error", "hyvae_device_supports_tc", "hyvae_launch_count",
-                                       "hyvae_groupnorm_workspace_bytes", "hyvae_profile_begin", "hyvae_profile_end",
+                                       "hyvae_groupnorm_workspace_bytes", "hyvae_profile_begin", "hyvae_profile_end", "hyvae_profile_executed_flops",
                                        "hyvae_conv3d_tc_gn_rows"])
 
 _lib = None
@@ -73,6 +73,8 @@ def lib():
         l.hyvae_launch_count.restype = C.c_int64
         l.hyvae_groupnorm_workspace_bytes.restype = C.c_int64
         l.hyvae_groupnorm_workspace_bytes.argtypes = [_VP, _i32]
+        l.hyvae_profile_executed_flops.restype = C.c_double
+        l.hyvae_profile_executed_flops.argtypes = []
         l.hyvae_conv3d_tc_gn_rows.restype = C.c_int64
         l.hyvae_conv3d_tc_gn_rows.argtypes = []
         _lib = l
@@ -102,7 +104,9 @@ def profile_end() -> dict:
     fn = lib().hyvae_profile_end
     fn.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]
     _check(fn(ms, work, cnt, n), "profile_end")
-    return {k: {"ms": ms[i], "work": work[i], "launches": int(cnt[i])} for i, k in enumerate(PROFILE_CLASSES)}
+    out = {k: {"ms": ms[i], "work": work[i], "launches": int(cnt[i])} for i, k in enumerate(PROFILE_CLASSES)}
+    out["conv_tc"]["executed"] = float(lib().hyvae_profile_executed_flops())
+    return out
 
 
 def launch_count() -> int:

@@ -43,6 +43,7 @@ enum ProfClass { PC_CONV_TC = 0, PC_CONV_DIRECT, PC_GN_STATS, PC_GN_APPLY, PC_PA
                  PC_TEMPORAL, PC_COUNT };
 struct ProfRec { cudaEvent_t a, b; int cls; double work; char tag[56]; };
 extern bool g_prof_on;
+extern double g_prof_exec_flops;  // tensor-core MACs*2 actually issued while profiling (<= algorithmic work: sub-pixel phases)
 extern std::vector<ProfRec> g_prof;
 extern std::vector<cudaEvent_t> g_prof_pool;
 inline cudaEvent_t prof_event() {
@@ -54,8 +55,9 @@ inline cudaEvent_t prof_event() {
 // RAII: brackets the launches of one C-ABI call with two events.  `work` = algorithmic flops or bytes.
 struct ProfScope {
   bool on; cudaStream_t st; ProfRec r;
-  ProfScope(int cls, double work, void* stream, const char* tag = "") : on(g_prof_on), st((cudaStream_t)stream) {
+  ProfScope(int cls, double work, void* stream, const char* tag = "", double executed = -1.0) : on(g_prof_on), st((cudaStream_t)stream) {
     if (on) {
+      if (cls == PC_CONV_TC) g_prof_exec_flops += executed >= 0.0 ? executed : work;
       r.cls = cls; r.work = work; r.a = prof_event(); r.b = prof_event();
       snprintf(r.tag, sizeof(r.tag), "%s", tag);
       cudaEventRecord(r.a, st);

@@ -957,7 +957,8 @@ extern "C" int hyvae_conv3d_upphase_tc(const hyvae_vol* x, const void* w, const 
   char tag[56];
   snprintf(tag, sizeof(tag), "up%d22 p%d%d%d %d->%d lo %dx%dx%dx%d BN%d", up_t, pt, ph, pw, x->C, y->C, y->B, To, x->H, x->W, BN);
   // algorithmic work = what the reference executes for these output voxels: 27 taps at high resolution
-  ProfScope prof(PC_CONV_TC, 2.0 * (double)y->B * To * x->H * x->W * y->C * x->C * 27, stream, tag);
+  ProfScope prof(PC_CONV_TC, 2.0 * (double)y->B * To * x->H * x->W * y->C * x->C * 27, stream, tag,
+                 2.0 * (double)y->B * To * x->H * x->W * y->C * x->C * nkt * 4);
 #define HYVAE_UP_LAUNCH(T)                                                           \
   switch (BN) {                                                                      \
     case 256: return launch_tc2<T, T, 256, true>(tmA, tmB, a, s);                    \

@@ -12,6 +12,7 @@ namespace hyvae {
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 bool g_prof_on = false;
+double g_prof_exec_flops = 0.0;
 std::vector<ProfRec> g_prof;
 std::vector<cudaEvent_t> g_prof_pool;
 
@@ -425,9 +426,12 @@ int64_t hyvae_launch_count(void) { return g_launches.load(); }
 int hyvae_profile_begin(void) {
   for (auto& r : g_prof) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
   g_prof.clear();
+  g_prof_exec_flops = 0.0;
   g_prof_on = true;
   return HYVAE_OK;
 }
+
+double hyvae_profile_executed_flops(void) { return g_prof_exec_flops; }
 
 int hyvae_profile_end(double* ms, double* work, int64_t* launches, int32_t n_classes) {
   g_prof_on = false;

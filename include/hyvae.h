@@ -152,6 +152,9 @@ int hyvae_blend_crop_scatter(void* cur, const void* above, const void* left, int
 #define HYVAE_PROFILE_CLASSES 9
 int hyvae_profile_begin(void);
 int hyvae_profile_end(double* ms, double* work, int64_t* launches, int32_t n_classes);
+/* Tensor-core flops actually issued by the conv launches since hyvae_profile_begin: equals the algorithmic work except
+ * for hyvae_conv3d_upphase_tc, which needs 8/27 (12/27) of the reference's MACs. */
+double hyvae_profile_executed_flops(void);
 
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t hyvae_launch_count(void);
