@@ -76,7 +76,8 @@ __device__ __forceinline__ HGroup decode_group(const HaloArgs& a, int64_t g, int
 template <typename T, int BN, int MT, bool PAIR>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const HaloArgs a) {
+                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const HaloArgs a) {
   using Cfg = HaloCfg<BN, MT, PAIR>;
   constexpr int NA = Cfg::NA, NB = Cfg::NB, NH = Cfg::NH, PITCH = Cfg::PITCH, TB = Cfg::TB;
   extern __shared__ uint8_t smem_raw[];
@@ -101,6 +102,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY);
     if (a.has_res) tma_prefetch_desc(&tmR);
+    if (a.sc_chunks) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW); }
     for (int s = 0; s < NA; ++s) { mbar_init(afull + 8 * s, NCTA); mbar_init(aempty + 8 * s, 1); }
     for (int s = 0; s < NB; ++s) { mbar_init(bfull + 8 * s, NCTA); mbar_init(bempty + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull + 8 * s, 1); mbar_init(tempty + 8 * s, 128 * NCTA); }
@@ -121,7 +123,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int kchunks = (a.Cin + 63) / 64;
-  const int steps_per_group = 3 * kchunks;  // (kt, kc)
+  // steps of a group: (kt, kc) of the 3x3x3 conv, then — fused 1x1x1 conv_shortcut of the resnet block
+  // (unet_causal_3d_blocks.py:407-415) — one step per 64-channel chunk of the block input, whose halo stage is read
+  // at the centre tap only and multiplied with the shortcut weights into the same accumulator
+  const int steps_main = 3 * kchunks;
+  const int steps_per_group = steps_main + a.sc_chunks;
   // work units: a group of MT m-tiles per CTA; a CTA pair walks two consecutive groups (2u, 2u+1) per unit
   const int64_t unit0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
   const int64_t ustride = PAIR ? (gridDim.x >> 1) : gridDim.x;
@@ -133,16 +139,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
     auto issue_A = [&](int64_t u, int step) {
       const HGroup m = decode_group(a, group_of(u), 8 * MT);
-      const int kt = step / kchunks, kc = step % kchunks;
+      const bool sc = step >= steps_main;
+      const int kt = step / kchunks, kc = sc ? step - steps_main : step % kchunks;
+      // shortcut input: logical (unpadded) coordinates, the 1-voxel rim of the box is never read
+      const CUtensorMap* map = sc ? &tmX : &tmA;
+      const int cw = sc ? m.w0 - 1 : m.w0, ch = sc ? m.h0 - 1 : m.h0, ct = sc ? m.t : m.t + kt;
       mbar_wait(aempty + 8 * sa, pa ^ 1);
       if (elect_one()) {
         if constexpr (PAIR) {
           if (leader) mbar_expect_tx(afull + 8 * sa, 2 * Cfg::A_TX);
-          tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull + 8 * sa, kc * 64, m.w0, m.h0, m.t + kt, m.b);
+          tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, map, afull + 8 * sa, kc * 64, cw, ch, ct, m.b);
           if (!leader) mbar_arrive_leader(afull + 8 * sa);
         } else {
           mbar_expect_tx(afull + 8 * sa, Cfg::A_TX);
-          tma_load_5d(sA + sa * Cfg::A_BYTES, &tmA, afull + 8 * sa, kc * 64, m.w0, m.h0, m.t + kt, m.b);
+          tma_load_5d(sA + sa * Cfg::A_BYTES, map, afull + 8 * sa, kc * 64, cw, ch, ct, m.b);
         }
       }
       __syncwarp();
@@ -152,22 +162,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int64_t u = unit0; u < units; u += ustride) {
       for (int step = 0; step < steps_per_group; ++step) {
         if (first) { issue_A(u, step); first = false; }
-        const int kt = step / kchunks, kc = step % kchunks;
+        const bool sc = step >= steps_main;
+        const int kt = step / kchunks, kc = sc ? step - steps_main : step % kchunks;
+        const int ntg = sc ? 1 : 9 / TB;  // weight stages of this step (the shortcut has a single tap; TB == 1 there)
+        const CUtensorMap* wmap = sc ? &tmW : &tmB;
 #pragma unroll 1
-        for (int tg = 0; tg < 9 / TB; ++tg) {
-          if (tg == (9 / TB) / 2) {  // prefetch the next A halo while the MMA works through this one
+        for (int tg = 0; tg < ntg; ++tg) {
+          if (tg == ntg / 2) {  // prefetch the next A halo while the MMA works through this one
             if (step + 1 < steps_per_group) issue_A(u, step + 1);
             else if (u + ustride < units) issue_A(u + ustride, 0);
           }
+          const int wtap = sc ? 0 : kt * 9 + tg * TB;
           mbar_wait(bempty + 8 * sb, pb ^ 1);
           if (elect_one()) {
             if constexpr (PAIR) {
               if (leader) mbar_expect_tx(bfull + 8 * sb, 2 * Cfg::B_BYTES);
-              tma_load_3d_2sm(sB + sb * Cfg::B_BYTES, &tmB, bfull + 8 * sb, kc * 64, (int)rank * Cfg::BROWS, kt * 9 + tg * TB);
+              tma_load_3d_2sm(sB + sb * Cfg::B_BYTES, wmap, bfull + 8 * sb, kc * 64, (int)rank * Cfg::BROWS, wtap);
               if (!leader) mbar_arrive_leader(bfull + 8 * sb);
             } else {
               mbar_expect_tx(bfull + 8 * sb, Cfg::B_BYTES);
-              tma_load_3d(sB + sb * Cfg::B_BYTES, &tmB, bfull + 8 * sb, kc * 64, 0, kt * 9 + tg * TB);
+              tma_load_3d(sB + sb * Cfg::B_BYTES, wmap, bfull + 8 * sb, kc * 64, 0, wtap);
             }
           }
           __syncwarp();
@@ -195,16 +209,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(afull + 8 * sa, pa);
           const uint32_t a_stage = sA + sa * Cfg::A_BYTES;
           // K = 16 slices that hold real channels in this 64-channel chunk (thin layers: conv_in has Cin = 8)
-          const int rem = a.Cin - (step % kchunks) * 64;
+          const bool sc = step >= steps_main;
+          const int rem = sc ? a.sc_cin - (step - steps_main) * 64 : a.Cin - (step % kchunks) * 64;
           const int nk = rem >= 64 ? 4 : (rem + 15) / 16;
+          const int ntg = sc ? 1 : 9 / TB;
 #pragma unroll 1
-          for (int tg = 0; tg < 9 / TB; ++tg) {
+          for (int tg = 0; tg < ntg; ++tg) {
             mbar_wait(bfull + 8 * sb, pb);
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
               for (int tt = 0; tt < TB; ++tt) {
-                const int tap9 = tg * TB + tt;
+                if (sc && tt > 0) break;
+                const int tap9 = sc ? 4 : tg * TB + tt;  // shortcut: centre tap (kh, kw) = (1, 1)
                 const int kh = tap9 / 3, kw = tap9 - 3 * kh;
                 const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * Cfg::B_BYTES + tt * Cfg::B_TAP_BYTES);
 #pragma unroll
@@ -363,7 +380,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <typename T, int BN, int MT, bool PAIR>
 static int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
-                         const HaloArgs& a, cudaStream_t stream) {
+                         const CUtensorMap& tmX, const CUtensorMap& tmW, const HaloArgs& a, cudaStream_t stream) {
   using Cfg = HaloCfg<BN, MT, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -385,7 +402,7 @@ static int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   cfg.blockDim = dim3(HALO_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  if (cudaLaunchKernelEx(&cfg, conv_halo_kernel<T, BN, MT, PAIR>, tmA, tmB, tmY, tmR, a) != cudaSuccess)
+  if (cudaLaunchKernelEx(&cfg, conv_halo_kernel<T, BN, MT, PAIR>, tmA, tmB, tmY, tmR, tmX, tmW, a) != cudaSuccess)
     return fail(HYVAE_ECUDA, "conv_halo: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return check_launch("conv3d_causal_tc (halo)");
 }
@@ -396,12 +413,12 @@ void halo_geometry(int bn, int mt, bool pair, int* twh, int* thh, int* taps_per_
 }
 
 int launch_halo(int dtype, int bn, int mt, bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
-                const CUtensorMap& tmR, const HaloArgs& a, cudaStream_t stream) {
+                const CUtensorMap& tmR, const CUtensorMap& tmX, const CUtensorMap& tmW, const HaloArgs& a, cudaStream_t stream) {
 #define HYVAE_HALO_CASE(T)                                                                                       \
-  if (bn == 128 && mt == 2) return pair ? launch_halo_t<T, 128, 2, true>(tmA, tmB, tmY, tmR, a, stream)           \
-                                        : launch_halo_t<T, 128, 2, false>(tmA, tmB, tmY, tmR, a, stream);         \
-  if (bn == 64 && mt == 2 && !pair) return launch_halo_t<T, 64, 2, false>(tmA, tmB, tmY, tmR, a, stream);         \
-  if (bn == 32 && mt == 2 && !pair) return launch_halo_t<T, 32, 2, false>(tmA, tmB, tmY, tmR, a, stream);
+  if (bn == 128 && mt == 2) return pair ? launch_halo_t<T, 128, 2, true>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream)           \
+                                        : launch_halo_t<T, 128, 2, false>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream);         \
+  if (bn == 64 && mt == 2 && !pair) return launch_halo_t<T, 64, 2, false>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream);         \
+  if (bn == 32 && mt == 2 && !pair) return launch_halo_t<T, 32, 2, false>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream);
   if (dtype == HYVAE_BF16) { HYVAE_HALO_CASE(__nv_bfloat16) } else { HYVAE_HALO_CASE(__half) }
 #undef HYVAE_HALO_CASE
   return fail(HYVAE_EUNSUPPORTED, "conv_halo: no instantiation for BN=%d MT=%d pair=%d", bn, mt, (int)pair);

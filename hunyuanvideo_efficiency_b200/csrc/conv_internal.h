@@ -18,6 +18,7 @@ struct HaloArgs {
   int tiles_h, groups_w;   // 16-row tiles, groups of MT 8-column m-tiles
   int64_t total;           // B * To * tiles_h * groups_w
   int has_res;
+  int sc_chunks, sc_cin;   // fused 1x1x1 shortcut conv: 64-channel chunks / channels of its input (0 = none)
   int round_like_ref;      // round conv + bias to the storage type before adding the residual
   double* gn_part;         // optional [B][gn_rows][gn_groups][2]
   int gn_groups, gn_cpg, gn_rows;
@@ -26,6 +27,6 @@ struct HaloArgs {
 
 void halo_geometry(int bn, int mt, bool pair, int* twh, int* thh, int* taps_per_b, int* brows);
 int launch_halo(int dtype, int bn, int mt, bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
-                const CUtensorMap& tmR, const HaloArgs& a, cudaStream_t stream);
+                const CUtensorMap& tmR, const CUtensorMap& tmX, const CUtensorMap& tmW, const HaloArgs& a, cudaStream_t stream);
 
 }  // namespace hyvae

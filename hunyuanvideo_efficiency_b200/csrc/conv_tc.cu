@@ -690,10 +690,33 @@ static void pick_tile(int Ho, int Wo, int sh, int sw, int* TH, int* TW) {
 
 extern "C" int64_t hyvae_conv3d_tc_gn_rows(void) { return (int64_t)num_sms() * 4; }
 
+static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
+                         const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
+                         int32_t round_like_ref, int32_t variant, double* gn_partials, int32_t gn_groups,
+                         const hyvae_vol* sc_x, const void* sc_w, void* stream);
+
 extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
                                       const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
                                       int32_t round_like_ref, int32_t variant, double* gn_partials, int32_t gn_groups,
                                       void* stream) {
+  return conv_tc_entry(x, w, bias, residual, y, k, st, sh, sw, round_like_ref, variant, gn_partials, gn_groups, nullptr, nullptr, stream);
+}
+
+// conv2 of a ResnetBlockCausal3D whose skip path is a 1x1x1 conv_shortcut (unet_causal_3d_blocks.py:407-415):
+// y = conv3x3x3(x) + sc_w * sc_x + bias, where bias is the SUM of both convs' biases.  The shortcut runs as extra K
+// chunks of the same accumulator, so its output tensor is never written or re-read.
+extern "C" int hyvae_conv3d_causal_tc_shortcut(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* sc_x,
+                                               const void* sc_w, const hyvae_vol* y, double* gn_partials, int32_t gn_groups,
+                                               void* stream) {
+  if (int e = check_vol(sc_x, "sc_x")) return e;
+  HYVAE_CHECK_ARG(sc_w != nullptr, "sc_w is null");
+  return conv_tc_entry(x, w, bias, nullptr, y, 3, 1, 1, 1, 0, 0, gn_partials, gn_groups, sc_x, sc_w, stream);
+}
+
+static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
+                         const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
+                         int32_t round_like_ref, int32_t variant, double* gn_partials, int32_t gn_groups,
+                         const hyvae_vol* sc_x, const void* sc_w, void* stream) {
   if (int e = check_vol(x, "x")) return e;
   if (int e = check_vol(y, "y")) return e;
   HYVAE_CHECK_ARG(w != nullptr, "w is null");
@@ -730,6 +753,12 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
   // ---- halo kernel (conv_halo.cu): every stride-1 3x3x3 conv with Cout <= 128 and a 16-bit output (variant 5 forces it)
   const bool halo_ok = k == 3 && st == 1 && sh == 1 && sw == 1 && y->C <= 128 && y->dtype == x->dtype &&
                        (gn_partials == nullptr || (gn_groups > 0 && y->C % gn_groups == 0 && y->C / gn_groups >= 2));
+  if (sc_x != nullptr) {
+    HYVAE_CHECK_ARG(halo_ok && y->C > 64, "fused shortcut needs a stride-1 3x3x3 conv with 64 < Cout <= 128 and a 16-bit output");
+    HYVAE_CHECK_ARG(sc_x->dtype == x->dtype && sc_x->B == y->B && sc_x->T == y->T && sc_x->H == y->H && sc_x->W == y->W && sc_x->C % 8 == 0,
+                    "shortcut input must have y's extent and x's dtype");
+    HYVAE_CHECK_ARG(((uintptr_t)sc_x->data & 15) == 0 && ((uintptr_t)sc_w & 15) == 0, "pointers must be 16-byte aligned");
+  }
   if (variant == 5 || variant == 6 || (variant == 0 && halo_ok)) {  // 5 = force the 1-CTA form, 6 = force the CTA-pair form
     HYVAE_CHECK_ARG(k == 3 && st == 1 && sh == 1 && sw == 1 && y->C <= 128 && y->dtype == x->dtype, "halo kernel: needs k=3, stride 1, Cout <= 128, 16-bit output");
     const int bn = y->C > 64 ? 128 : (y->C > 32 ? 64 : 32), mt = 2;
@@ -742,6 +771,7 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
     halo_geometry(bn, mt, pair, &twh, &thh, &taps_per_b, &brows);
     h.bias = bias; h.B = y->B; h.To = y->T; h.Ho = y->H; h.Wo = y->W; h.Cin = x->C; h.Cout = y->C;
     h.has_res = residual != nullptr; h.round_like_ref = round_like_ref;
+    h.sc_cin = sc_x ? sc_x->C : 0; h.sc_chunks = (h.sc_cin + 63) / 64;
     h.gn_part = gn_partials; h.gn_groups = gn_groups; h.gn_cpg = 0; h.gn_rows = num_sms() * 4; h.probe = a.probe;
     if (gn_partials) {
       HYVAE_CHECK_ARG(gn_groups > 0 && y->C % gn_groups == 0, "gn_groups=%d does not divide Cout=%d", gn_groups, y->C);
@@ -785,12 +815,32 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
     } else {
       tmR = tmY;
     }
+    CUtensorMap tmX = tmA, tmW = tmB;
+    if (sc_x) {
+      Vol vs = make_vol(sc_x);
+      cuuint64_t dims[5] = {(cuuint64_t)sc_x->C, (cuuint64_t)sc_x->W, (cuuint64_t)sc_x->H, (cuuint64_t)sc_x->T, (cuuint64_t)sc_x->B};
+      cuuint64_t strides[4] = {(cuuint64_t)vs.sW * 2, (cuuint64_t)vs.sH * 2, (cuuint64_t)vs.sT * 2, (cuuint64_t)vs.sB * 2};
+      cuuint32_t box[5] = {64, (cuuint32_t)twh, (cuuint32_t)thh, 1, 1};
+      cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+      CUresult r = encode(&tmX, dt, 5, (char*)sc_x->data + vs.at(0, 0, 0, 0) * 2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(shortcut x) failed with %d", (int)r);
+      cuuint64_t wd[3] = {(cuuint64_t)sc_x->C, (cuuint64_t)y->C, 1};
+      cuuint64_t ws[2] = {(cuuint64_t)sc_x->C * 2, (cuuint64_t)sc_x->C * y->C * 2};
+      cuuint32_t wb[3] = {64, (cuuint32_t)brows, 1};
+      cuuint32_t we[3] = {1, 1, 1};
+      r = encode(&tmW, dt, 3, const_cast<void*>(sc_w), wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(shortcut w) failed with %d", (int)r);
+    }
     char tag[56];
-    snprintf(tag, sizeof(tag), "k3 %d->%d %dx%dx%dx%d s111 BN%d halo%s", x->C, y->C, y->B, y->T, y->H, y->W, bn, pair ? "2" : "");
-    ProfScope prof(PC_CONV_TC, 2.0 * (double)y->B * y->T * y->H * y->W * y->C * x->C * 27, stream, tag);
-    return launch_halo(x->dtype, bn, mt, pair, tmA, tmB, tmY, tmR, h, (cudaStream_t)stream);
+    snprintf(tag, sizeof(tag), "k3 %d->%d %dx%dx%dx%d s111 BN%d halo%s%s", x->C, y->C, y->B, y->T, y->H, y->W, bn, pair ? "2" : "", sc_x ? "+sc" : "");
+    const double vox = (double)y->B * y->T * y->H * y->W;
+    ProfScope prof(PC_CONV_TC, 2.0 * vox * y->C * (x->C * 27.0 + (sc_x ? sc_x->C : 0)), stream, tag);
+    return launch_halo(x->dtype, bn, mt, pair, tmA, tmB, tmY, tmR, tmX, tmW, h, (cudaStream_t)stream);
   }
 
+  if (sc_x != nullptr) return fail(HYVAE_EUNSUPPORTED, "fused shortcut is only implemented in the halo kernel");
   pick_tile(y->H, y->W, sh, sw, &a.TH, &a.TW);
   // variant: 0 = auto, 1 = 1-CTA kernel with MT=1, 2 = 1-CTA kernel, 3 = CTA-pair kernel without the kh trick
   const int BN_sel = y->C > 128 ? 256 : (y->C > 64 ? 128 : (y->C > 32 ? 64 : 32));

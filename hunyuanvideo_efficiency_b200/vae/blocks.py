@@ -290,8 +290,28 @@ class ResnetBlockCausal3D(nn.Module):
         h = self.norm1.forward_vol(x, True, self.conv1.wants_halo(x.dtype))
         h = self.conv1.forward_vol(h)
         h = self.norm2.forward_vol(h, True, self.conv2.wants_halo(x.dtype))
+        if self.conv_shortcut is not None and self._can_fuse_shortcut(h, x):
+            return self._conv2_with_shortcut(h, x)
         skip = x if self.conv_shortcut is None else self.conv_shortcut.forward_vol(x)
         return self.conv2.forward_vol(h, residual=skip)
+
+    def _can_fuse_shortcut(self, h: Vol, x: Vol) -> bool:
+        """The 1x1x1 conv_shortcut runs as extra K chunks of conv2's accumulator (hyvae_conv3d_causal_tc_shortcut) when
+        conv2 is served by the halo kernel: 16-bit tensor-core path, 64 < Cout <= 128."""
+        c2, cs = self.conv2.conv, self.conv_shortcut.conv
+        return (os.environ.get("HYVAE_FUSE_SHORTCUT", "1") == "1" and h.dtype in _16BIT and 64 < c2.out_channels <= 128
+                and c2.out_channels % 8 == 0 and cs.in_channels % 8 == 0 and x.C == cs.in_channels and h.pad == self.conv2.halo
+                and h.C == c2.in_channels and c2.bias is not None and cs.bias is not None
+                and tc_eligible(h.dtype, c2.in_channels, c2.out_channels, (1, 1, 1), 3))
+
+    def _conv2_with_shortcut(self, h: Vol, x: Vol) -> Vol:
+        c2, cs = self.conv2.conv, self.conv_shortcut.conv
+        w2, b2 = c2.packed(h.dtype, pad8=True)
+        ws, bs = cs.packed(h.dtype, pad8=True)
+        key = (c2.bias._version, cs.bias._version, b2.data_ptr(), bs.data_ptr())
+        if getattr(self, "_bias_sum", None) is None or self._bias_sum[0] != key:
+            self._bias_sum = (key, (b2 + bs).contiguous())
+        return N.conv3d_tc_shortcut(h, w2, self._bias_sum[1], x, ws, c2.out_channels, gn_groups=self.conv2.emit_gn_groups)
 
     def forward(self, input_tensor, temb=None, scale: float = 1.0):
         return self.forward_vol(Vol.from_ncthw(input_tensor)).to_ncthw()

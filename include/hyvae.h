@@ -75,6 +75,14 @@ int hyvae_conv3d_causal_direct(const hyvae_vol* x, const void* w, const float* b
 int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
                            const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
                            int32_t round_like_ref, int32_t variant, double* gn_partials, int32_t gn_groups, void* stream);
+/* conv2 of a ResnetBlockCausal3D whose skip path is a 1x1x1 conv_shortcut (unet_causal_3d_blocks.py:338-348,407-415):
+ *   y = conv3x3x3(x; w) + conv1x1x1(sc_x; sc_w) + bias,   bias = conv2.bias + conv_shortcut.bias (summed by the caller).
+ * x carries the halo (2,1,1); sc_x is the block input (any halo) with y's extent; sc_w: [1][Cout][Csc] in x's dtype.
+ * Stride 1, 64 < Cout <= 128, 16-bit output (the halo kernel); other shapes return HYVAE_EUNSUPPORTED and the caller
+ * runs the shortcut as its own k=1 conv feeding `residual`. */
+int hyvae_conv3d_causal_tc_shortcut(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* sc_x,
+                                    const void* sc_w, const hyvae_vol* y, double* gn_partials, int32_t gn_groups,
+                                    void* stream);
 /* One output-parity phase of UpsampleCausal3D.forward (nearest x2 + 3x3x3 CausalConv3d, unet_causal_3d_blocks.py:
  * 152-175) computed directly from the LOW-resolution volume: the 27 high-res taps collapse onto nkt x 2 x 2 low-res taps
  * (nkt = 2 if up_t == 2, else 3) whose weights are sums of the original ones.

@@ -330,6 +330,40 @@ def test_resnet_and_midblock_fp32_vs_reference():
     assert O.rel_err(a["mid_y"], y.cpu()) < FP32_TOL
 
 
+@pytest.mark.parametrize("cin,cout,T,H,W", [(256, 128, 3, 24, 40), (64, 128, 2, 9, 21)])
+def test_resnet_block_fp16_fused_shortcut_vs_reference(cin, cout, T, H, W):
+    """ResnetBlockCausal3D with Cin != Cout (unet_causal_3d_blocks.py:338-348,407-415): the 1x1x1 conv_shortcut runs
+    as extra K chunks inside conv2 (hyvae_conv3d_causal_tc_shortcut).  Checked against the fp32 oracle evaluated on the
+    fp16-rounded parameters, and against the unfused schedule."""
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    from hunyuanvideo_efficiency_b200.vae.blocks import ResnetBlockCausal3D
+    torch.manual_seed(3)
+    r = ResnetBlockCausal3D(in_channels=cin, out_channels=cout, temb_channels=None, groups=32, eps=1e-6)
+    with torch.no_grad():
+        for n_, p_ in r.named_parameters():   # non-trivial norm affine parameters
+            if "norm" in n_:
+                p_.copy_(torch.randn_like(p_) * 0.3 + (1.0 if n_.endswith("weight") else 0.0))
+    r = r.half().to(_dev())
+    x = torch.randn(2, cin, T, H, W).half()
+    sd = {"b." + k: v.float().cpu() for k, v in r.state_dict().items()}
+    ref = O.resnet_block(sd, "b.", x.float(), 32)
+    n0 = N.launch_count()
+    y = r(x.to(_dev()))
+    fused_launches = N.launch_count() - n0
+    os.environ["HYVAE_FUSE_SHORTCUT"] = "0"
+    try:
+        n0 = N.launch_count()
+        y2 = r(x.to(_dev()))
+        unfused_launches = N.launch_count() - n0
+    finally:
+        os.environ.pop("HYVAE_FUSE_SHORTCUT")
+    assert fused_launches == unfused_launches - 1          # the k=1 shortcut launch is gone
+    assert O.rel_err(ref, y.float().cpu()) < 3e-3
+    assert O.rel_err(y2.float().cpu(), y.float().cpu()) < 2e-3
+
+
 # ----------------------------------------------------------------------------------------- whole model
 def _build(cfg, dtype, t_ops=None):
     from hunyuanvideo_efficiency_b200.vae import AutoencoderKLCausal3D, _apply_t_ops_config_to_vae
