@@ -23,6 +23,10 @@ class HyvaeError(RuntimeError):
     pass
 
 
+class HyvaeUnsupported(HyvaeError):
+    """HYVAE_EUNSUPPORTED (-3): the entry point does not take this shape; the caller picks another schedule."""
+
+
 class _CVol(C.Structure):
     _fields_ = [("data", C.c_void_p), ("dtype", C.c_int32), ("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32),
                 ("W", C.c_int32), ("C", C.c_int32), ("pt", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32)]
@@ -84,7 +88,8 @@ def lib():
 
 def _check(status: int, what: str):
     if status != 0:
-        raise HyvaeError(f"{what} failed ({status}): {lib().hyvae_last_error().decode()}")
+        cls = HyvaeUnsupported if status == -3 else HyvaeError
+        raise cls(f"{what} failed ({status}): {lib().hyvae_last_error().decode()}")
 
 
 def _stream() -> int:

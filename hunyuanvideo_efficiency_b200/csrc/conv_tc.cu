@@ -48,6 +48,7 @@ struct TcArgs {
   // the sub-pixel decomposition of nearest-upsample + conv (hyvae_conv3d_upphase_tc) has 2 (or 3) x 2 x 2 taps and a
   // box origin shifted by the phase.  Weight tap index = (kt * nsub + kh) * nkw + kw.
   int nkt, nkw, nsub, ot, oh, ow, a_tx;
+  int sc_chunks, sc_cin;  // kh-trick pair kernel: fused 1x1x1 shortcut conv (64-channel chunks / channels of its input)
 };
 
 constexpr int TC_THREADS = 192;
@@ -324,7 +325,8 @@ template <int BN, bool KHT> struct Tc2Cfg {
 template <typename T, typename OT, int BN, bool KHT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const TcArgs a) {
+                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+                const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const TcArgs a) {
   using Cfg = Tc2Cfg<BN, KHT>;
   constexpr int SB = Cfg::SB, NA = Cfg::NA, NSUB = Cfg::NSUB;
   constexpr bool TMA_EPI = KHT && sizeof(OT) == 2;  // staged TMA-store epilogue (16-bit output, 16 x 8 tiles)
@@ -418,6 +420,28 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
         }
+        if (KHT) {
+          // fused 1x1x1 conv_shortcut: one halo stage of the block input (box origin one row above the tile) and one
+          // weight stage per 64-channel chunk
+          for (int kc = 0; kc < a.sc_chunks; ++kc) {
+            mbar_wait(aempty_bar + 8 * sa, pa ^ 1);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(afull_bar + 8 * sa, 2 * a.a_tx);
+              tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmX, afull_bar + 8 * sa, kc * 64, m.w0, m.h0 - 1, m.t, m.b);
+              if (!leader) mbar_arrive_leader(afull_bar + 8 * sa);
+            }
+            __syncwarp();
+            if (++sa == NA) { sa = 0; pa ^= 1; }
+            mbar_wait(bempty_bar + 8 * sb, pb ^ 1);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(bfull_bar + 8 * sb, 2 * Cfg::B_STAGE_BYTES);
+              tma_load_3d_2sm(sB + sb * Cfg::B_STAGE_BYTES, &tmW, bfull_bar + 8 * sb, kc * 64, n0, 0);
+              if (!leader) mbar_arrive_leader(bfull_bar + 8 * sb);
+            }
+            __syncwarp();
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -454,6 +478,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (KHT) {
             if (elect_one()) umma_commit_2sm(aempty_bar + 8 * sa);
             __syncwarp();
+            if (++sa == NA) { sa = 0; pa ^= 1; }
+          }
+        }
+        if (KHT) {
+          for (int kc = 0; kc < a.sc_chunks; ++kc) {  // fused shortcut: the tile rows start one row into the stage
+            mbar_wait(afull_bar + 8 * sa, pa);
+            mbar_wait(bfull_bar + 8 * sb, pb);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t adesc = make_kmajor_sw128_desc(sA + sa * Cfg::A_BYTES + 1024);
+              const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * Cfg::B_STAGE_BYTES);
+              const int rem = a.sc_cin - kc * 64;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k * 16 < rem) umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+              umma_commit_2sm(bempty_bar + 8 * sb);
+              umma_commit_2sm(aempty_bar + 8 * sa);
+            }
+            __syncwarp();
+            if (++sb == SB) { sb = 0; pb ^= 1; }
             if (++sa == NA) { sa = 0; pa ^= 1; }
           }
         }
@@ -650,7 +694,8 @@ static int encode_out_map(CUtensorMap* tm, CUtensorMapDataType dt, const void* b
 }
 
 template <typename T, typename OT, int BN, bool KHT>
-static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
+static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream,
+                      const CUtensorMap* tmX = nullptr, const CUtensorMap* tmW = nullptr) {
   using Cfg = Tc2Cfg<BN, KHT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -668,7 +713,7 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
     if (a.res)
       if (int e = encode_out_map(&tmR, dt, a.res, a.roff, a.Cout, a.Wo, a.Ho, a.To, a.B, a.rsW, a.rsH, a.rsT, a.rsB)) return e;
   }
-  conv_tc2_kernel<T, OT, BN, KHT><<<(unsigned)(2 * pairs), TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, a);
+  conv_tc2_kernel<T, OT, BN, KHT><<<(unsigned)(2 * pairs), TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, tmX ? *tmX : tmA, tmW ? *tmW : tmB, a);
   return check_launch("conv3d_causal_tc (2-CTA)");
 }
 
@@ -749,12 +794,15 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
   a.k = k; a.st = st; a.sh = sh; a.sw = sw; a.round_like_ref = round_like_ref;
   { const char* pe = getenv("HYVAE_TC_PROBE"); a.probe = pe ? atoi(pe) : 0; }  // measurement only: results are garbage when set
   a.nkt = a.nkw = a.nsub = 3; a.ot = a.oh = a.ow = 0; a.a_tx = 18 * 1024;
+  a.sc_chunks = a.sc_cin = 0;
 
   // ---- halo kernel (conv_halo.cu): every stride-1 3x3x3 conv with Cout <= 128 and a 16-bit output (variant 5 forces it)
   const bool halo_ok = k == 3 && st == 1 && sh == 1 && sw == 1 && y->C <= 128 && y->dtype == x->dtype &&
                        (gn_partials == nullptr || (gn_groups > 0 && y->C % gn_groups == 0 && y->C / gn_groups >= 2));
   if (sc_x != nullptr) {
-    HYVAE_CHECK_ARG(halo_ok && y->C > 64, "fused shortcut needs a stride-1 3x3x3 conv with 64 < Cout <= 128 and a 16-bit output");
+    HYVAE_CHECK_ARG(k == 3 && st == 1 && sh == 1 && sw == 1 && y->C > 64 && y->dtype == x->dtype && variant == 0 &&
+                    (gn_partials == nullptr || (gn_groups > 0 && y->C % gn_groups == 0 && y->C / gn_groups >= 2)),
+                    "fused shortcut needs a stride-1 3x3x3 conv with Cout > 64 and a 16-bit output");
     HYVAE_CHECK_ARG(sc_x->dtype == x->dtype && sc_x->B == y->B && sc_x->T == y->T && sc_x->H == y->H && sc_x->W == y->W && sc_x->C % 8 == 0,
                     "shortcut input must have y's extent and x's dtype");
     HYVAE_CHECK_ARG(((uintptr_t)sc_x->data & 15) == 0 && ((uintptr_t)sc_w & 15) == 0, "pointers must be 16-byte aligned");
@@ -840,7 +888,6 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
     return launch_halo(x->dtype, bn, mt, pair, tmA, tmB, tmY, tmR, tmX, tmW, h, (cudaStream_t)stream);
   }
 
-  if (sc_x != nullptr) return fail(HYVAE_EUNSUPPORTED, "fused shortcut is only implemented in the halo kernel");
   pick_tile(y->H, y->W, sh, sw, &a.TH, &a.TW);
   // variant: 0 = auto, 1 = 1-CTA kernel with MT=1, 2 = 1-CTA kernel, 3 = CTA-pair kernel without the kh trick
   const int BN_sel = y->C > 128 ? 256 : (y->C > 64 ? 128 : (y->C > 32 ? 64 : 32));
@@ -877,7 +924,26 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
   a.total_tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;
 
   const CUtensorMapDataType dt = x->dtype == HYVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmX, tmW;
+  if (sc_x != nullptr) {
+    if (!(two_cta && kht)) return fail(HYVAE_EUNSUPPORTED, "fused shortcut needs the halo or the kh-trick pair kernel for this shape");
+    a.sc_cin = sc_x->C; a.sc_chunks = (sc_x->C + 63) / 64;
+    Vol vs = make_vol(sc_x);
+    cuuint64_t dims[5] = {(cuuint64_t)sc_x->C, (cuuint64_t)sc_x->W, (cuuint64_t)sc_x->H, (cuuint64_t)sc_x->T, (cuuint64_t)sc_x->B};
+    cuuint64_t strides[4] = {(cuuint64_t)vs.sW * 2, (cuuint64_t)vs.sH * 2, (cuuint64_t)vs.sT * 2, (cuuint64_t)vs.sB * 2};
+    cuuint32_t box[5] = {64, 8, 18, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmX, dt, 5, (char*)sc_x->data + vs.at(0, 0, 0, 0) * 2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(shortcut x) failed with %d", (int)r);
+    cuuint64_t wd[3] = {(cuuint64_t)sc_x->C, (cuuint64_t)y->C, 1};
+    cuuint64_t ws[2] = {(cuuint64_t)sc_x->C * 2, (cuuint64_t)sc_x->C * y->C * 2};
+    cuuint32_t wb[3] = {64, (cuuint32_t)(BN / 2), 1};
+    cuuint32_t we[3] = {1, 1, 1};
+    r = encode(&tmW, dt, 3, const_cast<void*>(sc_w), wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(shortcut w) failed with %d", (int)r);
+  }
   {
     cuuint64_t dims[5] = {(cuuint64_t)x->C, (cuuint64_t)vx.Wp(), (cuuint64_t)vx.Hp(), (cuuint64_t)vx.Tp(), (cuuint64_t)x->B};
     cuuint64_t strides[4] = {(cuuint64_t)vx.sW * 2, (cuuint64_t)vx.sH * 2, (cuuint64_t)vx.sT * 2, (cuuint64_t)vx.sB * 2};
@@ -898,9 +964,11 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
   }
   cudaStream_t s = (cudaStream_t)stream;
   char tag[56];
-  snprintf(tag, sizeof(tag), "k%d %d->%d %dx%dx%dx%d s%d%d%d BN%d %s%d", k, x->C, y->C, y->B, y->T, y->H, y->W, st, sh, sw, BN,
-           two_cta ? (kht ? "2ctaK" : "2cta") : "MT", MT);
-  ProfScope prof(PC_CONV_TC, 2.0 * (double)y->B * y->T * y->H * y->W * y->C * x->C * k * k * k, stream, tag);
+  snprintf(tag, sizeof(tag), "k%d %d->%d %dx%dx%dx%d s%d%d%d BN%d %s%d%s", k, x->C, y->C, y->B, y->T, y->H, y->W, st, sh, sw, BN,
+           two_cta ? (kht ? "2ctaK" : "2cta") : "MT", MT, sc_x ? "+sc" : "");
+  ProfScope prof(PC_CONV_TC, 2.0 * (double)y->B * y->T * y->H * y->W * y->C * ((double)x->C * k * k * k + (sc_x ? sc_x->C : 0)), stream, tag);
+  const CUtensorMap* pX = sc_x ? &tmX : nullptr;
+  const CUtensorMap* pW = sc_x ? &tmW : nullptr;
 #define HYVAE_TC_LAUNCH(T, OT)                                                                              \
   switch (BN) {                                                                                             \
     case 256: return launch_tc<T, OT, 256, 1>(tmA, tmB, a, s);                                              \
@@ -911,9 +979,9 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
   const bool f32out = (y->dtype == HYVAE_F32);
 #define HYVAE_TC2_LAUNCH(T, OT)                                                                                        \
   switch (BN) {                                                                                                        \
-    case 256: return kht ? launch_tc2<T, OT, 256, true>(tmA, tmB, a, s) : launch_tc2<T, OT, 256, false>(tmA, tmB, a, s); \
-    case 128: return kht ? launch_tc2<T, OT, 128, true>(tmA, tmB, a, s) : launch_tc2<T, OT, 128, false>(tmA, tmB, a, s); \
-    default: return kht ? launch_tc2<T, OT, 64, true>(tmA, tmB, a, s) : launch_tc2<T, OT, 64, false>(tmA, tmB, a, s);    \
+    case 256: return kht ? launch_tc2<T, OT, 256, true>(tmA, tmB, a, s, pX, pW) : launch_tc2<T, OT, 256, false>(tmA, tmB, a, s); \
+    case 128: return kht ? launch_tc2<T, OT, 128, true>(tmA, tmB, a, s, pX, pW) : launch_tc2<T, OT, 128, false>(tmA, tmB, a, s); \
+    default: return kht ? launch_tc2<T, OT, 64, true>(tmA, tmB, a, s, pX, pW) : launch_tc2<T, OT, 64, false>(tmA, tmB, a, s);    \
   }
   if (two_cta) {
     if (x->dtype == HYVAE_BF16) {
@@ -970,6 +1038,7 @@ extern "C" int hyvae_conv3d_upphase_tc(const hyvae_vol* x, const void* w, const 
   a.k = 3; a.st = a.sh = a.sw = 1; a.round_like_ref = 0;
   { const char* pe = getenv("HYVAE_TC_PROBE"); a.probe = pe ? atoi(pe) : 0; }
   a.nkt = nkt; a.nkw = 2; a.nsub = 2; a.ot = (up_t == 2 && pt == 1) ? 1 : 0; a.oh = ph; a.ow = pw; a.a_tx = 17 * 1024;
+  a.sc_chunks = a.sc_cin = 0;
   a.TH = 16; a.TW = 8;
   a.tiles_h = (x->H + 15) / 16; a.tiles_w = (x->W + 7) / 8;
   const int BN = y->C > 128 ? 256 : (y->C > 64 ? 128 : 64);

@@ -297,9 +297,10 @@ class ResnetBlockCausal3D(nn.Module):
 
     def _can_fuse_shortcut(self, h: Vol, x: Vol) -> bool:
         """The 1x1x1 conv_shortcut runs as extra K chunks of conv2's accumulator (hyvae_conv3d_causal_tc_shortcut) when
-        conv2 is served by the halo kernel: 16-bit tensor-core path, 64 < Cout <= 128."""
+        conv2 is served by the halo kernel or the kh-trick pair kernel: 16-bit tensor-core path, Cout > 64."""
         c2, cs = self.conv2.conv, self.conv_shortcut.conv
-        return (os.environ.get("HYVAE_FUSE_SHORTCUT", "1") == "1" and h.dtype in _16BIT and 64 < c2.out_channels <= 128
+        return (os.environ.get("HYVAE_FUSE_SHORTCUT", "1") == "1" and h.dtype in _16BIT and 64 < c2.out_channels
+                and (c2.out_channels <= 128 or (h.H + 15) // 16 * ((h.W + 7) // 8) * h.T * h.B >= 2)
                 and c2.out_channels % 8 == 0 and cs.in_channels % 8 == 0 and x.C == cs.in_channels and h.pad == self.conv2.halo
                 and h.C == c2.in_channels and c2.bias is not None and cs.bias is not None
                 and tc_eligible(h.dtype, c2.in_channels, c2.out_channels, (1, 1, 1), 3))
@@ -311,7 +312,10 @@ class ResnetBlockCausal3D(nn.Module):
         key = (c2.bias._version, cs.bias._version, b2.data_ptr(), bs.data_ptr())
         if getattr(self, "_bias_sum", None) is None or self._bias_sum[0] != key:
             self._bias_sum = (key, (b2 + bs).contiguous())
-        return N.conv3d_tc_shortcut(h, w2, self._bias_sum[1], x, ws, c2.out_channels, gn_groups=self.conv2.emit_gn_groups)
+        try:
+            return N.conv3d_tc_shortcut(h, w2, self._bias_sum[1], x, ws, c2.out_channels, gn_groups=self.conv2.emit_gn_groups)
+        except N.HyvaeUnsupported:   # tile shape the fused kernels do not take: run the shortcut as its own k=1 conv
+            return self.conv2.forward_vol(h, residual=self.conv_shortcut.forward_vol(x))
 
     def forward(self, input_tensor, temb=None, scale: float = 1.0):
         return self.forward_vol(Vol.from_ncthw(input_tensor)).to_ncthw()

@@ -78,8 +78,8 @@ int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const float* bias,
 /* conv2 of a ResnetBlockCausal3D whose skip path is a 1x1x1 conv_shortcut (unet_causal_3d_blocks.py:338-348,407-415):
  *   y = conv3x3x3(x; w) + conv1x1x1(sc_x; sc_w) + bias,   bias = conv2.bias + conv_shortcut.bias (summed by the caller).
  * x carries the halo (2,1,1); sc_x is the block input (any halo) with y's extent; sc_w: [1][Cout][Csc] in x's dtype.
- * Stride 1, 64 < Cout <= 128, 16-bit output (the halo kernel); other shapes return HYVAE_EUNSUPPORTED and the caller
- * runs the shortcut as its own k=1 conv feeding `residual`. */
+ * Stride 1, Cout > 64, 16-bit output (halo kernel for Cout <= 128, kh-trick pair kernel above); shapes those kernels do
+ * not take return HYVAE_EUNSUPPORTED and the caller runs the shortcut as its own k=1 conv feeding `residual`. */
 int hyvae_conv3d_causal_tc_shortcut(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* sc_x,
                                     const void* sc_w, const hyvae_vol* y, double* gn_partials, int32_t gn_groups,
                                     void* stream);

@@ -330,7 +330,7 @@ def test_resnet_and_midblock_fp32_vs_reference():
     assert O.rel_err(a["mid_y"], y.cpu()) < FP32_TOL
 
 
-@pytest.mark.parametrize("cin,cout,T,H,W", [(256, 128, 3, 24, 40), (64, 128, 2, 9, 21)])
+@pytest.mark.parametrize("cin,cout,T,H,W", [(256, 128, 3, 24, 40), (64, 128, 2, 9, 21), (128, 256, 3, 20, 24), (512, 256, 2, 18, 32)])
 def test_resnet_block_fp16_fused_shortcut_vs_reference(cin, cout, T, H, W):
     """ResnetBlockCausal3D with Cin != Cout (unet_causal_3d_blocks.py:338-348,407-415): the 1x1x1 conv_shortcut runs
     as extra K chunks inside conv2 (hyvae_conv3d_causal_tc_shortcut).  Checked against the fp32 oracle evaluated on the
@@ -359,7 +359,9 @@ def test_resnet_block_fp16_fused_shortcut_vs_reference(cin, cout, T, H, W):
         unfused_launches = N.launch_count() - n0
     finally:
         os.environ.pop("HYVAE_FUSE_SHORTCUT")
-    assert fused_launches == unfused_launches - 1          # the k=1 shortcut launch is gone
+    assert fused_launches <= unfused_launches              # the k=1 shortcut launch is gone when the tile shape allows
+    if cout <= 128:
+        assert fused_launches == unfused_launches - 1
     assert O.rel_err(ref, y.float().cpu()) < 3e-3
     assert O.rel_err(y2.float().cpu(), y.float().cpu()) < 2e-3
 
