@@ -50,6 +50,7 @@ _SIGNATURES = {
     "hyvae_softmax_frame_causal": [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp],
     "hyvae_avgpool_t": [_VP, _VP, _i32, _i32, _vp],
     "hyvae_interp_t_nearest": [_VP, _VP, _f32, _vp],
+    "hyvae_image_postprocess": [_vp, _i32, _vp, _i64, _vp],
     "hyvae_blend_crop_scatter": [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32,
                                  _i32, _i32, _i32, _i32, C.POINTER(_i64), _vp],
 }
@@ -335,3 +336,13 @@ def blend_crop_scatter(cur: torch.Tensor, above, left, N: int, Yc: int, Xc: int,
     ns = (_i64 * 4)(*n_strides) if n_strides is not None else None
     _check(lib().hyvae_blend_crop_scatter(cur.data_ptr(), _ptr(above), _ptr(left), _DT[cur.dtype], N, Yc, Xc, Ya, Xl, ev, eh,
                                           _ptr(out), Yo, Xo, y0, x0, crop_y, crop_x, ns, _stream()), "blend_crop_scatter")
+
+
+def image_postprocess(image: torch.Tensor) -> torch.Tensor:
+    """float((image / 2 + 0.5).clamp(0, 1)) in one pass (pipeline_hunyuan_video.py:1090-1092); returns fp32 on the device."""
+    assert image.is_cuda and image.is_contiguous()
+    if image.numel() % 8 or image.dtype == torch.float32:
+        return (image / 2 + 0.5).clamp(0, 1).float()
+    out = torch.empty(image.shape, dtype=torch.float32, device=image.device)
+    _check(lib().hyvae_image_postprocess(image.data_ptr(), _DT[image.dtype], out.data_ptr(), image.numel(), _stream()), "image_postprocess")
+    return out

@@ -410,6 +410,21 @@ __global__ void blend_crop_scatter_kernel(T* __restrict__ cur, const T* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// pipeline tail: image = (image / 2 + 0.5).clamp(0, 1) in the image dtype, then .float()
+// (pipeline_hunyuan_video.py:1090-1092) as ONE pass: 16-bit in, fp32 out.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) image_postprocess_kernel(const T* __restrict__ src, float* __restrict__ dst, int64_t n8) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    Vec8<T> q; q.load(src + i * 8);
+    float f[8]; q.get(f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fminf(fmaxf(rnd<T>(fmaf(f[j], 0.5f, 0.5f)), 0.f), 1.f);  // x/2 is exact; the sum rounds like the tensor op
+    Vec8<float> o; o.set(f); o.store(dst + i * 8);
+  }
+}
+
 }  // namespace hyvae
 
 using namespace hyvae;
@@ -612,6 +627,14 @@ int hyvae_interp_t_nearest(const hyvae_vol* x, const hyvae_vol* y, float inv_sca
   ProfScope prof(PC_TEMPORAL, (double)total * dtype_size(x->dtype) * 2, stream);
   HYVAE_DISPATCH_DTYPE(x->dtype, T, (temporal_kernel<T, 1><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, 0, 0, inv_scale)));
   return check_launch("interp_t_nearest");
+}
+
+int hyvae_image_postprocess(const void* src, int32_t src_dtype, float* dst, int64_t n, void* stream) {
+  HYVAE_CHECK_ARG(src && dst && n > 0 && n % 8 == 0, "image_postprocess: need n %% 8 == 0 (n=%lld)", (long long)n);
+  HYVAE_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "pointers must be 16-byte aligned");
+  ProfScope prof(PC_LAYOUT, (double)n * (dtype_size(src_dtype) + 4), stream);
+  HYVAE_DISPATCH_DTYPE(src_dtype, T, (image_postprocess_kernel<T><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const T*)src, dst, n / 8)));
+  return check_launch("image_postprocess");
 }
 
 int hyvae_blend_crop_scatter(void* cur, const void* above, const void* left, int32_t dtype, int64_t N,

@@ -152,6 +152,12 @@ int hyvae_blend_crop_scatter(void* cur, const void* above, const void* left, int
                              void* out, int32_t Yo, int32_t Xo, int32_t y0, int32_t x0, int32_t crop_y,
                              int32_t crop_x, const int64_t* n_strides, void* stream);
 
+/* ---- pipeline tail ------------------------------------------------------------------------------
+ * Replaces `image = (image / 2 + 0.5).clamp(0, 1); image = image.cpu().float()` of
+ * pipeline_hunyuan_video.py:1090-1092 (device part): dst[i] = float(clamp(T(src[i] / 2 + 0.5), 0, 1)), one pass.
+ * n must be a multiple of 8; src in `src_dtype`, dst fp32. */
+int hyvae_image_postprocess(const void* src, int32_t src_dtype, float* dst, int64_t n, void* stream);
+
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------------
  * profile_begin/end bracket a region; while on, every C-ABI call is timed with two CUDA events on its
  * stream.  profile_end synchronises and returns, per kernel class (0 conv_tc, 1 conv_direct, 2 gn_stats,

@@ -504,3 +504,35 @@ def test_full_size_tile_properties_bf16():
     d2 = m.decode(z).sample
     assert d1.shape == (1, 3, 17, 256, 256) and torch.equal(d1, d2)
     assert torch.isfinite(d1.float()).all()
+
+
+def test_pipeline_tail_matches_reference_ops():
+    """pipeline_hunyuan_video.py:1060-1092: latents / scaling_factor -> tiled decode -> (x / 2 + 0.5).clamp(0, 1) -> float."""
+    from hunyuanvideo_efficiency_b200.pipeline_tail import decode_latents
+    cfg = dict(W.SMALL_CONFIG, block_out_channels=[64, 128, 256, 256], scaling_factor=0.476986)
+    m = _build(cfg, torch.float16)
+    z = W.make_latent((1, 16, 5, 12, 10)).to(_dev(), torch.float16)
+    out = decode_latents(m, z)
+    ref = m.decode(z / cfg["scaling_factor"], return_dict=False)[0]
+    ref = (ref / 2 + 0.5).clamp(0, 1).cpu().float()
+    assert out.dtype == torch.float32 and out.device.type == "cpu" and torch.equal(out, ref)
+    img = decode_latents(m, z[:, :, 0], to_cpu=False)                 # 4-D latents: one frame, temporal dim squeezed
+    assert img.shape == (1, 3, 96, 80) and img.is_cuda
+
+
+def test_clip_driver_on_gpu(tmp_path):
+    """hunyuanvideo_efficiency_b200/infer.py with the real model: pinned H2D on a copy stream, round trip, async D2H + save."""
+    from hunyuanvideo_efficiency_b200 import infer as I
+    cfg = dict(W.SMALL_CONFIG, block_out_channels=[64, 128, 256, 256])
+    m = _build(cfg, torch.float16)
+    d, out = os.path.join(str(tmp_path), "in"), os.path.join(str(tmp_path), "out")
+    os.makedirs(d)
+    clips = [W.make_video((3, 9, 32, 40), seed) for seed in (1, 2, 3)]
+    for i, c in enumerate(clips):
+        torch.save(c, os.path.join(d, f"c{i}.pt"))
+    done = I.run_clips(I.roundtrip(m), d, out, device=_dev(), in_dtype=torch.float16)
+    assert len(done) == 3
+    for i, c in enumerate(clips):
+        y = torch.load(os.path.join(out, f"c{i}.pt"))
+        ref = m(c[None].to(_dev(), torch.float16), return_dict=False, return_posterior=True)[0].cpu().float()
+        assert y.dtype == torch.float32 and torch.equal(y, ref)
