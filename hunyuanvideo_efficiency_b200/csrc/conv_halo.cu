@@ -32,25 +32,34 @@ namespace hyvae {
 
 constexpr int HALO_THREADS = 192;
 
-template <int BN, int MT, bool PAIR> struct HaloCfg {
+// THIN (Cin <= 16, e.g. conv_in 3 -> 128 with the input stored as 16 channels): rows are 32 bytes (one K = 16 MMA slice)
+// with SWIZZLE_32B instead of 128-byte rows that would be 7/8 zero fill: a halo stage is 10 KB, so the ring is deep enough
+// to hide the TMA latency behind the short (9 taps x 64 clk) steps, and ALL 27 weight taps stay resident in shared memory.
+template <int BN, int MT, bool PAIR, bool THIN = false> struct HaloCfg {
+  static constexpr int ROWB = THIN ? 32 : 128;                       // bytes per voxel row of an operand stage
   static constexpr int TWH = 8 * MT + 2, THH = 18;                  // halo patch: columns x rows
-  static constexpr int PITCH = TWH;                                  // smem rows (of 128 B) per halo row: dense
-  static constexpr int A_TX = TWH * THH * 128;                      // bytes TMA delivers per A stage
+  static constexpr int PITCH = TWH;                                  // smem rows per halo row: dense
+  static constexpr int A_TX = TWH * THH * ROWB;                     // bytes TMA delivers per A stage
   static constexpr int A_BYTES = (A_TX + 1023) / 1024 * 1024;
-  static constexpr int TB = BN >= 128 ? 1 : 3;                       // (kh, kw) taps per B stage (9 % TB == 0)
+  static constexpr int TB = THIN ? 27 : (BN >= 128 ? 1 : 3);         // taps per B stage (THIN: all of them, loaded once)
   static constexpr int BROWS = PAIR ? BN / 2 : BN;                   // weight rows this CTA stages
-  static constexpr int B_TAP_BYTES = BROWS * 128;
+  static constexpr int B_TAP_BYTES = BROWS * ROWB;
   static constexpr int B_BYTES = TB * B_TAP_BYTES;
-  static constexpr int NA = 2;
   static constexpr int NH = (BN + 63) / 64;                          // 64-channel halves of the output tile
-  static constexpr int OUT_BYTES = NH * 16384;                       // one m-tile of output staging, reused by the MT m-tiles
+  static constexpr int OUT_BYTES = MT * NH * 16384;                  // one staging tile per m-tile slot: a tile's TMA store is only
+                                                                     // waited for when its slot comes round again, MT tiles later
   static constexpr int BUDGET = 227 * 1024 - 2048;                   // minus alignment slack and barrier block
+  static constexpr int NA_THIN_RAW = (BUDGET - OUT_BYTES - (B_BYTES + 1023) / 1024 * 1024) / A_BYTES;
+  static constexpr int NA = THIN ? (NA_THIN_RAW > 8 ? 8 : NA_THIN_RAW) : 2;
   static constexpr int NB_RAW = (BUDGET - NA * A_BYTES - OUT_BYTES) / B_BYTES;
-  static constexpr int NB = NB_RAW > 12 ? 12 : NB_RAW;
+  static constexpr int NB = THIN ? 1 : (NB_RAW > 12 ? 12 : NB_RAW);
+  static constexpr int B_RING_BYTES = (NB * B_BYTES + 1023) / 1024 * 1024;
   static constexpr int ACC_COLS = MT * BN;
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
-  static constexpr int SMEM_BYTES = NA * A_BYTES + NB * B_BYTES + OUT_BYTES + 2048;
-  static_assert(NB >= 3, "B ring too shallow");
+  static constexpr int SMEM_BYTES = NA * A_BYTES + B_RING_BYTES + OUT_BYTES + 2048;
+  static_assert(THIN || NB >= 3, "B ring too shallow");
+  static_assert(!THIN || NA >= 4, "A ring too shallow");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
 };
 
@@ -60,6 +69,10 @@ template <int BN, int MT, bool PAIR> struct HaloCfg {
 // TMA-written SWIZZLE_128B region may be row 0 of an operand, and 8-row groups may start at any row.
 __device__ __forceinline__ uint64_t make_halo_desc(uint32_t addr, uint32_t sbo_bytes) {
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// same for 32-byte rows (SWIZZLE_32B, layout type 6): one row = one K = 16 slice, 8-row groups of 256 B when dense
+__device__ __forceinline__ uint64_t make_sw32_desc(uint32_t addr, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
 }
 
 struct HGroup { int b, t, h0, w0; };
@@ -73,18 +86,18 @@ __device__ __forceinline__ HGroup decode_group(const HaloArgs& a, int64_t g, int
   return r;
 }
 
-template <typename T, int BN, int MT, bool PAIR>
+template <typename T, int BN, int MT, bool PAIR, bool THIN>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const HaloArgs a) {
-  using Cfg = HaloCfg<BN, MT, PAIR>;
+  using Cfg = HaloCfg<BN, MT, PAIR, THIN>;
   constexpr int NA = Cfg::NA, NB = Cfg::NB, NH = Cfg::NH, PITCH = Cfg::PITCH, TB = Cfg::TB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + NA * Cfg::A_BYTES;
-  const uint32_t sOut = sB + NB * Cfg::B_BYTES;
+  const uint32_t sOut = sB + Cfg::B_RING_BYTES;
   const uint32_t bars = sOut + Cfg::OUT_BYTES;
   const uint32_t afull = bars, aempty = afull + 8 * NA;
   const uint32_t bfull = aempty + 8 * NA, bempty = bfull + 8 * NB;
@@ -158,8 +171,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (++sa == NA) { sa = 0; pa ^= 1; }
     };
+    if constexpr (THIN) {
+      // all 27 weight taps once, then a deep ring of 10 KB halo stages (one per frame tap kt)
+      if (elect_one()) {
+        if constexpr (PAIR) {
+          if (leader) mbar_expect_tx(bfull, 2 * Cfg::B_BYTES);
+          tma_load_3d_2sm(sB, &tmB, bfull, 0, (int)rank * Cfg::BROWS, 0);
+          if (!leader) mbar_arrive_leader(bfull);
+        } else {
+          mbar_expect_tx(bfull, Cfg::B_BYTES);
+          tma_load_3d(sB, &tmB, bfull, 0, 0, 0);
+        }
+      }
+      __syncwarp();
+      for (int64_t u = unit0; u < units; u += ustride)
+        for (int step = 0; step < 3; ++step) issue_A(u, step);
+    }
     bool first = true;
-    for (int64_t u = unit0; u < units; u += ustride) {
+    for (int64_t u = unit0; u < units && !THIN; u += ustride) {
       for (int step = 0; step < steps_per_group; ++step) {
         if (first) { issue_A(u, step); first = false; }
         const bool sc = step >= steps_main;
@@ -199,7 +228,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       auto commit = [&](uint32_t bar) { if constexpr (PAIR) umma_commit_2sm(bar); else umma_commit(bar); };
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       int iter = 0;
-      for (int64_t u = unit0; u < units; u += ustride, ++iter) {
+      if constexpr (THIN) mbar_wait(bfull, 0);  // the resident weights
+      for (int64_t u = unit0; u < units && THIN; u += ustride, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait(tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
+        for (int kt = 0; kt < 3; ++kt) {
+          mbar_wait(afull + 8 * sa, pa);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_stage = sA + sa * Cfg::A_BYTES;
+#pragma unroll
+            for (int tap9 = 0; tap9 < 9; ++tap9) {
+              const int kh = tap9 / 3, kw = tap9 - 3 * kh;
+              const uint64_t bdesc = make_sw32_desc(sB + (uint32_t)((kt * 9 + tap9) * Cfg::B_TAP_BYTES), 256);
+#pragma unroll
+              for (int i = 0; i < MT; ++i)
+                mma(d_tmem + i * BN, make_sw32_desc(a_stage + (uint32_t)((kh * PITCH + kw + 8 * i) * 32), PITCH * 32), bdesc, (kt | tap9) != 0);
+            }
+            commit(aempty + 8 * sa);
+          }
+          __syncwarp();
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+        }
+        if (elect_one()) commit(tfull + 8 * acc);
+        __syncwarp();
+      }
+      for (int64_t u = unit0; u < units && !THIN; u += ustride, ++iter) {
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
         mbar_wait(tempty + 8 * acc, acc_phase ^ 1);
@@ -255,7 +312,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int gb = -1;       // batch item the accumulators belong to
     uint32_t rph = 0;  // phase of this warp's residual barrier
     const uint32_t rbar = rfull + 8 * q;
-    const uint32_t stage_w = sOut + q * 4096;  // this warp's 32 rows of the staging tile (per 64-channel half: + hf * 16384)
+    const uint32_t stage_q = sOut + q * 4096;  // this warp's 32 rows of a staging tile (slot i: + i * NH * 16384, half hf: + hf * 16384)
     auto gn_flush = [&]() {
       if (a.gn_part == nullptr || gb < 0) return;
       const int V = 2 * (32 / a.gn_cpg);
@@ -281,14 +338,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (live && m.b != gb) { gn_flush(); gb = m.b; }
       // The staging rows of this warp are reused by every m-tile: they are free once the previous TMA stores have read
       // them.  The residual tile of the first m-tile is fetched while the MMAs of this group are still running.
+      // Every m-tile slot commits exactly one bulk group per work unit (an empty one if the tile is skipped), so when
+      // slot i is acquired the group that last read it is the MT-th newest: allow the MT - 1 newer ones to be pending.
       auto stage_acquire = [&](int i) {
         if (lane == 0) {
-          bulk_wait_read0();
+          bulk_wait_read<MT - 1>();
           if (a.has_res) {
             mbar_expect_tx(rbar, NH * 4096);
 #pragma unroll
             for (int hf = 0; hf < NH; ++hf)
-              tma_load_5d(stage_w + hf * 16384, &tmR, rbar, hf * 64, m.w0 + 8 * i, m.h0 + 4 * q, m.t, m.b);
+              tma_load_5d(stage_q + (i * NH + hf) * 16384, &tmR, rbar, hf * 64, m.w0 + 8 * i, m.h0 + 4 * q, m.t, m.b);
           }
         }
         __syncwarp();
@@ -299,8 +358,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = (m.h0 + hh) < a.Ho;
 #pragma unroll 1
       for (int i = 0; i < MT; ++i) {
-        if (!live || m.w0 + 8 * i >= a.Wo) continue;  // warp-uniform
+        if (!live || m.w0 + 8 * i >= a.Wo) {  // warp-uniform
+          if (lane == 0) bulk_commit();        // keep one group per slot and unit
+          continue;
+        }
         if (i > 0) stage_acquire(i);
+        const uint32_t stage_w = stage_q + i * NH * 16384;
         const bool valid = row_ok && (m.w0 + 8 * i + ww) < a.Wo;
         if (a.has_res) { mbar_wait(rbar, rph); rph ^= 1u; }
         const uint32_t t_cols = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS + i * BN);
@@ -378,13 +441,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <typename T, int BN, int MT, bool PAIR>
+template <typename T, int BN, int MT, bool PAIR, bool THIN = false>
 static int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
                          const CUtensorMap& tmX, const CUtensorMap& tmW, const HaloArgs& a, cudaStream_t stream) {
-  using Cfg = HaloCfg<BN, MT, PAIR>;
+  using Cfg = HaloCfg<BN, MT, PAIR, THIN>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_halo_kernel<T, BN, MT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_halo_kernel<T, BN, MT, PAIR, THIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
       return fail(HYVAE_ECUDA, "conv_halo: cannot opt in to %d bytes of shared memory", Cfg::SMEM_BYTES);
     attr_set = true;
   }
@@ -402,19 +465,22 @@ static int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   cfg.blockDim = dim3(HALO_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  if (cudaLaunchKernelEx(&cfg, conv_halo_kernel<T, BN, MT, PAIR>, tmA, tmB, tmY, tmR, tmX, tmW, a) != cudaSuccess)
+  if (cudaLaunchKernelEx(&cfg, conv_halo_kernel<T, BN, MT, PAIR, THIN>, tmA, tmB, tmY, tmR, tmX, tmW, a) != cudaSuccess)
     return fail(HYVAE_ECUDA, "conv_halo: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   return check_launch("conv3d_causal_tc (halo)");
 }
 
-// geometry the host needs for the tensor maps: A box {64, twh, thh}; B box {64, brows, taps_per_b}
-void halo_geometry(int bn, int mt, bool pair, int* twh, int* thh, int* taps_per_b, int* brows) {
-  *twh = 8 * mt + 2; *thh = 18; *taps_per_b = bn >= 128 ? 1 : 3; *brows = pair ? bn / 2 : bn;
+// geometry the host needs for the tensor maps: A box {64 (16 thin), twh, thh}; B box {64 (16), brows, taps_per_b}
+void halo_geometry(int bn, int mt, bool pair, bool thin, int* twh, int* thh, int* taps_per_b, int* brows) {
+  *twh = 8 * mt + 2; *thh = 18; *taps_per_b = thin ? 27 : (bn >= 128 ? 1 : 3); *brows = pair ? bn / 2 : bn;
 }
 
-int launch_halo(int dtype, int bn, int mt, bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+int launch_halo(int dtype, int bn, int mt, bool pair, bool thin, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
                 const CUtensorMap& tmR, const CUtensorMap& tmX, const CUtensorMap& tmW, const HaloArgs& a, cudaStream_t stream) {
 #define HYVAE_HALO_CASE(T)                                                                                       \
+  if (thin && bn == 128 && mt == 2) return pair ? launch_halo_t<T, 128, 2, true, true>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream)    \
+                                                : launch_halo_t<T, 128, 2, false, true>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream);  \
+  if (thin) return fail(HYVAE_EUNSUPPORTED, "conv_halo: the thin-Cin form is only built for BN=128");            \
   if (bn == 128 && mt == 2) return pair ? launch_halo_t<T, 128, 2, true>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream)           \
                                         : launch_halo_t<T, 128, 2, false>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream);         \
   if (bn == 64 && mt == 2 && !pair) return launch_halo_t<T, 64, 2, false>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream);         \

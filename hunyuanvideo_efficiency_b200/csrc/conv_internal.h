@@ -25,8 +25,8 @@ struct HaloArgs {
   int probe;
 };
 
-void halo_geometry(int bn, int mt, bool pair, int* twh, int* thh, int* taps_per_b, int* brows);
-int launch_halo(int dtype, int bn, int mt, bool pair, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+void halo_geometry(int bn, int mt, bool pair, bool thin, int* twh, int* thh, int* taps_per_b, int* brows);
+int launch_halo(int dtype, int bn, int mt, bool pair, bool thin, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
                 const CUtensorMap& tmR, const CUtensorMap& tmX, const CUtensorMap& tmW, const HaloArgs& a, cudaStream_t stream);
 
 }  // namespace hyvae

@@ -815,8 +815,12 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
     h.total = (int64_t)y->B * y->T * h.tiles_h * h.groups_w;
     // CTA pairs (M = 256 MMAs, half of the weight tile per CTA) for the wide tile once there is work for every pair
     const bool pair = bn == 128 && (variant == 6 || (variant == 0 && h.total >= num_sms()));
+    // thin-Cin form (conv_in: 3 channels stored as 16): 32-byte rows, SWIZZLE_32B, resident weights
+    const bool thin = x->C == 16 && bn == 128 && sc_x == nullptr && variant != 5;
+    const int krow = thin ? 16 : 64;
+    const CUtensorMapSwizzle swz = thin ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B;
     int twh, thh, taps_per_b, brows;
-    halo_geometry(bn, mt, pair, &twh, &thh, &taps_per_b, &brows);
+    halo_geometry(bn, mt, pair, thin, &twh, &thh, &taps_per_b, &brows);
     h.bias = bias; h.B = y->B; h.To = y->T; h.Ho = y->H; h.Wo = y->W; h.Cin = x->C; h.Cout = y->C;
     h.has_res = residual != nullptr; h.round_like_ref = round_like_ref;
     h.sc_cin = sc_x ? sc_x->C : 0; h.sc_chunks = (h.sc_cin + 63) / 64;
@@ -831,19 +835,19 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
     {
       cuuint64_t dims[5] = {(cuuint64_t)x->C, (cuuint64_t)vx.Wp(), (cuuint64_t)vx.Hp(), (cuuint64_t)vx.Tp(), (cuuint64_t)x->B};
       cuuint64_t strides[4] = {(cuuint64_t)vx.sW * 2, (cuuint64_t)vx.sH * 2, (cuuint64_t)vx.sT * 2, (cuuint64_t)vx.sB * 2};
-      cuuint32_t box[5] = {64, (cuuint32_t)twh, (cuuint32_t)thh, 1, 1};
+      cuuint32_t box[5] = {(cuuint32_t)krow, (cuuint32_t)twh, (cuuint32_t)thh, 1, 1};
       cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-      CUresult r = encode(&tmA, dt, 5, x->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+      CUresult r = encode(&tmA, dt, 5, x->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(A halo) failed with %d", (int)r);
     }
     {
       cuuint64_t dims[3] = {(cuuint64_t)x->C, (cuuint64_t)y->C, 27};
       cuuint64_t strides[2] = {(cuuint64_t)x->C * 2, (cuuint64_t)x->C * y->C * 2};
-      cuuint32_t box[3] = {64, (cuuint32_t)brows, (cuuint32_t)taps_per_b};
+      cuuint32_t box[3] = {(cuuint32_t)krow, (cuuint32_t)brows, (cuuint32_t)taps_per_b};
       cuuint32_t estr[3] = {1, 1, 1};
       CUresult r = encode(&tmB, dt, 3, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          swz, thin ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(B) failed with %d", (int)r);
     }
     auto out_map = [&](CUtensorMap* tm, const hyvae_vol* v, const Vol& vv) -> int {
@@ -882,10 +886,10 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
       if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(shortcut w) failed with %d", (int)r);
     }
     char tag[56];
-    snprintf(tag, sizeof(tag), "k3 %d->%d %dx%dx%dx%d s111 BN%d halo%s%s", x->C, y->C, y->B, y->T, y->H, y->W, bn, pair ? "2" : "", sc_x ? "+sc" : "");
+    snprintf(tag, sizeof(tag), "k3 %d->%d %dx%dx%dx%d s111 BN%d halo%s%s%s", x->C, y->C, y->B, y->T, y->H, y->W, bn, pair ? "2" : "", sc_x ? "+sc" : "", thin ? " thin" : "");
     const double vox = (double)y->B * y->T * y->H * y->W;
     ProfScope prof(PC_CONV_TC, 2.0 * vox * y->C * (x->C * 27.0 + (sc_x ? sc_x->C : 0)), stream, tag);
-    return launch_halo(x->dtype, bn, mt, pair, tmA, tmB, tmY, tmR, tmX, tmW, h, (cudaStream_t)stream);
+    return launch_halo(x->dtype, bn, mt, pair, thin, tmA, tmB, tmY, tmR, tmX, tmW, h, (cudaStream_t)stream);
   }
 
   pick_tile(y->H, y->W, sh, sw, &a.TH, &a.TW);

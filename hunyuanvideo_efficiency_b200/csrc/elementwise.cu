@@ -42,7 +42,16 @@ __global__ void ncthw_to_vol_kernel(const S* __restrict__ src, Vol d, int src_C,
     int w = min(max(wp - d.pw, 0), d.W - 1);
     const S* s = src + b * sb + t * st + h * sh + w * sw;
     D* o = dst + i * d.C;
-    for (int c = 0; c < d.C; ++c) o[c] = c < src_C ? from_f<D>(to_f<S>(s[c * sc])) : from_f<D>(0.f);  // zero channel padding
+    if ((d.C & 7) == 0) {  // 16-byte stores (conv_in: 3 channels stored as 16)
+      for (int c0 = 0; c0 < d.C; c0 += 8) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = (c0 + j) < src_C ? to_f<S>(s[(c0 + j) * sc]) : 0.f;
+        Vec8<D> q; q.set(f); q.store(o + c0);
+      }
+    } else {
+      for (int c = 0; c < d.C; ++c) o[c] = c < src_C ? from_f<D>(to_f<S>(s[c * sc])) : from_f<D>(0.f);  // zero channel padding
+    }
   }
 }
 

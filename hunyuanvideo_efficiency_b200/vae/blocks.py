@@ -61,18 +61,27 @@ class _Conv3dParams(nn.Module):
             nn.init.uniform_(self.bias, -bound, bound)
         self._packed = None
 
+    def cin_padded(self) -> int:
+        """Input channels the tensor-core kernels see: multiples of 8 (16-byte rows); a thin stride-1 3x3x3 layer with a
+        wide output (conv_in, 3 -> 128) is stored as 16 channels = one K = 16 MMA slice per 32-byte row (conv_halo.cu, THIN)."""
+        ci, co = self.in_channels, self.out_channels
+        if ci < 16 and 64 < co <= 128 and self.kernel_size[0] == 3 and tuple(int(v) for v in self.stride) == (1, 1, 1):
+            return 16
+        return -(-ci // 8) * 8
+
     def packed(self, dtype, pad8: bool = False):
         """[taps][Cout][Cin] weights in the activation dtype + fp32 bias (kernel layout), cached.  pad8 zero-pads
-        Cout and Cin up to multiples of 8 (16-byte rows) for the tensor-core kernel."""
+        Cout up to a multiple of 8 and Cin up to cin_padded() (16-byte rows) for the tensor-core kernel."""
         w = self.weight
-        key = (w._version, w.data_ptr(), dtype, w.device, None if self.bias is None else self.bias._version, pad8)
+        key = (w._version, w.data_ptr(), dtype, w.device, None if self.bias is None else self.bias._version, pad8,
+               tuple(int(v) for v in self.stride))
         if self._packed is None or self._packed[0] != key:
             k = self.kernel_size[0]
             co, ci = self.out_channels, self.in_channels
             pw = w.detach().permute(2, 3, 4, 0, 1).reshape(k * k * k, co, ci).to(dtype)
             pb = None if self.bias is None else self.bias.detach().float()
-            if pad8 and (co % 8 or ci % 8):
-                cop, cip = -(-co // 8) * 8, -(-ci // 8) * 8
+            if pad8 and (co % 8 or ci != self.cin_padded()):
+                cop, cip = -(-co // 8) * 8, self.cin_padded()
                 full = torch.zeros((k * k * k, cop, cip), dtype=dtype, device=w.device)
                 full[:, :co, :ci] = pw
                 pw = full
@@ -136,7 +145,7 @@ class CausalConv3d(nn.Module):
         """(halo, channel count) a producer should write so that this conv needs no extra pad pass."""
         c = self.conv
         if tc_eligible(dtype, c.in_channels, c.out_channels, c.stride, c.kernel_size[0]):
-            return self.halo, -(-c.in_channels // 8) * 8
+            return self.halo, c.cin_padded()
         return (0, 0, 0), c.in_channels
 
     def forward_vol(self, x: Vol, residual: Optional[Vol] = None, up=(1, 1, 1), out_dtype=None) -> Vol:

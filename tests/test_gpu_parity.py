@@ -167,7 +167,7 @@ def test_tc_thin_layers_and_fused_gn_stats():
     x = torch.randn(2, 3, 5, 20, 24, generator=g).half()
     cin3.emit_gn_groups = 32
     pad, ch = cin3.input_layout(torch.float16)
-    assert (pad, ch) == ((2, 1, 1), 8)
+    assert (pad, ch) == ((2, 1, 1), 16)     # thin-Cin form: 3 channels stored as 16 (one K = 16 slice per 32-byte row)
     y = cin3.forward_vol(N.Vol.from_ncthw(x.to(_dev()), pad=pad, channels=ch))
     ref = O.causal_conv3d(x.float(), cin3.conv.weight.detach().half().float().cpu(), cin3.conv.bias.detach().float().cpu())
     assert O.rel_err(ref, y.to_ncthw().float().cpu()) < 2e-3
