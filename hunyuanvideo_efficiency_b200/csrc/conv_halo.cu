@@ -48,7 +48,7 @@ template <int BN, int MT, bool PAIR, bool THIN = false> struct HaloCfg {
   static constexpr int NH = (BN + 63) / 64;                          // 64-channel halves of the output tile
   static constexpr int OUT_BYTES = MT * NH * 16384;                  // one staging tile per m-tile slot: a tile's TMA store is only
                                                                      // waited for when its slot comes round again, MT tiles later
-  static constexpr int BUDGET = 227 * 1024 - 2048;                   // minus alignment slack and barrier block
+  static constexpr int BUDGET = 227 * 1024 - 4096;                   // minus alignment slack, barrier block, per-warp bias copies
   static constexpr int NA_THIN_RAW = (BUDGET - OUT_BYTES - (B_BYTES + 1023) / 1024 * 1024) / A_BYTES;
   static constexpr int NA = THIN ? (NA_THIN_RAW > 8 ? 8 : NA_THIN_RAW) : 2;
   static constexpr int NB_RAW = (BUDGET - NA * A_BYTES - OUT_BYTES) / B_BYTES;
@@ -56,7 +56,7 @@ template <int BN, int MT, bool PAIR, bool THIN = false> struct HaloCfg {
   static constexpr int B_RING_BYTES = (NB * B_BYTES + 1023) / 1024 * 1024;
   static constexpr int ACC_COLS = MT * BN;
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
-  static constexpr int SMEM_BYTES = NA * A_BYTES + B_RING_BYTES + OUT_BYTES + 2048;
+  static constexpr int SMEM_BYTES = NA * A_BYTES + B_RING_BYTES + OUT_BYTES + 4096;
   static_assert(THIN || NB >= 3, "B ring too shallow");
   static_assert(!THIN || NA >= 4, "A ring too shallow");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -104,6 +104,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tfull = bempty + 8 * NB, tempty = tfull + 16;
   const uint32_t rfull = tempty + 16;                       // [4 warps]
   const uint32_t tmem_slot = rfull + 8 * 4;
+  const uint32_t sbias_all = bars + 1024;                   // [4 warps][BN] fp32
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
 
@@ -312,6 +313,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int gb = -1;       // batch item the accumulators belong to
     uint32_t rph = 0;  // phase of this warp's residual barrier
     const uint32_t rbar = rfull + 8 * q;
+    const uint32_t sbias = sbias_all + q * (BN * 4);
+    epi_load_bias<BN>(a.bias, 0, a.Cout, sbias, lane);
     const uint32_t stage_q = sOut + q * 4096;  // this warp's 32 rows of a staging tile (slot i: + i * NH * 16384, half hf: + hf * 16384)
     auto gn_flush = [&]() {
       if (a.gn_part == nullptr || gb < 0) return;
@@ -367,49 +370,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool valid = row_ok && (m.w0 + 8 * i + ww) < a.Wo;
         if (a.has_res) { mbar_wait(rbar, rph); rph ^= 1u; }
         const uint32_t t_cols = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS + i * BN);
-#pragma unroll
-        for (int j = 0; j < BN / 32; ++j) {
-          uint32_t v[32];
-          tmem_ld32(t_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
-          tmem_ld_wait();
-          float f[32];
-#pragma unroll
-          for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
-          const int nc = j * 32;
-          if (nc < a.Cout) {  // warp-uniform
-            const uint32_t srow = stage_w + (j >> 1) * 16384 + lane * 128;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int n = nc + c * 8;
-              if (a.bias && n < a.Cout) {
-                const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n);
-                const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n + 4);
-                f[c * 8 + 0] += b0.x; f[c * 8 + 1] += b0.y; f[c * 8 + 2] += b0.z; f[c * 8 + 3] += b0.w;
-                f[c * 8 + 4] += b1.x; f[c * 8 + 5] += b1.y; f[c * 8 + 6] += b1.z; f[c * 8 + 7] += b1.w;
-              }
-              const uint32_t sa16 = srow + ((uint32_t)((((j & 1) * 4 + c) ^ (lane & 7))) << 4);
-              if (a.has_res) {
-                Vec8<T> r; r.v = lds128(sa16);
-                float rf[8]; r.get(rf);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[c * 8 + e] = (a.round_like_ref ? rnd<T>(f[c * 8 + e]) : f[c * 8 + e]) + rf[e];
-              }
-              Vec8<T> o; o.set(&f[c * 8]);
-              sts128(sa16, o.v);
-            }
-            if (a.gn_part) {
-              float r;
-              switch (a.gn_cpg) {
-                case 2: r = gn_chunk_reduce<2>(f, valid, lane); break;
-                case 4: r = gn_chunk_reduce<4>(f, valid, lane); break;
-                case 8: r = gn_chunk_reduce<8>(f, valid, lane); break;
-                case 16: r = gn_chunk_reduce<16>(f, valid, lane); break;
-                default: r = gn_chunk_reduce<32>(f, valid, lane); break;
-              }
-              gacc[j] += (double)r;
-            }
-          }
-        }
+        HYVAE_EPI_TILE_SWITCH(T, BN, a.gn_part ? a.gn_cpg : 0, t_cols, q, lane, stage_w, sbias, 0, a.Cout, a.bias != nullptr,
+                              a.has_res != 0, a.round_like_ref != 0, valid, gacc)
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {

@@ -313,12 +313,12 @@ template <int BN, bool KHT> struct Tc2Cfg {
   // 128-row x 64-channel SWIZZLE_128B staging block per 64-channel half of the tile
   static constexpr int NH = (BN + 63) / 64;
   static constexpr int OUT_BYTES = KHT ? NH * 16384 : 0;
-  static constexpr int BUDGET = (KHT ? 225 : 200) * 1024 - OUT_BYTES;
+  static constexpr int BUDGET = (KHT ? 225 * 1024 - 4 * BN * 4 : 200 * 1024) - OUT_BYTES;
   static constexpr int SB_RAW = KHT ? (BUDGET - SA * A_BYTES) / B_STAGE_BYTES : BUDGET / (A_BYTES + B_STAGE_BYTES);
   static constexpr int SB = SB_RAW > 12 ? 12 : SB_RAW;
   static constexpr int NA = KHT ? SA : SB;                            // number of A buffers
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = NA * A_BYTES + SB * B_STAGE_BYTES + OUT_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = NA * A_BYTES + SB * B_STAGE_BYTES + OUT_BYTES + 1024 + 1024 + (KHT ? 4 * BN * 4 : 0);
   static_assert(SB >= 4, "B ring too shallow");
 };
 
@@ -341,6 +341,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tfull_bar = aempty_bar + 8 * NA, tempty_bar = tfull_bar + 16;
   const uint32_t rfull_bar = tempty_bar + 16;  // [4 epilogue warps]: residual tile landed (TMA_EPI only)
   const uint32_t tmem_slot = rfull_bar + 32;
+  const uint32_t sbias_all = bars + 1024;      // [4 warps][BN] fp32 (TMA_EPI only)
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
 
@@ -517,6 +518,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int hh = 4 * q + (lane >> 3), ww = lane & 7;
       const uint32_t rbar = rfull_bar + 8 * q;
       const uint32_t stage_w = sOut + q * 4096;
+      const uint32_t sbias = sbias_all + q * (BN * 4);
+      int bias_nt = -1;
       uint32_t rph = 0;
       double gacc[BN / 32];
 #pragma unroll
@@ -565,49 +568,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const bool valid = (m.h0 + hh) < a.Ho && (m.w0 + ww) < a.Wo;
           if (a.res) { mbar_wait(rbar, rph); rph ^= 1u; }
           const uint32_t t_cols = tmem_base + (uint32_t)(acc * BN);
-#pragma unroll
-          for (int j = 0; j < BN / 32; ++j) {
-            uint32_t v[32];
-            tmem_ld32(t_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
-            tmem_ld_wait();
-            float f[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
-            const int nc = n0 + j * 32;
-            if (nc < a.Cout) {  // warp-uniform
-              const uint32_t srow = stage_w + (j >> 1) * 16384 + lane * 128;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const int n = nc + c * 8;
-                if (a.bias && n < a.Cout) {
-                  const float4 b0 = *reinterpret_cast<const float4*>(a.bias + n);
-                  const float4 b1 = *reinterpret_cast<const float4*>(a.bias + n + 4);
-                  f[c * 8 + 0] += b0.x; f[c * 8 + 1] += b0.y; f[c * 8 + 2] += b0.z; f[c * 8 + 3] += b0.w;
-                  f[c * 8 + 4] += b1.x; f[c * 8 + 5] += b1.y; f[c * 8 + 6] += b1.z; f[c * 8 + 7] += b1.w;
-                }
-                const uint32_t sa16 = srow + ((uint32_t)((((j & 1) * 4 + c) ^ (lane & 7))) << 4);
-                if (a.res) {
-                  Vec8<T> r; r.v = lds128(sa16);
-                  float rf[8]; r.get(rf);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[c * 8 + e] = (a.round_like_ref ? rnd<T>(f[c * 8 + e]) : f[c * 8 + e]) + rf[e];
-                }
-                Vec8<T> o; o.set(&f[c * 8]);
-                sts128(sa16, o.v);
-              }
-              if (a.gn_part) {
-                float r;
-                switch (a.gn_cpg) {
-                  case 2: r = gn_chunk_reduce<2>(f, valid, lane); break;
-                  case 4: r = gn_chunk_reduce<4>(f, valid, lane); break;
-                  case 8: r = gn_chunk_reduce<8>(f, valid, lane); break;
-                  case 16: r = gn_chunk_reduce<16>(f, valid, lane); break;
-                  default: r = gn_chunk_reduce<32>(f, valid, lane); break;
-                }
-                gacc[j] += (double)r;
-              }
-            }
-          }
+          if (nt != bias_nt) { epi_load_bias<BN>(a.bias, n0, a.Cout, sbias, lane); bias_nt = nt; }
+          HYVAE_EPI_TILE_SWITCH(T, BN, a.gn_part ? a.gn_cpg : 0, t_cols, q, lane, stage_w, sbias, n0, a.Cout, a.bias != nullptr,
+                                a.res != nullptr, a.round_like_ref != 0, valid, gacc)
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {

@@ -173,6 +173,80 @@ __device__ __forceinline__ float gn_chunk_reduce(const float* f, bool valid, int
   return halving_reduce<V>(v, lane);
 }
 
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+
+// Staged epilogue of ONE 128-voxel x BN-channel accumulator tile for this warp's 32 rows (TMEM lane quarter q):
+// TMEM -> registers -> + bias (per-warp copy in shared memory: with 227 KB of shared memory there is no L1 left, a
+// global bias load was an L2 round trip per 32 columns) -> + residual (already in the staging rows, put there by TMA)
+// -> 16-bit -> swizzled staging rows (the caller issues the TMA store) -> GroupNorm partials by the halving tree into
+// the warp's fp64 register accumulators.  CPG (channels per group, 0 = no statistics) is a template parameter and the
+// caller switches on it ONCE per tile: with the switch inside the unrolled column loop all five variants were
+// interleaved in the instruction stream and the epilogue stalled on instruction fetch (ncu: stall_no_inst).
+template <typename T, int BN, int CPG>
+__device__ __forceinline__ void epi_tile(uint32_t t_cols, int q, int lane, uint32_t stage_w, uint32_t sbias, int n0, int Cout,
+                                         bool has_bias, bool has_res, bool rlr, bool valid, double (&gacc)[BN / 32]) {
+#pragma unroll
+  for (int j = 0; j < BN / 32; ++j) {
+    uint32_t v[32];
+    tmem_ld32(t_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+    const int nc = n0 + j * 32;
+    if (nc < Cout) {  // warp-uniform
+      const uint32_t srow = stage_w + (j >> 1) * 16384 + lane * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (has_bias) {  // columns >= Cout read zeros (the per-warp copy is zero padded)
+          const float4 b0 = lds_f4(sbias + (uint32_t)(j * 32 + c * 8) * 4), b1 = lds_f4(sbias + (uint32_t)(j * 32 + c * 8 + 4) * 4);
+          f[c * 8 + 0] += b0.x; f[c * 8 + 1] += b0.y; f[c * 8 + 2] += b0.z; f[c * 8 + 3] += b0.w;
+          f[c * 8 + 4] += b1.x; f[c * 8 + 5] += b1.y; f[c * 8 + 6] += b1.z; f[c * 8 + 7] += b1.w;
+        }
+        const uint32_t sa16 = srow + ((uint32_t)((((j & 1) * 4 + c) ^ (lane & 7))) << 4);
+        if (has_res) {
+          Vec8<T> r; r.v = lds128(sa16);
+          float rf[8]; r.get(rf);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[c * 8 + e] = (rlr ? rnd<T>(f[c * 8 + e]) : f[c * 8 + e]) + rf[e];
+        }
+        Vec8<T> o; o.set(&f[c * 8]);
+        sts128(sa16, o.v);
+      }
+      if (CPG > 0) gacc[j] += (double)gn_chunk_reduce<(CPG > 0 ? CPG : 1)>(f, valid, lane);
+    }
+  }
+}
+
+// per-warp bias copy: BN floats at `sbias` (shared), zero beyond Cout; each lane fetches 8 consecutive values
+template <int BN>
+__device__ __forceinline__ void epi_load_bias(const float* bias, int n0, int Cout, uint32_t sbias, int lane) {
+  if (lane * 8 < BN) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = n0 + lane * 8 + h * 4;
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias != nullptr && n < Cout) b = *reinterpret_cast<const float4*>(bias + n);  // Cout is a multiple of 8
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbias + (uint32_t)(lane * 8 + h * 4) * 4), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+    }
+  }
+  __syncwarp();
+}
+
+#define HYVAE_EPI_TILE_SWITCH(T, BN, cpg, ...)                         \
+  switch (cpg) {                                                       \
+    case 0: epi_tile<T, BN, 0>(__VA_ARGS__); break;                    \
+    case 2: epi_tile<T, BN, 2>(__VA_ARGS__); break;                    \
+    case 4: epi_tile<T, BN, 4>(__VA_ARGS__); break;                    \
+    case 8: epi_tile<T, BN, 8>(__VA_ARGS__); break;                    \
+    case 16: epi_tile<T, BN, 16>(__VA_ARGS__); break;                  \
+    default: epi_tile<T, BN, 32>(__VA_ARGS__); break;                  \
+  }
+
 // ---------------------------------------------------------------------------------- CTA-pair (cta_group::2) forms
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {

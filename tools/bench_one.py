@@ -8,7 +8,7 @@ what = sys.argv[1] if len(sys.argv) > 1 else "conv256"
 CASES = {  # Cin, Cout, T, H, W, residual, variant
     "conv128": (128, 128, 17, 256, 256, True, 0), "conv128_1cta": (128, 128, 17, 256, 256, True, 2),
     "conv256": (256, 256, 17, 128, 128, True, 0), "conv512": (512, 512, 17, 64, 64, True, 0),
-    "convin": (8, 128, 17, 256, 256, False, 0), "convout": (128, 8, 17, 256, 256, False, 0),
+    "convin": (16, 128, 17, 256, 256, False, 0), "convout": (128, 8, 17, 256, 256, False, 0),
 }
 if what in CASES:
     Cin, Cout, T, H, W, res, variant = CASES[what]
