@@ -316,8 +316,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t sbias = sbias_all + q * (BN * 4);
     epi_load_bias<BN>(a.bias, 0, a.Cout, sbias, lane);
     const uint32_t stage_q = sOut + q * 4096;  // this warp's 32 rows of a staging tile (slot i: + i * NH * 16384, half hf: + hf * 16384)
+    float lacc[64];
+#pragma unroll
+    for (int e = 0; e < 64; ++e) lacc[e] = 0.f;
     auto gn_flush = [&]() {
       if (a.gn_part == nullptr || gb < 0) return;
+      if (epi_lane_acc(BN, a.gn_cpg)) {
+        epi_flush_lanes<BN>(lacc, a.gn_cpg, 0, a.gn_groups, a.gn_part + ((int64_t)gb * a.gn_rows + blockIdx.x * 4 + q) * a.gn_groups * 2, lane);
+        return;
+      }
       const int V = 2 * (32 / a.gn_cpg);
       const int per = 32 / V;  // lanes holding the same value
       if (lane % per == 0) {
@@ -371,7 +378,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (a.has_res) { mbar_wait(rbar, rph); rph ^= 1u; }
         const uint32_t t_cols = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS + i * BN);
         HYVAE_EPI_TILE_SWITCH(T, BN, a.gn_part ? a.gn_cpg : 0, t_cols, q, lane, stage_w, sbias, 0, a.Cout, a.bias != nullptr,
-                              a.has_res != 0, a.round_like_ref != 0, valid, gacc)
+                              a.has_res != 0, a.round_like_ref != 0, valid, gacc, lacc)
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {

@@ -525,8 +525,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
       for (int j = 0; j < BN / 32; ++j) gacc[j] = 0.0;
       int gb = -1, gnt = 0;
+      float lacc[64];
+#pragma unroll
+      for (int e = 0; e < 64; ++e) lacc[e] = 0.f;
       auto gn_flush = [&]() {
         if (a.gn_part == nullptr || gb < 0) return;
+        if (epi_lane_acc(BN, a.gn_cpg)) {
+          epi_flush_lanes<BN>(lacc, a.gn_cpg, gnt * BN / a.gn_cpg, a.gn_groups,
+                              a.gn_part + ((int64_t)gb * a.gn_rows + blockIdx.x * 4 + q) * a.gn_groups * 2, lane);
+          return;
+        }
         const int V = 2 * (32 / a.gn_cpg);
         const int per = 32 / V;
         if (lane % per == 0) {
@@ -570,7 +578,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t t_cols = tmem_base + (uint32_t)(acc * BN);
           if (nt != bias_nt) { epi_load_bias<BN>(a.bias, n0, a.Cout, sbias, lane); bias_nt = nt; }
           HYVAE_EPI_TILE_SWITCH(T, BN, a.gn_part ? a.gn_cpg : 0, t_cols, q, lane, stage_w, sbias, n0, a.Cout, a.bias != nullptr,
-                                a.res != nullptr, a.round_like_ref != 0, valid, gacc)
+                                a.res != nullptr, a.round_like_ref != 0, valid, gacc, lacc)
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {

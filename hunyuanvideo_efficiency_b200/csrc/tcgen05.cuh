@@ -188,7 +188,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t a) {
 // interleaved in the instruction stream and the epilogue stalled on instruction fetch (ncu: stall_no_inst).
 template <typename T, int BN, int CPG>
 __device__ __forceinline__ void epi_tile(uint32_t t_cols, int q, int lane, uint32_t stage_w, uint32_t sbias, int n0, int Cout,
-                                         bool has_bias, bool has_res, bool rlr, bool valid, double (&gacc)[BN / 32]) {
+                                         bool has_bias, bool has_res, bool rlr, bool valid, double (&gacc)[BN / 32], float (&lacc)[64]) {
 #pragma unroll
   for (int j = 0; j < BN / 32; ++j) {
     uint32_t v[32];
@@ -217,10 +217,40 @@ __device__ __forceinline__ void epi_tile(uint32_t t_cols, int q, int lane, uint3
         Vec8<T> o; o.set(&f[c * 8]);
         sts128(sa16, o.v);
       }
-      if (CPG > 0) gacc[j] += (double)gn_chunk_reduce<(CPG > 0 ? CPG : 1)>(f, valid, lane);
+      if constexpr (CPG > 0 && 2 * BN / (CPG > 0 ? CPG : 1) <= 64) {
+        // per-LANE fp32 partial sums of this row, kept in registers across tiles; lanes are only combined when the
+        // caller flushes (epi_flush_lanes): no shuffle and no fp64 add on the per-tile path
+#pragma unroll
+        for (int g = 0; g < 32 / CPG; ++g) {
+          float sm = 0.f, sq = 0.f;
+#pragma unroll
+          for (int c = 0; c < CPG; ++c) { const float u = valid ? f[g * CPG + c] : 0.f; sm += u; sq = fmaf(u, u, sq); }
+          lacc[(j * (32 / CPG) + g) * 2] += sm;
+          lacc[(j * (32 / CPG) + g) * 2 + 1] += sq;
+        }
+      } else if constexpr (CPG > 0) {
+        gacc[j] += (double)gn_chunk_reduce<(CPG > 0 ? CPG : 1)>(f, valid, lane);
+      }
     }
   }
 }
+
+// Flush of the per-lane GroupNorm accumulators of epi_tile: two halving trees of 32 values leave value v (= (group - first
+// group of the tile) * 2 + moment) in lane v % 32 of round v / 32; the lane adds it to the warp's private fp64 row.
+template <int BN>
+__device__ __forceinline__ void epi_flush_lanes(float (&lacc)[64], int cpg, int first_group, int gn_groups, double* row, int lane) {
+  const int nval = 2 * BN / cpg;  // <= 64
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float v[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) { v[e] = lacc[32 * r + e]; lacc[32 * r + e] = 0.f; }
+    const float tot = halving_reduce<32>(v, lane);
+    const int idx = 32 * r + lane, grp = first_group + (idx >> 1);
+    if (idx < nval && grp < gn_groups) row[grp * 2 + (idx & 1)] += (double)tot;  // private slot: plain RMW
+  }
+}
+__device__ __forceinline__ bool epi_lane_acc(int bn, int cpg) { return cpg > 0 && 2 * bn / cpg <= 64; }
 
 // per-warp bias copy: BN floats at `sbias` (shared), zero beyond Cout; each lane fetches 8 consecutive values
 template <int BN>
