@@ -306,7 +306,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // (half the MACs per A byte) need to leave the L2-bandwidth bound.  A and B run in separate TMA rings.
 template <int BN, bool KHT> struct Tc2Cfg {
   static constexpr int NSUB = KHT ? 3 : 1;                            // B stages (taps) consumed per A stage
-  static constexpr int A_BYTES = KHT ? 18 * 1024 : A_STAGE_BYTES;
+  static constexpr int A_BYTES = KHT ? 20 * 1024 : A_STAGE_BYTES;     // KHT halo stage: 18 rows x 8 or 10 rows x 16 voxels
   static constexpr int B_STAGE_BYTES = (BN / 2) * 64 * 2;             // this CTA's half of the weight tile
   static constexpr int SA = KHT ? 3 : 0;                              // A ring depth (KHT); non-KHT shares the B ring index
   // KHT kernels with a 16-bit output run the epilogue through shared memory and TMA stores (see conv_halo.cu): one
@@ -466,7 +466,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tc_fence_after();
             if (elect_one()) {
               // KHT: tap kh reads the halo stage 8 rows (= 1024 B, one swizzle atom) further down
-              const uint64_t adesc = make_kmajor_sw128_desc(KHT ? sA + sa * Cfg::A_BYTES + sub * 1024 : sA + sb * Cfg::A_BYTES);
+              const uint64_t adesc = make_kmajor_sw128_desc(KHT ? sA + sa * Cfg::A_BYTES + sub * a.TW * 128 : sA + sb * Cfg::A_BYTES);
               const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * Cfg::B_STAGE_BYTES);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -488,7 +488,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(bfull_bar + 8 * sb, pb);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t adesc = make_kmajor_sw128_desc(sA + sa * Cfg::A_BYTES + 1024);
+              const uint64_t adesc = make_kmajor_sw128_desc(sA + sa * Cfg::A_BYTES + a.TW * 128);
               const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * Cfg::B_STAGE_BYTES);
               const int rem = a.sc_cin - kc * 64;
 #pragma unroll
@@ -515,7 +515,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // and 64-channel half; GroupNorm partials by the halving tree into per-warp fp64 register accumulators that are
       // flushed when the (batch item, n-tile) changes.  Same scheme as conv_halo.cu.
       constexpr int NH = Cfg::NH;
-      const int hh = 4 * q + (lane >> 3), ww = lane & 7;
+      const int hq = (32 * q) / a.TW;                                  // first tile row of this warp's 32 voxels
+      const int hh = (32 * q + lane) / a.TW, ww = (32 * q + lane) % a.TW;
       const uint32_t rbar = rfull_bar + 8 * q;
       const uint32_t stage_w = sOut + q * 4096;
       const uint32_t sbias = sbias_all + q * (BN * 4);
@@ -565,7 +566,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               mbar_expect_tx(rbar, NH * 4096);
 #pragma unroll
               for (int hf = 0; hf < NH; ++hf)
-                tma_load_5d(stage_w + hf * 16384, &tmR, rbar, n0 + hf * 64, m.w0, m.h0 + 4 * q, m.t, m.b);
+                tma_load_5d(stage_w + hf * 16384, &tmR, rbar, n0 + hf * 64, m.w0, m.h0 + hq, m.t, m.b);
             }
           }
           __syncwarp();
@@ -585,7 +586,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int hf = 0; hf < NH; ++hf)
               if (n0 + hf * 64 < a.Cout)
-                tma_store_5d(&tmY, stage_w + hf * 16384, n0 + hf * 64, m.w0, m.h0 + 4 * q, m.t, m.b);
+                tma_store_5d(&tmY, stage_w + hf * 16384, n0 + hf * 64, m.w0, m.h0 + hq, m.t, m.b);
             bulk_commit();
           }
         }
@@ -653,11 +654,11 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArg
 // Tensor map of the OUTPUT lattice of a conv (or of its residual): logical dims (C, W, H, T, B) with the element strides
 // of TcArgs, so a phase of the upsample decomposition (stride-2 scatter into y) is a dense box over a strided view.
 static int encode_out_map(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, int64_t off, int C, int W, int H, int T, int B,
-                          int64_t sW, int64_t sH, int64_t sT, int64_t sB) {
+                          int64_t sW, int64_t sH, int64_t sT, int64_t sB, int TW) {
   EncodeTiledFn encode = get_encode_fn();
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t strides[4] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sT * 2, (cuuint64_t)sB * 2};
-  cuuint32_t box[5] = {64, 8, 4, 1, 1};
+  cuuint32_t box[5] = {64, (cuuint32_t)TW, (cuuint32_t)(32 / TW), 1, 1};  // one warp's 32 voxels of a TH x TW tile
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = encode(tm, dt, 5, (char*)const_cast<void*>(base) + off * 2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -679,10 +680,10 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
   CUtensorMap tmY = tmA, tmR = tmA;  // placeholders unless the staged TMA-store epilogue is compiled in
   if (KHT && sizeof(OT) == 2) {
     const CUtensorMapDataType dt = TcFmt<T>::fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    if (int e = encode_out_map(&tmY, dt, a.y, a.yoff, a.Cout, a.Wo, a.Ho, a.To, a.B, a.ysW, a.ysH, a.ysT, a.ysB)) return e;
+    if (int e = encode_out_map(&tmY, dt, a.y, a.yoff, a.Cout, a.Wo, a.Ho, a.To, a.B, a.ysW, a.ysH, a.ysT, a.ysB, a.TW)) return e;
     tmR = tmY;
     if (a.res)
-      if (int e = encode_out_map(&tmR, dt, a.res, a.roff, a.Cout, a.Wo, a.Ho, a.To, a.B, a.rsW, a.rsH, a.rsT, a.rsB)) return e;
+      if (int e = encode_out_map(&tmR, dt, a.res, a.roff, a.Cout, a.Wo, a.Ho, a.To, a.B, a.rsW, a.rsH, a.rsT, a.rsB, a.TW)) return e;
   }
   conv_tc2_kernel<T, OT, BN, KHT><<<(unsigned)(2 * pairs), TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, tmX ? *tmX : tmA, tmW ? *tmW : tmB, a);
   return check_launch("conv3d_causal_tc (2-CTA)");
@@ -874,11 +875,16 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
   if (((variant == 0 && !prefer_1cta) || variant == 4) && k == 3 && st == 1 && sh == 1 && sw == 1 && BN_sel >= 64) {
     // 16 x 8 tiles: accept up to 15 % more padded area than the best 128-voxel tile shape
     const int64_t area_best = (int64_t)((y->H + a.TH - 1) / a.TH) * a.TH * ((y->W + a.TW - 1) / a.TW) * a.TW;
-    const int64_t area_kht = (int64_t)((y->H + 15) / 16) * 16 * ((y->W + 7) / 8) * 8;
-    const int64_t mt_kht = (int64_t)y->B * y->T * ((y->H + 15) / 16) * ((y->W + 7) / 8);
+    // kh-trick tiles: 16 rows x 8 columns, or 8 x 16 when that wastes less (ragged 18 / 36 / 72-row tiles of the 720p split)
+    const int64_t area_168 = (int64_t)((y->H + 15) / 16) * 16 * ((y->W + 7) / 8) * 8;
+    const int64_t area_816 = (int64_t)((y->H + 7) / 8) * 8 * ((y->W + 15) / 16) * 16;
+    const bool t816 = area_816 < area_168;
+    const int kth = t816 ? 8 : 16, ktw = t816 ? 16 : 8;
+    const int64_t area_kht = t816 ? area_816 : area_168;
+    const int64_t mt_kht = (int64_t)y->B * y->T * ((y->H + kth - 1) / kth) * ((y->W + ktw - 1) / ktw);
     // (the staged epilogue of the kh-trick kernel reduces GroupNorm partials for >= 2 channels per group)
     const bool gn_ok = gn_partials == nullptr || (gn_groups > 0 && y->C % gn_groups == 0 && y->C / gn_groups >= 2);
-    if (area_kht * 100 <= area_best * 115 && mt_kht >= 2 && gn_ok) { kht = true; a.TH = 16; a.TW = 8; }
+    if (area_kht * 100 <= area_best * 115 && mt_kht >= 2 && gn_ok) { kht = true; a.TH = kth; a.TW = ktw; a.a_tx = (kth + 2) * ktw * 128; }
   }
   a.tiles_h = (y->H + a.TH - 1) / a.TH; a.tiles_w = (y->W + a.TW - 1) / a.TW;
   const int BN = BN_sel;
@@ -906,7 +912,7 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
     Vol vs = make_vol(sc_x);
     cuuint64_t dims[5] = {(cuuint64_t)sc_x->C, (cuuint64_t)sc_x->W, (cuuint64_t)sc_x->H, (cuuint64_t)sc_x->T, (cuuint64_t)sc_x->B};
     cuuint64_t strides[4] = {(cuuint64_t)vs.sW * 2, (cuuint64_t)vs.sH * 2, (cuuint64_t)vs.sT * 2, (cuuint64_t)vs.sB * 2};
-    cuuint32_t box[5] = {64, 8, 18, 1, 1};
+    cuuint32_t box[5] = {64, (cuuint32_t)a.TW, (cuuint32_t)(a.TH + 2), 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&tmX, dt, 5, (char*)sc_x->data + vs.at(0, 0, 0, 0) * 2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -337,23 +337,43 @@ __device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
   return v;
 }
 
+// One block per row; the visible part of the row (<= L floats) is read from HBM ONCE into shared memory, max / exp /
+// sum run on the staged copy, and the probabilities are written with 8-byte stores (the masked tail as zeros).
 template <typename T>
-__global__ void softmax_frame_causal_kernel(const float* __restrict__ S, T* __restrict__ P, int L, int n_hw, float scale) {
+__global__ void __launch_bounds__(256) softmax_frame_causal_kernel(const float* __restrict__ S, T* __restrict__ P, int L, int n_hw, float scale) {
+  extern __shared__ float row[];  // lim floats
   __shared__ float sh[32];
-  const int64_t row = blockIdx.x;  // b*L + i
-  const int i = (int)(row % L);
+  const int64_t r = blockIdx.x;  // b*L + i
+  const int i = (int)(r % L);
   const int lim = min((i / n_hw + 1) * n_hw, L);
-  const float* s = S + row * L;
-  T* p = P + row * L;
+  const float* s = S + r * L;
+  T* p = P + r * L;
+  const bool vec = (L & 3) == 0 && (lim & 3) == 0;
   float m = -INFINITY;
-  for (int j = threadIdx.x; j < lim; j += blockDim.x) m = fmaxf(m, s[j]);
+  if (vec) {
+    for (int j = threadIdx.x * 4; j < lim; j += blockDim.x * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(s + j);
+      *reinterpret_cast<float4*>(row + j) = v;
+      m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+  } else {
+    for (int j = threadIdx.x; j < lim; j += blockDim.x) { const float v = s[j]; row[j] = v; m = fmaxf(m, v); }
+  }
   m = block_reduce(m, sh, true);
   float sum = 0.f;
-  for (int j = threadIdx.x; j < lim; j += blockDim.x) sum += expf((s[j] - m) * scale);
+  for (int j = threadIdx.x; j < lim; j += blockDim.x) { const float e = expf((row[j] - m) * scale); row[j] = e; sum += e; }
   sum = block_reduce(sum, sh, false);
   const float inv = 1.f / sum;
-  for (int j = threadIdx.x; j < L; j += blockDim.x)
-    p[j] = from_f<T>(j < lim ? expf((s[j] - m) * scale) * inv : 0.f);
+  if (vec && sizeof(T) == 2) {
+    for (int j = threadIdx.x * 4; j < L; j += blockDim.x * 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < lim) v = *reinterpret_cast<const float4*>(row + j);
+      T o[4] = {from_f<T>(v.x * inv), from_f<T>(v.y * inv), from_f<T>(v.z * inv), from_f<T>(v.w * inv)};
+      *reinterpret_cast<uint2*>(p + j) = *reinterpret_cast<const uint2*>(o);
+    }
+  } else {
+    for (int j = threadIdx.x; j < L; j += blockDim.x) p[j] = from_f<T>(j < lim ? row[j] * inv : 0.f);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -609,8 +629,17 @@ int hyvae_softmax_frame_causal(const float* S, void* P, int32_t p_dtype, int32_t
                                float scale, void* stream) {
   HYVAE_CHECK_ARG(S && P && B > 0 && L > 0 && n_hw > 0 && L % n_hw == 0, "bad softmax arguments (L=%d n_hw=%d)", L, n_hw);
   ProfScope prof(PC_SOFTMAX, (double)B * L * L * (4 + dtype_size(p_dtype)), stream);
-  HYVAE_DISPATCH_DTYPE(p_dtype, T, (softmax_frame_causal_kernel<T><<<(unsigned)((int64_t)B * L), 256, 0, (cudaStream_t)stream>>>(
-      S, (T*)P, L, n_hw, scale)));
+  HYVAE_CHECK_ARG(L <= 48 * 1024, "softmax row of %d floats does not fit the shared-memory staging (max 49152)", L);
+  const size_t smem = (size_t)L * sizeof(float);
+  HYVAE_DISPATCH_DTYPE(p_dtype, T, {
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(softmax_frame_causal_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024 * 4) != cudaSuccess)
+        return fail(HYVAE_ECUDA, "softmax: cannot opt in to 192 KB of shared memory");
+      attr_set = true;
+    }
+    softmax_frame_causal_kernel<T><<<(unsigned)((int64_t)B * L), 256, smem, (cudaStream_t)stream>>>(S, (T*)P, L, n_hw, scale);
+  });
   return check_launch("softmax_frame_causal");
 }
 
