@@ -174,7 +174,7 @@ __device__ __forceinline__ float gn_act(float u) {
 }
 
 template <typename T, bool SILU, bool RLR>
-__global__ void __launch_bounds__(256, 4) gn_apply_kernel(Vol x, Vol y, const double* __restrict__ sums, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256, 3) gn_apply_kernel(Vol x, Vol y, const double* __restrict__ sums, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int groups, float eps, int rows_per_block) {
   extern __shared__ float sh[];  // scale[C], shift[C]
   const int C = x.C, CV = C / 8, b = blockIdx.y;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(Vol x, Vol y, const do
       // blockDim % CV == 0: this thread always lands on the same 8 channels -> scale/shift live in registers.
       // Four 16-byte loads are issued before the first use (the kernel was latency bound with two: ncu showed 42 % of
       // the stall samples on the first consumer of the load at 45 % occupancy).
-      constexpr int U = 4;
+      constexpr int U = 8;
       for (int i = threadIdx.x; i < row_elems; i += U * blockDim.x) {
         Vec8<T> q[U];
 #pragma unroll
