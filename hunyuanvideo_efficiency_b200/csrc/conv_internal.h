@@ -29,4 +29,9 @@ void halo_geometry(int bn, int mt, bool pair, bool thin, int* twh, int* thh, int
 int launch_halo(int dtype, int bn, int mt, bool pair, bool thin, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
                 const CUtensorMap& tmR, const CUtensorMap& tmX, const CUtensorMap& tmW, const HaloArgs& a, cudaStream_t stream);
 
+// conv_stack.cu: stride-1 3x3x3 conv with Cout <= 8 (decoder conv_out), the nine (kh, kw) taps stacked along N.
+// A box {64, 18, 18}; B box {64, 80, 1} over the packed weights viewed as [kt][72][Cin].
+int launch_conv_stack(int dtype, const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloArgs& a, void* y, int64_t ysB, int64_t ysT,
+                      int64_t ysH, int64_t ysW, int64_t yoff, cudaStream_t stream);
+
 }  // namespace hyvae

@@ -779,6 +779,38 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
                     "shortcut input must have y's extent and x's dtype");
     HYVAE_CHECK_ARG(((uintptr_t)sc_x->data & 15) == 0 && ((uintptr_t)sc_w & 15) == 0, "pointers must be 16-byte aligned");
   }
+  // ---- stacked-tap kernel (conv_stack.cu): the decoder's conv_out (Cout stored as 8), variant 7 forces it
+  if ((variant == 7 || (variant == 0 && halo_ok)) && y->C == 8 && x->C % 64 == 0 && residual == nullptr && gn_partials == nullptr && sc_x == nullptr) {
+    HaloArgs h;
+    h.bias = bias; h.B = y->B; h.To = y->T; h.Ho = y->H; h.Wo = y->W; h.Cin = x->C; h.Cout = y->C;
+    h.tiles_h = (y->H + 15) / 16; h.groups_w = (y->W + 15) / 16;
+    h.total = (int64_t)y->B * y->T * h.tiles_h * h.groups_w;
+    h.has_res = 0; h.round_like_ref = 0; h.sc_chunks = h.sc_cin = 0; h.gn_part = nullptr; h.gn_groups = h.gn_cpg = h.gn_rows = 0; h.probe = a.probe;
+    const CUtensorMapDataType dt = x->dtype == HYVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUtensorMap tmA, tmB;
+    {
+      cuuint64_t dims[5] = {(cuuint64_t)x->C, (cuuint64_t)vx.Wp(), (cuuint64_t)vx.Hp(), (cuuint64_t)vx.Tp(), (cuuint64_t)x->B};
+      cuuint64_t strides[4] = {(cuuint64_t)vx.sW * 2, (cuuint64_t)vx.sH * 2, (cuuint64_t)vx.sT * 2, (cuuint64_t)vx.sB * 2};
+      cuuint32_t box[5] = {64, 18, 18, 1, 1};
+      cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+      CUresult r = encode(&tmA, dt, 5, x->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(A stack) failed with %d", (int)r);
+    }
+    {  // packed weights [27][8][Cin] == [kt][(kh,kw,c) = 72][Cin]; rows 72..79 of the box are zero fill
+      cuuint64_t dims[3] = {(cuuint64_t)x->C, 72, 3};
+      cuuint64_t strides[2] = {(cuuint64_t)x->C * 2, (cuuint64_t)x->C * 72 * 2};
+      cuuint32_t box[3] = {64, 80, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = encode(&tmB, dt, 3, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(B stack) failed with %d", (int)r);
+    }
+    char tag[56];
+    snprintf(tag, sizeof(tag), "k3 %d->%d %dx%dx%dx%d s111 stacked taps", x->C, y->C, y->B, y->T, y->H, y->W);
+    ProfScope prof(PC_CONV_TC, 2.0 * (double)y->B * y->T * y->H * y->W * y->C * x->C * 27, stream, tag);
+    return launch_conv_stack(x->dtype, tmA, tmB, h, y->data, vy.sB, vy.sT, vy.sH, vy.sW, vy.at(0, 0, 0, 0), (cudaStream_t)stream);
+  }
   if (variant == 5 || variant == 6 || (variant == 0 && halo_ok)) {  // 5 = force the 1-CTA form, 6 = force the CTA-pair form
     HYVAE_CHECK_ARG(k == 3 && st == 1 && sh == 1 && sw == 1 && y->C <= 128 && y->dtype == x->dtype, "halo kernel: needs k=3, stride 1, Cout <= 128, 16-bit output");
     const int bn = y->C > 64 ? 128 : (y->C > 32 ? 64 : 32), mt = 2;

@@ -212,7 +212,8 @@ def test_tc_cta_pair_kernel_matches_single_cta_kernel(Cin, Cout, T, H, W, stride
     (2, 128, 128, 3, 40, 24, True, 32),    # two 16x16 groups in W (second m-tile of the last group half empty), batch 2
     (2, 64, 128, 2, 21, 19, False, 32),    # ragged H and W, Cin = one chunk
     (1, 256, 128, 3, 32, 48, True, 32),    # four K chunks (decoder 256 -> 128)
-    (1, 128, 8, 3, 40, 40, False, 0),      # conv_out: Cout padded 3 -> 8, BN = 32, three taps per weight stage
+    (1, 128, 8, 3, 40, 40, False, 0),      # conv_out: Cout padded 3 -> 8 (halo kernel BN = 32; auto = stacked-tap kernel)
+    (2, 128, 8, 2, 21, 35, False, 0),      # conv_out, ragged tile edges, batch 2
     (1, 8, 128, 3, 40, 40, False, 32),     # conv_in: Cin padded 3 -> 8, one K = 16 slice per tap
     (1, 64, 64, 3, 32, 32, True, 32),      # BN = 64
     (1, 128, 128, 5, 6, 5, True, 32),      # smaller than one tile
@@ -232,7 +233,12 @@ def test_tc_halo_kernel_matches_oracle_and_single_cta_kernel(B, Cin, Cout, T, H,
         r.t.normal_()
     ys = [N.conv3d_tc(xv, wp, b.to(_dev()), 3, (1, 1, 1), Cout, residual=r, variant=v, gn_groups=gn, round_like_ref=False)
           for v in (5, 2, 5, 0)]
-    assert torch.equal(ys[0].t, ys[2].t) and torch.equal(ys[0].t, ys[3].t)      # reproducible; auto picks the halo kernel
+    assert torch.equal(ys[0].t, ys[2].t)                                        # reproducible
+    if Cout == 8 and Cin % 64 == 0:   # auto = the stacked-tap kernel (conv_stack.cu): other summation order, also reproducible
+        y7 = N.conv3d_tc(xv, wp, b.to(_dev()), 3, (1, 1, 1), Cout, variant=7, round_like_ref=False)
+        assert torch.equal(ys[3].t, y7.t) and O.rel_err(ys[0].t.float().cpu(), ys[3].t.float().cpu()) < 1e-3
+    else:
+        assert torch.equal(ys[0].t, ys[3].t)                                    # auto picks the halo kernel
     if Cout > 64:   # CTA-pair form (cta_group::2, half of the weight tile per CTA): same MMA order, same result
         yp = N.conv3d_tc(xv, wp, b.to(_dev()), 3, (1, 1, 1), Cout, residual=r, variant=6, gn_groups=gn, round_like_ref=False)
         assert torch.equal(ys[0].t, yp.t)

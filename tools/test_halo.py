@@ -13,9 +13,9 @@ def run_case(name, variant, probe):
                                    "c256": (256, 128, 3, 32, 48, True, 32), "thin": (128, 8, 3, 40, 40, False, 0),
                                    "c8": (16, 128, 3, 40, 40, False, 32), "c64": (64, 64, 3, 32, 32, True, 32),
                                    "big": (128, 128, 17, 256, 256, True, 32), "bignr": (128, 128, 17, 256, 256, False, 32),
-                                   "big256": (256, 128, 17, 256, 256, False, 32), "bigthin": (128, 8, 17, 256, 256, False, 0), "bigc8": (16, 128, 17, 256, 256, False, 32), "bigc8ng": (16, 128, 17, 256, 256, False, 0)}[name]
+                                   "big256": (256, 128, 17, 256, 256, False, 32), "bigthin": (128, 8, 17, 256, 256, False, 0), "bigc8": (16, 128, 17, 256, 256, False, 32), "bigc8ng": (16, 128, 17, 256, 256, False, 0), "thinrag": (128, 8, 2, 21, 35, False, 0)}[name]
     torch.manual_seed(0)
-    B = 2 if name in ("small", "rag") else 1
+    B = 2 if name in ("small", "rag", "thinrag") else 1
     x = N.Vol(B, T, H, W, Cin, torch.float16, dev, (2, 1, 1)); x.t.normal_()
     w = (torch.randn(27, Cout, Cin, device=dev) / (27 * Cin) ** 0.5).half()
     b = torch.randn(Cout, device=dev)
@@ -53,7 +53,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         run_case(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]))
     else:
-        cases = [("bigc8", 0, 0), ("bigc8", 0, 4), ("bigc8ng", 0, 0)]
+        cases = [("thin", 0, 0), ("thin", 5, 0), ("thinrag", 0, 0), ("bigthin", 0, 0), ("bigthin", 5, 0)]
         for c in cases:
             p = subprocess.run([sys.executable, __file__, c[0], str(c[1]), str(c[2])], capture_output=True, text=True, timeout=120)
             print((p.stdout.strip() or "(no output)") + ("" if p.returncode == 0 else f"  [rc={p.returncode}] {p.stderr.strip()[-300:]}"), flush=True)
