@@ -48,6 +48,7 @@ _SIGNATURES = {
     "hyvae_groupnorm_apply": [_VP, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _VP, _vp],
     "hyvae_pad_upsample": [_VP, _VP, _i32, _i32, _i32, _vp],
     "hyvae_softmax_frame_causal": [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp],
+    "hyvae_attn_block_causal": [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _f32, _vp],
     "hyvae_avgpool_t": [_VP, _VP, _i32, _i32, _vp],
     "hyvae_interp_t_nearest": [_VP, _VP, _f32, _vp],
     "hyvae_image_postprocess": [_vp, _i32, _vp, _i64, _vp],
@@ -97,7 +98,7 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-PROFILE_CLASSES = ("conv_tc", "conv_direct", "gn_stats", "gn_apply", "pad_upsample", "softmax", "layout", "blend", "temporal")
+PROFILE_CLASSES = ("conv_tc", "conv_direct", "gn_stats", "gn_apply", "pad_upsample", "softmax", "layout", "blend", "temporal", "attn")
 
 
 def profile_begin():
@@ -316,6 +317,18 @@ def softmax_frame_causal(S: torch.Tensor, n_hw: int, scale: float, p_dtype) -> t
     _check(lib().hyvae_softmax_frame_causal(S.data_ptr(), P.data_ptr(), _DT[p_dtype], B, L, n_hw, scale, _stream()),
            "softmax_frame_causal")
     return P
+
+
+def attn_block_causal(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, bv, n_hw: int, scale: float) -> torch.Tensor:
+    """Fused softmax(scale Q K^T + frame-causal mask) V + bv (hyvae_attn_block_causal).  q, k: [L][D]; vt: [D][L].
+    Raises HyvaeUnsupported for shapes the fused kernel does not take."""
+    L, D = q.shape
+    assert k.shape == (L, D) and vt.shape == (D, L) and q.dtype == k.dtype == vt.dtype
+    assert q.is_contiguous() and k.is_contiguous() and vt.is_contiguous()
+    o = torch.empty((L, D), dtype=q.dtype, device=q.device)
+    _check(lib().hyvae_attn_block_causal(q.data_ptr(), k.data_ptr(), vt.data_ptr(), _ptr(bv), o.data_ptr(), _DT[q.dtype],
+                                         L, n_hw, D, scale, _stream()), "attn_block_causal")
+    return o
 
 
 def avgpool_t(x: Vol, k: int, s: int) -> Vol:

@@ -40,7 +40,7 @@ inline int check_launch(const char* what) {
 
 // ---- optional per-kernel-class timing (CUDA events on the launching stream; bench.py's roofline leg) ----
 enum ProfClass { PC_CONV_TC = 0, PC_CONV_DIRECT, PC_GN_STATS, PC_GN_APPLY, PC_PAD_UPSAMPLE, PC_SOFTMAX, PC_LAYOUT, PC_BLEND,
-                 PC_TEMPORAL, PC_COUNT };
+                 PC_TEMPORAL, PC_ATTN, PC_COUNT };
 struct ProfRec { cudaEvent_t a, b; int cls; double work; char tag[56]; };
 extern bool g_prof_on;
 extern double g_prof_exec_flops;  // tensor-core MACs*2 actually issued while profiling (<= algorithmic work: sub-pixel phases)

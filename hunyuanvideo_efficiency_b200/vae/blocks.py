@@ -377,6 +377,14 @@ class Attention(nn.Module):
         self.to_q, self.to_k, self.to_v = _Linear(query_dim, dim_head), _Linear(query_dim, dim_head), _Linear(query_dim, dim_head)
         self.to_out = nn.ModuleList([_Linear(dim_head, query_dim), nn.Identity()])
 
+    @staticmethod
+    def fused_eligible(dtype, L: int, Cn: int) -> bool:
+        """The flash-style tcgen05 kernel takes 16-bit operands, head widths 128/256/512 and L % 8 == 0 (TMA row pitch of
+        V^T); HYVAE_ATTN_UNFUSED=1 forces the GEMM -> softmax -> GEMM schedule (A/B measurements, parity tests)."""
+        if os.environ.get("HYVAE_ATTN_UNFUSED", "0") == "1" or os.environ.get("HYVAE_FORCE_DIRECT", "0") == "1":
+            return False
+        return N.device_supports_tc() and dtype in _16BIT and Cn in (128, 256, 512) and L % 8 == 0
+
     def forward_vol(self, x: Vol) -> Vol:
         B, T, H, W, Cn = x.dims
         L, n_hw = T * H * W, H * W
@@ -392,10 +400,18 @@ class Attention(nn.Module):
             k = _gemm_nt(xb, wk, bk, Cn)
             wv_rows = Vol(1, 1, 1, Cn, Cn, x.dtype, x.device, tensor=wv.reshape(1, 1, 1, Cn, Cn))
             vt = _gemm_nt(wv_rows, xb.t.reshape(L, Cn), None, L)                      # V^T [C][L], bias folded below
-            s = _gemm_nt(q, k.t.reshape(L, Cn), None, L, out_dtype=torch.float32)     # S [L][L] fp32
-            p = N.softmax_frame_causal(s.t.reshape(1, L, L), n_hw, self.scale, x.dtype)
-            pv = Vol(1, 1, 1, L, L, x.dtype, x.device, tensor=p.reshape(1, 1, 1, L, L))
-            o = _gemm_nt(pv, vt.t.reshape(Cn, L), bv, Cn)                             # rows of P sum to 1 => + bv
+            o = None
+            if self.fused_eligible(x.dtype, L, Cn):
+                try:  # one kernel: S and P stay in TMEM / shared memory (attn_fused.cu)
+                    ot = N.attn_block_causal(q.t.reshape(L, Cn), k.t.reshape(L, Cn), vt.t.reshape(Cn, L), bv, n_hw, self.scale)
+                    o = Vol(1, 1, 1, L, Cn, x.dtype, x.device, tensor=ot.reshape(1, 1, 1, L, Cn))
+                except N.HyvaeUnsupported:
+                    o = None
+            if o is None:
+                s = _gemm_nt(q, k.t.reshape(L, Cn), None, L, out_dtype=torch.float32)     # S [L][L] fp32
+                p = N.softmax_frame_causal(s.t.reshape(1, L, L), n_hw, self.scale, x.dtype)
+                pv = Vol(1, 1, 1, L, L, x.dtype, x.device, tensor=p.reshape(1, 1, 1, L, L))
+                o = _gemm_nt(pv, vt.t.reshape(Cn, L), bv, Cn)                             # rows of P sum to 1 => + bv
             res = Vol(1, 1, 1, L, Cn, x.dtype, x.device, tensor=x.t[b].reshape(1, 1, 1, L, Cn)) if self.residual_connection else None
             ob = Vol(1, 1, 1, L, Cn, x.dtype, x.device, tensor=out.t[b].reshape(1, 1, 1, L, Cn))
             _gemm_nt(o, wo, bo, Cn, residual=res, out=ob)

@@ -129,6 +129,17 @@ int hyvae_pad_upsample(const hyvae_vol* x, const hyvae_vol* y, int32_t up_t, int
 int hyvae_softmax_frame_causal(const float* S, void* P, int32_t p_dtype, int32_t B, int32_t L, int32_t n_hw,
                                float scale, void* stream);
 
+/* ---- fused mid-block attention core ------------------------------------------------------------
+ * Replaces, in one tcgen05 kernel, F.scaled_dot_product_attention with the additive frame-causal mask of
+ * prepare_causal_attention_mask (unet_causal_3d_blocks.py:38-46; diffusers Attention call site :661, one head):
+ *   O[i][:] = sum_j softmax_j(scale * Q[i].K[j], j < (i/n_hw+1)*n_hw) * V[j][:] + bv
+ * q, k: [L][D]; vt: V transposed, [D][L]; o: [L][D]; all `dtype` (bf16/f16), fp32 bv[D] (may be NULL; rows of the
+ * softmax sum to 1, so the value projection's bias is added once at the end).  S and P stay in TMEM / shared memory.
+ * Returns HYVAE_EUNSUPPORTED unless D is 128, 256 or 512 and L % 8 == 0: the caller then runs the unfused
+ * GEMM -> hyvae_softmax_frame_causal -> GEMM schedule. */
+int hyvae_attn_block_causal(const void* q, const void* k, const void* vt, const float* bv, void* o, int32_t dtype,
+                            int64_t L, int32_t n_hw, int32_t D, float scale, void* stream);
+
 /* ---- temporal ops of the stride/pool/bucket experiments ---------------------------------------
  * avgpool_t replaces F.pad((0,0,0,0,k-1,0),'replicate')+F.avg_pool3d((k,1,1),(s,1,1)) :665-668,767-772;
  * interp_t replaces F.interpolate(scale_factor=(sc,1,1), mode='nearest') :893-897,906-910
@@ -161,7 +172,7 @@ int hyvae_image_postprocess(const void* src, int32_t src_dtype, float* dst, int6
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------------
  * profile_begin/end bracket a region; while on, every C-ABI call is timed with two CUDA events on its
  * stream.  profile_end synchronises and returns, per kernel class (0 conv_tc, 1 conv_direct, 2 gn_stats,
- * 3 gn_apply, 4 pad_upsample, 5 softmax, 6 layout, 7 blend, 8 temporal), the summed device milliseconds,
+ * 3 gn_apply, 4 pad_upsample, 5 softmax, 6 layout, 7 blend, 8 temporal, 9 attn), the summed device milliseconds,
  * the summed ALGORITHMIC work (flops for convs, bytes for the HBM-bound classes) and the launch count. */
 #define HYVAE_PROFILE_CLASSES 9
 int hyvae_profile_begin(void);

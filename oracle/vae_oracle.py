@@ -86,6 +86,13 @@ def resnet_block(sd: Dict[str, Tensor], p: str, x: Tensor, groups: int) -> Tenso
     return (x + h) / 1.0  # :415, output_scale_factor == 1
 
 
+def sdpa_frame_causal(q: Tensor, k: Tensor, v: Tensor, n_frame: int, n_hw: int, scale: float) -> Tensor:
+    """The F.scaled_dot_product_attention call inside diffusers' AttnProcessor2_0 (call site unet_causal_3d_blocks.py:661)
+    with the additive mask of :38-46, one head: softmax(q k^T * scale + mask) v.  q, k, v: [L][D]."""
+    s = torch.matmul(q, k.transpose(0, 1)) * scale + frame_causal_mask(n_frame, n_hw, q.dtype)
+    return torch.matmul(torch.softmax(s, dim=-1), v)
+
+
 def attention_block(sd: Dict[str, Tensor], p: str, x: Tensor, groups: int) -> Tensor:
     """unet_causal_3d_blocks.py:656-662 + diffusers Attention (one head, head_dim = C)."""
     B, C, T, H, W = x.shape

@@ -99,6 +99,68 @@ def test_softmax_frame_causal():
     assert torch.count_nonzero(P.cpu()[0, 0, hw:]) == 0
 
 
+@pytest.mark.parametrize("T,hw,D,dtype,spread", [
+    (3, 64, 512, torch.float16, False),    # L = 192: tiles cross frame boundaries, ragged last tile
+    (5, 72, 512, torch.bfloat16, False),   # L = 360
+    (9, 288, 512, torch.float16, True),    # the smallest 720p latent tile (9 x 18 x 16); score range forces O rescaling
+    (4, 40, 256, torch.float16, True),
+    (3, 48, 128, torch.bfloat16, False),
+    (2, 1024, 512, torch.float16, False),  # n_hw = 8 key blocks per frame, every tile inside one frame
+])
+def test_attn_fused_matches_oracle(T, hw, D, dtype, spread):
+    """hyvae_attn_block_causal (flash-style tcgen05 kernel) against the oracle's SDPA restatement, evaluated in fp32 on the
+    same 16-bit-rounded q, k, v.  P is rounded to the operand type once: 2^-11 (fp16) / 2^-8 (bf16) relative per term."""
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    L = T * hw
+    g = torch.Generator().manual_seed(7)
+    q = torch.randn(L, D, generator=g)
+    k = torch.randn(L, D, generator=g)
+    v = torch.randn(L, D, generator=g)
+    if spread:  # later key blocks score far higher: the running maximum jumps by more than 2^8 -> lazy rescale path
+        k[128:] *= 6.0
+        k[384:] *= 3.0
+    bv = torch.randn(D, generator=g)
+    q, k, v = q.to(dtype), k.to(dtype), v.to(dtype)
+    ref = O.sdpa_frame_causal(q.float(), k.float(), v.float(), T, hw, D ** -0.5) + bv
+    o = N.attn_block_causal(q.to(_dev()), k.to(_dev()), v.t().contiguous().to(_dev()), bv.to(_dev()), hw, D ** -0.5)
+    err = O.rel_err(ref, o.float().cpu())
+    assert err < (2e-3 if dtype == torch.float16 else 1e-2), err
+    # rows of the first frame must not see any later key: recompute them from the first frame alone
+    ref0 = O.sdpa_frame_causal(q[:hw].float(), k[:hw].float(), v[:hw].float(), 1, hw, D ** -0.5) + bv
+    assert O.rel_err(ref0, o[:hw].float().cpu()) < (2e-3 if dtype == torch.float16 else 1e-2)
+
+
+def test_attn_fused_rejects_unsupported_shapes():
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    q = torch.zeros(90, 64, dtype=torch.float16, device=_dev())
+    with pytest.raises(N.HyvaeUnsupported):
+        N.attn_block_causal(q, q, q.t().contiguous(), None, 30, 0.125)
+
+
+def test_midblock_fused_attention_matches_unfused_schedule(monkeypatch):
+    """The mid block with the fused attention kernel against the GEMM -> softmax -> GEMM schedule of the same build, and
+    both against the oracle evaluated in fp32 on the same parameters."""
+    from hunyuanvideo_efficiency_b200.vae.blocks import UNetMidBlockCausal3D
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    torch.manual_seed(3)
+    mb = UNetMidBlockCausal3D(in_channels=256, temb_channels=None, resnet_groups=32, attention_head_dim=256).half()
+    x = torch.randn(1, 256, 3, 12, 16).half()
+    sd = {k_: v_.float() for k_, v_ in mb.state_dict().items()}
+    ref = O.mid_block(sd, "", x.float(), 32)
+    mbd = mb.to(_dev())
+    y_f = mbd(x.to(_dev())).float().cpu()
+    monkeypatch.setenv("HYVAE_ATTN_UNFUSED", "1")
+    y_u = mbd(x.to(_dev())).float().cpu()
+    assert O.rel_err(ref, y_f) < 5e-3 and O.rel_err(ref, y_u) < 5e-3
+    assert O.rel_err(y_u, y_f) < 2e-3
+
+
 def test_temporal_pool_and_interp():
     N = _N()
     x = torch.randn(1, 16, 7, 4, 5)
