@@ -295,7 +295,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "e2e": None if args.no_e2e else {"value": frames_per_step / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": host_video.numel() * 4, "d2h_bytes_per_step": int(host_out.numel() * 2)},
-            "roofline": {"kernel": "tcgen05 implicit-GEMM CausalConv3d (conv_halo_kernel, conv_tc2_kernel, conv_tc_kernel)",
+            "roofline": {"kernel": "tcgen05 implicit-GEMM CausalConv3d (conv_halo_kernel, conv_tc2_kernel, conv_tc_kernel, conv_stack_kernel)",
                          "bound": "tensor", "achieved": tc_tflops, "peak": peak, "unit": "TFLOP/s", "frac": tc_tflops / peak,
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['_source']}): the kernels run inside a multi-second step under the 1 kW cap",
                          "frac_of_burst_peak": tc_tflops / peaks["bf16_tflops"],
@@ -310,6 +310,12 @@ def run_ours(args):
             "conv_path": {"conv_tflop_per_step_rank0": conv_flops / 1e12,
                           "executed_conv_tflop_per_step_rank0": tc.get("executed", tc["work"]) / args.steps / 1e12,
                           "path_util_vs_sustained_peak": (conv_flops * (world if world > 1 else 1) / 1e12) / (ms_per_step / 1e3) / (peak * world)},
+            "attention": {"kernel": "attn_fused_kernel (flash-style tcgen05: S, P in TMEM / shared memory; frame-causal block skipping)",
+                          "ms_per_step": prof["attn"]["ms"] / args.steps, "launches_per_step": prof["attn"]["launches"] / args.steps,
+                          "dense_tflop_per_step": prof["attn"]["work"] / args.steps / 1e12,
+                          "achieved_dense_tflops": prof["attn"]["work"] / (prof["attn"]["ms"] * 1e9) if prof["attn"]["ms"] > 0 else 0.0,
+                          "note": "SURVEY 8d attn_flops definition (4*L^2*D per call, dense, not halved for causality); the q/k/v/out "
+                                  "projections are k=1 launches of the conv class"},
             "kernel_ms_per_step_rank0": shares,
         }
         if world == 1 and not args.no_cpu_baseline and args.workload == "config4":
