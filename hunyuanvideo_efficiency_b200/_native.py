@@ -49,6 +49,8 @@ _SIGNATURES = {
     "hyvae_pad_upsample": [_VP, _VP, _i32, _i32, _i32, _vp],
     "hyvae_softmax_frame_causal": [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp],
     "hyvae_attn_block_causal": [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _f32, _vp],
+    "hyvae_video_to_frames_u8": [_vp, _i32, C.POINTER(_i64), _i32, _i32, _i32, _i32, _i32, _vp, _vp],
+    "hyvae_frame_metrics_u8": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp],
     "hyvae_avgpool_t": [_VP, _VP, _i32, _i32, _vp],
     "hyvae_interp_t_nearest": [_VP, _VP, _f32, _vp],
     "hyvae_image_postprocess": [_vp, _i32, _vp, _i64, _vp],
@@ -57,7 +59,7 @@ _SIGNATURES = {
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["hyvae_version", "hyvae_last_error", "hyvae_device_supports_tc", "hyvae_launch_count",
                                        "hyvae_groupnorm_workspace_bytes", "hyvae_profile_begin", "hyvae_profile_end", "hyvae_profile_executed_flops",
-                                       "hyvae_conv3d_tc_gn_rows"])
+                                       "hyvae_conv3d_tc_gn_rows", "hyvae_frame_metrics_workspace_bytes"])
 
 _lib = None
 
@@ -79,6 +81,8 @@ def lib():
         l.hyvae_device_supports_tc.restype = C.c_int
         l.hyvae_launch_count.restype = C.c_int64
         l.hyvae_groupnorm_workspace_bytes.restype = C.c_int64
+        l.hyvae_frame_metrics_workspace_bytes.restype = C.c_int64
+        l.hyvae_frame_metrics_workspace_bytes.argtypes = [_i32, _i32, _i32]
         l.hyvae_groupnorm_workspace_bytes.argtypes = [_VP, _i32]
         l.hyvae_profile_executed_flops.restype = C.c_double
         l.hyvae_profile_executed_flops.argtypes = []
@@ -329,6 +333,35 @@ def attn_block_causal(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, bv, n_
     _check(lib().hyvae_attn_block_causal(q.data_ptr(), k.data_ptr(), vt.data_ptr(), _ptr(bv), o.data_ptr(), _DT[q.dtype],
                                          L, n_hw, D, scale, _stream()), "attn_block_causal")
     return o
+
+
+def video_to_frames_u8(video: torch.Tensor, rescale: bool = True) -> torch.Tensor:
+    """(C, T, H, W) or (1, C, T, H, W) float video -> [T][H][W][C] uint8 frames, quantised like save_videos_grid."""
+    if video.ndim == 5:
+        assert video.shape[0] == 1, "one video per call (save_videos_grid tiles a batch into a grid; not needed here)"
+        video = video[0]
+    Cn, T, H, W = video.shape
+    out = torch.empty((T, H, W, Cn), dtype=torch.uint8, device=video.device)
+    st = (_i64 * 4)(*video.stride())
+    _check(lib().hyvae_video_to_frames_u8(video.data_ptr(), _DT[video.dtype], st, Cn, T, H, W, int(rescale), out.data_ptr(), _stream()),
+           "video_to_frames_u8")
+    return out
+
+
+def frame_metrics_u8(a: torch.Tensor, b: torch.Tensor):
+    """Per-frame (ssd int64 [N], min_a, max_a, min_b, max_b int32 [N], ssim float64 [N]) of two [N][H][W][C] uint8 frame stacks."""
+    assert a.shape == b.shape and a.dtype == b.dtype == torch.uint8 and a.is_contiguous() and b.is_contiguous()
+    n, H, W, Cn = a.shape
+    nb = int(lib().hyvae_frame_metrics_workspace_bytes(n, H, W))
+    if nb < 0:
+        raise HyvaeError(f"frame_metrics_u8: frames of {H}x{W} are smaller than the 7x7 SSIM window")
+    ws = torch.empty((nb + 32 * n,), dtype=torch.uint8, device=a.device)
+    raw = torch.empty((n, 8), dtype=torch.int32, device=a.device)
+    ssim = torch.empty((n,), dtype=torch.float64, device=a.device)
+    _check(lib().hyvae_frame_metrics_u8(a.data_ptr(), b.data_ptr(), n, H, W, Cn, raw.data_ptr(), ssim.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), _stream()), "frame_metrics_u8")
+    ssd = raw.view(torch.int64)[:, 0]
+    return ssd, raw[:, 2], raw[:, 3], raw[:, 4], raw[:, 5], ssim
 
 
 def avgpool_t(x: Vol, k: int, s: int) -> Vol:

@@ -233,6 +233,39 @@ class _ConvParamsOnly(nn.Module):
         return self.forward_vol(Vol.from_ncthw(x)).to_ncthw()
 
 
+_TILE_STREAMS = {}
+
+
+def run_tiles(thunks, n_streams: int = 1):
+    """Evaluate independent tile sub-model calls (thunks returning a tensor), optionally dealt round-robin over
+    `n_streams` CUDA streams.  Every conv kernel is a persistent grid with one CTA per SM, so a second stream cannot
+    steal SMs from a running conv; what it does is start the NEXT kernel's CTAs on the SMs that the tail wave of the
+    current one leaves idle (the 17 x 32 x 32 mid-block layers fill only 136 of 148 SMs' worth of tiles), and let the
+    HBM-bound GroupNorm / pad passes of one tile run under the tensor-bound convs of another.  Results do not depend
+    on the interleaving: each kernel's tile schedule is static and the GroupNorm partial buffers are per stream.
+    The first thunk runs alone on the caller's stream: it creates the lazily packed weights the others read."""
+    thunks = list(thunks)
+    if n_streams <= 1 or len(thunks) <= 2 or not torch.cuda.is_available():
+        return [f() for f in thunks]
+    main = torch.cuda.current_stream()
+    dev = torch.cuda.current_device()
+    side = _TILE_STREAMS.setdefault((dev, n_streams), [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)])
+    outs = [thunks[0]()]
+    for st in side:
+        st.wait_stream(main)
+    lanes = [main] + side
+    for k, f in enumerate(thunks[1:]):
+        st = lanes[k % n_streams]
+        with torch.cuda.stream(st):
+            o = f()
+        if st is not main:
+            o.record_stream(main)  # allocated in the side stream's pool, consumed (blend / gather) on the caller's stream
+        outs.append(o)
+    for st in side:
+        main.wait_stream(st)
+    return outs
+
+
 class AutoencoderKLCausal3D(nn.Module):
     """autoencoder_kl_causal_3d.py:53-616 (the parts callers use)."""
 
@@ -271,6 +304,8 @@ class AutoencoderKLCausal3D(nn.Module):
         self.tile_latent_min_size = int(ss / (2 ** (len(block_out_channels) - 1)))
         self.tile_overlap_factor = 0.25
         self.bf16_compute = "fp16"  # see _act_dtype()
+        # sub-model calls of different tiles are independent: run them on this many CUDA streams (run_tiles)
+        self.tile_streams = int(os.environ.get("HYVAE_TILE_STREAMS", "2"))
 
     # ---- diffusers-style config / nn.Module conveniences
     @property
@@ -423,9 +458,10 @@ class AutoencoderKLCausal3D(nn.Module):
 
     # ---- spatial tiling (:362-469)
     def _spatial_tiled(self, x: torch.Tensor, fn, tile: int, stride: int, extent: int, limit: int) -> torch.Tensor:
-        rows = []
-        for i in range(0, x.shape[-2], stride):
-            rows.append([fn(x[:, :, :, i:i + tile, j:j + tile]) for j in range(0, x.shape[-1], stride)])
+        ii, jj = list(range(0, x.shape[-2], stride)), list(range(0, x.shape[-1], stride))
+        outs = run_tiles([(lambda i=i, j=j: fn(x[:, :, :, i:i + tile, j:j + tile])) for i in ii for j in jj],
+                         self.tile_streams if x.is_cuda else 1)
+        rows = [outs[r * len(jj):(r + 1) * len(jj)] for r in range(len(ii))]
         return self._assemble_spatial(rows, extent, limit)
 
     def _assemble_spatial(self, rows, extent: int, limit: int) -> torch.Tensor:

@@ -18,6 +18,8 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
+from .model import run_tiles
+
 
 @dataclass(frozen=True)
 class TileSpec:
@@ -123,12 +125,13 @@ class TileParallelVAE:
             oshape = lambda s: (B, cout, (s.t1 - s.t0 - 1) * r_t + 1, (s.h1 - s.h0) * r_s, (s.w1 - s.w0) * r_s)
         specs = tile_grid(T, H, W, temporal=v.use_temporal_tiling, spatial=v.use_spatial_tiling, min_t=min_t, min_s=min_s, overlap=ov)
         owner = lpt_assign([s.cost for s in specs], self.world)
+        mine_k = [k for k in range(len(specs)) if owner[k] == self.rank]
+        outs = run_tiles([(lambda s=specs[k]: fn(x[:, :, s.t0:s.t1, s.h0:s.h1, s.w0:s.w1]).contiguous()) for k in mine_k],
+                         getattr(v, "tile_streams", 1) if x.is_cuda else 1)
         mine = {}
-        for k, s in enumerate(specs):
-            if owner[k] == self.rank:
-                t = fn(x[:, :, s.t0:s.t1, s.h0:s.h1, s.w0:s.w1])
-                assert tuple(t.shape) == oshape(s), (tuple(t.shape), oshape(s))
-                mine[k] = t.contiguous()
+        for k, t in zip(mine_k, outs):
+            assert tuple(t.shape) == oshape(specs[k]), (tuple(t.shape), oshape(specs[k]))
+            mine[k] = t
         dtype = next(iter(mine.values())).dtype if mine else getattr(v, "dtype", x.dtype)
         tiles = self._exchange(mine, [oshape(s) for s in specs], owner, dtype, x.device, to_all)
         if tiles is None:

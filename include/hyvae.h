@@ -140,6 +140,22 @@ int hyvae_softmax_frame_causal(const float* S, void* P, int32_t p_dtype, int32_t
 int hyvae_attn_block_causal(const void* q, const void* k, const void* vt, const float* bv, void* o, int32_t dtype,
                             int64_t L, int32_t n_hw, int32_t D, float scale, void* stream);
 
+/* ---- reconstruction metrics of the stride/pool/bucket experiments --------------------------------
+ * video_to_frames_u8 replaces save_videos_grid's quantisation (hyvideo/utils/file_utils.py:58-66) for one video:
+ *   src (C, T, H, W) with element strides strides_cthw[4] -> dst frames [T][H][W][C] uint8,
+ *   x = (x+1)/2 if rescale; clamp(0,1); (uint8)(x*255) (truncation), all in fp32.
+ * frame_metrics_u8 replaces compute_psnr / compute_ssim of evaluation/compute_metrics.py:31-41 per frame pair
+ * (a = original, b = reconstruction, both [N][H][W][C] uint8, C <= 4): the integer sum of squared differences and the
+ * value ranges (PSNR, data_range and the constant-frame rule are finished by the caller), and scikit-image's
+ * structural_similarity(win_size=7, uniform window, sample covariance, K1=.01, K2=.03, data_range=max(a)-min(a),
+ * channel_axis=-1) in fp64.  workspace: hyvae_frame_metrics_workspace_bytes(N,H,W) + N*sizeof(hyvae_frame_stats) bytes. */
+typedef struct { uint64_t ssd; int32_t min_a, max_a, min_b, max_b; int32_t pad[2]; } hyvae_frame_stats;
+int hyvae_video_to_frames_u8(const void* src, int32_t dtype, const int64_t* strides_cthw, int32_t C, int32_t T, int32_t H,
+                             int32_t W, int32_t rescale, void* dst, void* stream);
+int64_t hyvae_frame_metrics_workspace_bytes(int32_t N, int32_t H, int32_t W);
+int hyvae_frame_metrics_u8(const void* a, const void* b, int32_t N, int32_t H, int32_t W, int32_t C, void* stats,
+                           double* ssim, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- temporal ops of the stride/pool/bucket experiments ---------------------------------------
  * avgpool_t replaces F.pad((0,0,0,0,k-1,0),'replicate')+F.avg_pool3d((k,1,1),(s,1,1)) :665-668,767-772;
  * interp_t replaces F.interpolate(scale_factor=(sc,1,1), mode='nearest') :893-897,906-910

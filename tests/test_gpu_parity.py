@@ -561,6 +561,22 @@ def test_tc_model_path_matches_direct_path_bf16():
     assert O.rel_err(dec_d.float().cpu(), dec_tc.float().cpu()) < BF16_TOL
 
 
+def test_tile_streams_do_not_change_results():
+    """Tiles dealt over 1, 2 and 3 CUDA streams (run_tiles): bit-identical latents and reconstruction, repeatedly."""
+    cfg = dict(W.SMALL_CONFIG, block_out_channels=[64, 128, 256, 256])
+    m = _build(cfg, torch.bfloat16)
+    m.enable_tiling()
+    x = W.make_video((1, 3, 21, 72, 88)).to(_dev(), torch.bfloat16)
+    outs = []
+    for n in (1, 2, 3, 2):
+        m.tile_streams = n
+        dec, post = m(x, return_dict=False, return_posterior=True)
+        outs.append((dec.clone(), post.mode().clone()))
+    torch.cuda.synchronize()
+    for dec, lat in outs[1:]:
+        assert torch.equal(dec, outs[0][0]) and torch.equal(lat, outs[0][1])
+
+
 def test_full_size_tile_properties_bf16():
     """HY config at one canonical decoder tile shape (BASELINE config 2's unit): linearity-free properties
     that do not need the oracle at full size: determinism, and tiled == untiled when one tile covers the input."""
@@ -604,3 +620,62 @@ def test_clip_driver_on_gpu(tmp_path):
         y = torch.load(os.path.join(out, f"c{i}.pt"))
         ref = m(c[None].to(_dev(), torch.float16), return_dict=False, return_posterior=True)[0].cpu().float()
         assert y.dtype == torch.float32 and torch.equal(y, ref)
+
+
+# ----------------------------------------------------------------------------------------- metrics of the t-ops sweeps
+def test_video_quantisation_matches_save_videos_grid_rule():
+    from oracle import metrics_oracle as MO
+    N = _N()
+    g = torch.Generator().manual_seed(11)
+    v = (torch.rand(3, 4, 21, 35, generator=g) * 2.6 - 1.3)      # values outside [-1, 1] exercise the clamp
+    for dt in (torch.float32, torch.float16, torch.bfloat16):
+        vd = v.to(dt)
+        ref = MO.video_to_frames_u8(vd.float().numpy(), True)
+        out = N.video_to_frames_u8(vd.to(_dev()), True).cpu().numpy()
+        assert (out == ref).all()
+    sl = v[:, 1:, ::2, 3:30]                                       # strided view, no rescale
+    ref = MO.video_to_frames_u8(sl.numpy(), False)
+    assert (N.video_to_frames_u8(sl.to(_dev())[:, :, :, :], False).cpu().numpy() == ref).all()
+    big = v.to(_dev())[:, :, ::2, 3:30]
+    assert (N.video_to_frames_u8(big, True).cpu().numpy() == MO.video_to_frames_u8(big.cpu().numpy(), True)).all()
+
+
+@pytest.mark.parametrize("T,H,W,C", [(3, 37, 53, 3), (2, 240, 432, 3), (2, 7, 7, 3), (2, 16, 40, 1)])
+def test_frame_psnr_ssim_match_oracle(T, H, W, C):
+    from oracle import metrics_oracle as MO
+    from hunyuanvideo_efficiency_b200 import metrics as M
+    rng = __import__("numpy").random.default_rng(T * 1000 + H)
+    a = rng.integers(0, 256, (T, H, W, C), dtype="uint8")
+    b = (a.astype("int64") + rng.integers(-25, 26, a.shape)).clip(0, 255).astype("uint8")
+    b[1] = a[1]                                                    # identical frame: PSNR 100, SSIM 1
+    ps, ss = M.frame_metrics(torch.from_numpy(a).to(_dev()), torch.from_numpy(b).to(_dev()))
+    for i in range(T):
+        assert ps[i] == pytest.approx(MO.psnr_frame(a[i], b[i]), rel=1e-12)
+        assert ss[i] == pytest.approx(MO.ssim_frame(a[i], b[i]), abs=1e-10)
+    flat = a.copy(); flat[0] = 9                                   # constant original frame -> SSIM 1 (compute_metrics.py:39-40)
+    _, ss = M.frame_metrics(torch.from_numpy(flat).to(_dev()), torch.from_numpy(b).to(_dev()))
+    assert ss[0] == 1.0
+    # zip semantics: the shorter stack decides
+    ps2, _ = M.frame_metrics(torch.from_numpy(a).to(_dev()), torch.from_numpy(b[:1]).to(_dev()))
+    assert len(ps2) == 1 and ps2[0] == ps[0]
+
+
+def test_sweep_config_roundtrip_and_scores(tmp_path):
+    """One pool experiment and one stride experiment through sweep.run_config on a small fp16 model: the scores equal the
+    oracle's metrics of (input, our reconstruction), T changes as the hooks dictate, and the module is restored."""
+    from oracle import metrics_oracle as MO
+    from hunyuanvideo_efficiency_b200 import sweep as S
+    m = _build(W.SMALL_CONFIG, torch.float16)
+    x = W.make_video((3, 9, 40, 48))
+    torch.save(x, tmp_path / "clip0.pt")
+    base = S.default_t_ops_config()
+    plain = m(x[None].to(_dev(), torch.float16), return_dict=False)[0].float().cpu()
+    for cfg in (None, S.enumerate_pool_configs(base)[0][1], S.enumerate_stride_configs(base)[0][1]):
+        res = S.run_config(m, cfg, str(tmp_path), ["clip0.pt"], _dev(), torch.float16, save_dir=str(tmp_path / "rec"))
+        rec = torch.load(tmp_path / "rec" / "clip0.pt")
+        ref = MO.compare_videos([(MO.video_to_frames_u8(x.numpy()), MO.video_to_frames_u8(rec[0].numpy()))])
+        assert res["PSNR"] == pytest.approx(ref["PSNR"], rel=1e-9) and res["SSIM"] == pytest.approx(ref["SSIM"], abs=1e-9)
+        if cfg is None:
+            assert torch.equal(rec, plain)
+    after = m(x[None].to(_dev(), torch.float16), return_dict=False)[0].float().cpu()
+    assert torch.equal(after, plain)                                # hooks and strides restored

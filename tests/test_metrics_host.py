@@ -1,0 +1,84 @@
+"""CPU tests of the metric oracle (restated skimage SSIM vs explicit window loops) and of the sweep host logic."""
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import metrics_oracle as MO
+from hunyuanvideo_efficiency_b200 import sweep as S
+
+
+def _frames(seed, shape=(15, 19, 3), noise=12):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 256, shape, dtype=np.uint8)
+    b = np.clip(a.astype(np.int64) + rng.integers(-noise, noise + 1, shape), 0, 255).astype(np.uint8)
+    return a, b
+
+
+def test_ssim_restatement_matches_bruteforce_windows():
+    for seed in range(3):
+        a, b = _frames(seed)
+        assert abs(MO.ssim_frame(a, b) - MO.ssim_frame_bruteforce(a, b)) < 1e-12
+    a, _ = _frames(5)
+    assert MO.ssim_frame(a, a) == pytest.approx(1.0, abs=1e-12)
+    flat = np.full((9, 9, 3), 7, dtype=np.uint8)
+    assert MO.ssim_frame(flat, a[:9, :9]) == 1.0 and MO.ssim_frame(a[:9, :9], flat) == 1.0   # compute_metrics.py:39-40
+
+
+def test_psnr_and_quantisation_rules():
+    a, b = _frames(1)
+    mse = np.mean(((a.astype(np.float64) - b.astype(np.float64)) / 255.0) ** 2)
+    assert MO.psnr_frame(a, b) == pytest.approx(-10 * np.log10(mse), rel=1e-12)
+    assert MO.psnr_frame(a, a) == 100                                                        # :33-34
+    v = np.array([-1.5, -1.0, -0.999, 0.0, 0.5, 0.999, 1.0, 3.0], dtype=np.float32).reshape(1, 1, 1, 8)
+    q = MO.video_to_frames_u8(v)                                                            # (T, H, W, C) = (1, 1, 8, 1)
+    assert q.reshape(-1).tolist() == [0, 0, 0, 127, 191, 254, 255, 255]                      # truncation, not rounding
+    assert MO.video_to_frames_u8(np.float32([[[[0.5]]]]), rescale=False).item() == 127
+
+
+def test_compare_videos_zips_to_the_shorter_video():
+    a, b = _frames(2, (4, 9, 11, 3))
+    full = MO.compare_videos([(a, b)])
+    short = MO.compare_videos([(a, b[:3])])
+    assert short["PSNR"] == pytest.approx(np.mean([MO.psnr_frame(a[i], b[i]) for i in range(3)]))
+    assert full["SSIM"] == pytest.approx(np.mean([MO.ssim_frame(a[i], b[i]) for i in range(4)]))
+
+
+def test_enumerators_follow_the_reference_order_and_counts():
+    base = S.default_t_ops_config()
+    assert len(S.encoder_slots(base)) == 16 and len(S.decoder_slots(base)) == 24
+    pool = S.enumerate_pool_configs(base)
+    assert len(pool) == 384 and pool[0][0] == "exp_1" and pool[-1][0] == "exp_384"
+    # exp_1: encoder (0, 0, before) x decoder (0, 0, before); exp_2 moves the decoder slot first
+    c1, c2, c25 = pool[0][1], pool[1][1], pool[24][1]
+    assert c1["encoder"]["down_blocks"][0]["enable_t_pool_before_block"] == [True, False]
+    assert c1["decoder"]["up_blocks"][0]["enable_t_interp_before_block"] == [True, False, False]
+    assert c2["decoder"]["up_blocks"][0]["enable_t_interp_after_block"] == [True, False, False]
+    assert c25["encoder"]["down_blocks"][0]["enable_t_pool_after_block"] == [True, False]
+    for _, c in pool:
+        n_e = sum(sum(b["enable_t_pool_before_block"]) + sum(b["enable_t_pool_after_block"]) for b in c["encoder"]["down_blocks"])
+        n_d = sum(sum(b["enable_t_interp_before_block"]) + sum(b["enable_t_interp_after_block"]) for b in c["decoder"]["up_blocks"])
+        assert (n_e, n_d) == (1, 1)
+    assert len(S.enumerate_pool_configs(base, max_combos=10)) == 10
+    stride = S.enumerate_stride_configs(base)
+    assert len(stride) == 72
+    assert stride[0][1]["encoder"]["down_blocks"][0]["downsample_stride"] == [2, 2, 2]
+    assert stride[24][1]["encoder"]["down_blocks"][1]["downsample_stride"] == [4, 2, 2]
+    assert stride[48][1]["encoder"]["down_blocks"][2]["downsample_stride"] == [4, 2, 2]
+    assert base["encoder"]["down_blocks"][0]["downsample_stride"] == [1, 2, 2]   # the base is not mutated
+    assert [n for n, _ in S.configs_of_rank(pool[:5], 1, 2)] == ["exp_2", "exp_4"]
+
+
+def test_snapshot_restore_of_t_ops_state(tmp_path):
+    from hunyuanvideo_efficiency_b200.synthetic import SMALL_CONFIG
+    from hunyuanvideo_efficiency_b200.vae import AutoencoderKLCausal3D, _apply_t_ops_config_to_vae
+    m = AutoencoderKLCausal3D.from_config(SMALL_CONFIG)
+    snap = S.snapshot_t_ops(m)
+    cfg = S.enumerate_stride_configs(S.default_t_ops_config())[30][1]
+    _apply_t_ops_config_to_vae(m, cfg)
+    assert m.encoder.down_blocks[1].downsamplers[0].conv.conv.stride == (4, 2, 2)
+    S.restore_t_ops(m, snap)
+    assert m.encoder.down_blocks[1].downsamplers[0].conv.conv.stride == (2, 2, 2)
+    assert all(c is None for c in m.decoder.up_blocks[0].resnet_interp_configs)
+    p = S.write_metrics({"PSNR": 31.5, "SSIM": 0.9}, "in", "out", str(tmp_path / "exp_1"))
+    assert open(p).read().splitlines()[1:5] == ["Root1: in", "Root2: out", "PSNR: 31.5", "SSIM: 0.9"]
