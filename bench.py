@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 METRIC = "vae_encode_decode_frames_per_sec_720p_129f"
 UNIT = "frames/s"
 FRAMES, HEIGHT, WIDTH = 129, 720, 1280
+CPU_SAMPLE_SHAPE = (1, 3, 17, 256, 256)   # bounded sample the CPU arm times (scaled to the workload by conv FLOPs)
 WORKLOAD = "config4: enable_tiling(); encode(1x3x129x720x1280) -> mode() -> decode(); 84+84 sub-model calls"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the committed `ncu --set full`
 # capture (profiles/r01_ncu_conv_halo_pair_128.txt): conv_halo_kernel<half,128,2,pair>, 128 -> 128 channels, 17x256x256
@@ -82,7 +83,8 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------ reference arm
 def cpu_sample(threads: int):
     """One bounded CPU sample of the workload through the oracle port of the reference: fp32 encode+decode of a
-    1x3x9x128x128 clip with the HY config (untiled).  Returns (seconds, conv_flops_of_sample)."""
+    1x3x17x256x256 clip with the HY config (untiled: BASELINE config 1, one canonical tile of the tiled workload; about
+    10-20 s on 16 host threads).  Returns (seconds, conv_flops_of_sample)."""
     import torch
     from oracle import flops as FL
     from oracle import vae_oracle as O
@@ -91,14 +93,14 @@ def cpu_sample(threads: int):
     cfg = W.HY_VAE_CONFIG
     if not hasattr(cpu_sample, "_sd"):
         cpu_sample._sd = W.make_state_dict(cfg)
-    shape = (1, 3, 9, 128, 128)
+    shape = CPU_SAMPLE_SHAPE
     x = W.make_video(shape)
     tl = O.Tiling.from_cfg(cfg)
     t0 = time.perf_counter()
     with torch.no_grad():
         O.forward(cpu_sample._sd, cfg, x, tl)
     dt = time.perf_counter() - t0
-    fe, (t, h, w) = FL.encoder_tile_flops(cfg, 1, 9, 128, 128)
+    fe, (t, h, w) = FL.encoder_tile_flops(cfg, *shape[:1], *shape[2:])
     fd, _ = FL.decoder_tile_flops(cfg, 1, t, h, w)
     return dt, fe + fd
 
@@ -129,7 +131,7 @@ def run_reference(args):
     sec_per_sample = sum(ts) / len(ts)
     sec_full = sec_per_sample * full / fl  # scale the sample to the whole clip by conv FLOPs
     value = FRAMES / sec_full
-    sample = (f"oracle port of the reference, fp32, {threads} host threads: encode+decode of 1x3x9x128x128 (HY config, "
+    sample = (f"oracle port of the reference, fp32, {threads} host threads: encode+decode of {'x'.join(map(str, CPU_SAMPLE_SHAPE))} (HY config, "
               f"{fl / 1e12:.2f} conv TFLOP, {sec_per_sample:.1f} s), scaled to the {full / 1e12:.1f} TFLOP of the full tiled workload")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec_full * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -343,7 +345,7 @@ def run_ours(args):
             full = full_workload_flops()
             line["cpu_baseline"] = {
                 "value": FRAMES / (dt * full / fl), "unit": UNIT, "cores": threads, "kind": "port",
-                "sample": f"oracle port (fp32): encode+decode 1x3x9x128x128, {fl / 1e12:.2f} conv TFLOP in {dt:.1f} s, "
+                "sample": f"oracle port (fp32): encode+decode {'x'.join(map(str, CPU_SAMPLE_SHAPE))}, {fl / 1e12:.2f} conv TFLOP in {dt:.1f} s, "
                           f"scaled by conv FLOPs to the {full / 1e12:.1f} TFLOP workload"}
         print(json.dumps(line), flush=True)
     if world > 1:
