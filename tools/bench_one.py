@@ -34,6 +34,12 @@ elif what == "conv512s":  # mid-block conv at the canonical tile: 512 -> 512, 17
     r = N.Vol(1, 17, 32, 32, 512, torch.float16, dev); r.t.normal_()
     for _ in range(6):
         N.conv3d_tc(x, w, b, 3, (1, 1, 1), 512, residual=r, gn_groups=32)
+elif what == "attn":     # fused mid-block attention at the canonical tile: L = 17 x 32 x 32, D = 512
+    L, D = 17408, 512
+    q = torch.randn(L, D, device=dev).half(); k = torch.randn(L, D, device=dev).half()
+    vt = torch.randn(D, L, device=dev).half(); bv = torch.randn(D, device=dev)
+    for _ in range(4):
+        N.attn_block_causal(q, k, vt, bv, 1024, D ** -0.5)
 else:
     x = N.Vol(1, 17, 256, 256, 128, torch.float16, dev); x.t.normal_()
     g, b = torch.ones(128, device=dev), torch.zeros(128, device=dev)
