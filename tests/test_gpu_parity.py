@@ -132,6 +132,37 @@ def test_attn_fused_matches_oracle(T, hw, D, dtype, spread):
     assert O.rel_err(ref0, o[:hw].float().cpu()) < (2e-3 if dtype == torch.float16 else 1e-2)
 
 
+def test_attn_fused_full_size_matches_unfused_chain_and_is_reproducible():
+    """BASELINE's canonical mid-block shape (L = 17 x 32 x 32, D = 512), too large for the CPU oracle in test time: the
+    fused kernel against the GEMM -> softmax -> GEMM chain of the same library (itself oracle-checked at small sizes),
+    bit-reproducibility, and the causal property (changing later frames' keys / values leaves earlier rows unchanged)."""
+    from hunyuanvideo_efficiency_b200.vae.blocks import _gemm_nt
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    T, hw, D = 17, 1024, 512
+    L = T * hw
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = torch.randn(L, D, device=_dev(), generator=g).half()
+    k = torch.randn(L, D, device=_dev(), generator=g).half()
+    vt = torch.randn(D, L, device=_dev(), generator=g).half()
+    bv = torch.randn(D, device=_dev(), generator=g)
+    o1 = N.attn_block_causal(q, k, vt, bv, hw, D ** -0.5)
+    o2 = N.attn_block_causal(q, k, vt, bv, hw, D ** -0.5)
+    assert torch.equal(o1, o2)
+    qv = N.Vol(1, 1, 1, L, D, torch.float16, _dev(), tensor=q.reshape(1, 1, 1, L, D))
+    s = _gemm_nt(qv, k, None, L, out_dtype=torch.float32)
+    p = N.softmax_frame_causal(s.t.reshape(1, L, L), hw, D ** -0.5, torch.float16)
+    pv = N.Vol(1, 1, 1, L, L, torch.float16, _dev(), tensor=p.reshape(1, 1, 1, L, L))
+    ou = _gemm_nt(pv, vt, bv, D).t.reshape(L, D)
+    assert O.rel_err(ou.float().cpu(), o1.float().cpu()) < 1e-3
+    k2, vt2 = k.clone(), vt.clone()
+    k2[9 * hw:] = 0
+    vt2[:, 9 * hw:] = 1
+    o3 = N.attn_block_causal(q, k2, vt2, bv, hw, D ** -0.5)
+    assert torch.equal(o3[:9 * hw], o1[:9 * hw]) and not torch.equal(o3[9 * hw:], o1[9 * hw:])
+
+
 def test_attn_fused_rejects_unsupported_shapes():
     N = _N()
     if not N.device_supports_tc():
