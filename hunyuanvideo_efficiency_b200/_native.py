@@ -217,6 +217,7 @@ def conv3d_direct(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, resi
     return y
 
 
+VARIANT_TFOLD = 0x100  # hyvae_conv3d_causal_tc: `w` carries the 18 folded first-frame tap slices after the 27 (include/hyvae.h)
 _GN_PART = {}
 
 

@@ -140,24 +140,37 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // steps of a group: (kt, kc) of the 3x3x3 conv, then — fused 1x1x1 conv_shortcut of the resnet block
   // (unet_causal_3d_blocks.py:407-415) — one step per 64-channel chunk of the block input, whose halo stage is read
   // at the centre tap only and multiplied with the shortcut weights into the same accumulator
-  const int steps_main = 3 * kchunks;
-  const int steps_per_group = steps_main + a.sc_chunks;
+  // (first-frame temporal fold: a unit of output frame 0 / 1 has 1 / 2 frame taps instead of 3, see tfold_class)
   // work units: a group of MT m-tiles per CTA; a CTA pair walks two consecutive groups (2u, 2u+1) per unit
   const int64_t unit0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
   const int64_t ustride = PAIR ? (gridDim.x >> 1) : gridDim.x;
   const int64_t units = PAIR ? (a.total + 1) / 2 : a.total;
   auto group_of = [&](int64_t u) -> int64_t { return PAIR ? 2 * u + rank : u; };
+  // fold class of a unit from the output frame(s) of its group(s): 32-bit divisions only — this also runs on the MMA
+  // issuing warp, where decode_group's 64-bit div/mod chain per unit drained the tensor pipe's queue (measured: -3 %)
+  const uint32_t gpf = (uint32_t)(a.tiles_h * a.groups_w);  // groups per output frame
+  auto frame_of = [&](int64_t g) -> int { return (int)(((uint32_t)g / gpf) % (uint32_t)a.To); };
+  auto unit_cls = [&](int64_t u) -> int {
+    if (!a.tfold) return 2;
+    if constexpr (PAIR) {
+      const int64_t g0 = 2 * u, g1 = 2 * u + 1;
+      return tfold_class(1, frame_of(g0), g0 < a.total, frame_of(g1), g1 < a.total);
+    } else {
+      return tfold_class(1, frame_of(u), true, 0, false);
+    }
+  };
 
   if (warp == 0) {
     // ================= TMA producer (warp-uniform loops, one elected lane issues) =================
     int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-    auto issue_A = [&](int64_t u, int step) {
+    auto issue_A = [&](int64_t u, int step, int cls) {
       const HGroup m = decode_group(a, group_of(u), 8 * MT);
+      const int steps_main = (cls + 1) * kchunks;
       const bool sc = step >= steps_main;
       const int kt = step / kchunks, kc = sc ? step - steps_main : step % kchunks;
       // shortcut input: logical (unpadded) coordinates, the 1-voxel rim of the box is never read
       const CUtensorMap* map = sc ? &tmX : &tmA;
-      const int cw = sc ? m.w0 - 1 : m.w0, ch = sc ? m.h0 - 1 : m.h0, ct = sc ? m.t : m.t + kt;
+      const int cw = sc ? m.w0 - 1 : m.w0, ch = sc ? m.h0 - 1 : m.h0, ct = sc ? m.t : m.t + (2 - cls) + kt;
       mbar_wait(aempty + 8 * sa, pa ^ 1);
       if (elect_one()) {
         if constexpr (PAIR) {
@@ -186,12 +199,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       __syncwarp();
       for (int64_t u = unit0; u < units; u += ustride)
-        for (int step = 0; step < 3; ++step) issue_A(u, step);
+        for (int step = 0; step < 3; ++step) issue_A(u, step, 2);
     }
     bool first = true;
     for (int64_t u = unit0; u < units && !THIN; u += ustride) {
+      const int cls = unit_cls(u);
+      const int cls_next = (u + ustride < units) ? unit_cls(u + ustride) : 2;
+      const int steps_main = (cls + 1) * kchunks, steps_per_group = steps_main + a.sc_chunks;
       for (int step = 0; step < steps_per_group; ++step) {
-        if (first) { issue_A(u, step); first = false; }
+        if (first) { issue_A(u, step, cls); first = false; }
         const bool sc = step >= steps_main;
         const int kt = step / kchunks, kc = sc ? step - steps_main : step % kchunks;
         const int ntg = sc ? 1 : 9 / TB;  // weight stages of this step (the shortcut has a single tap; TB == 1 there)
@@ -199,10 +215,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
         for (int tg = 0; tg < ntg; ++tg) {
           if (tg == ntg / 2) {  // prefetch the next A halo while the MMA works through this one
-            if (step + 1 < steps_per_group) issue_A(u, step + 1);
-            else if (u + ustride < units) issue_A(u + ustride, 0);
+            if (step + 1 < steps_per_group) issue_A(u, step + 1, cls);
+            else if (u + ustride < units) issue_A(u + ustride, 0, cls_next);
           }
-          const int wtap = sc ? 0 : kt * 9 + tg * TB;
+          const int wtap = sc ? 0 : tfold_wgroup(cls, kt) * 9 + tg * TB;
           mbar_wait(bempty + 8 * sb, pb ^ 1);
           if (elect_one()) {
             if constexpr (PAIR) {
@@ -263,6 +279,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
+        const int steps_main = (unit_cls(u) + 1) * kchunks, steps_per_group = steps_main + a.sc_chunks;
         for (int step = 0; step < steps_per_group; ++step) {
           mbar_wait(afull + 8 * sa, pa);
           const uint32_t a_stage = sA + sa * Cfg::A_BYTES;

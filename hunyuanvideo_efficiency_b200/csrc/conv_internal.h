@@ -23,6 +23,7 @@ struct HaloArgs {
   double* gn_part;         // optional [B][gn_rows][gn_groups][2]
   int gn_groups, gn_cpg, gn_rows;
   int probe;
+  int tfold;              // weights carry the 18 folded first-frame taps (tfold_* in tcgen05.cuh)
 };
 
 void halo_geometry(int bn, int mt, bool pair, bool thin, int* twh, int* thh, int* taps_per_b, int* brows);

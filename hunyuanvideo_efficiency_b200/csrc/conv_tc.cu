@@ -49,6 +49,7 @@ struct TcArgs {
   // box origin shifted by the phase.  Weight tap index = (kt * nsub + kh) * nkw + kw.
   int nkt, nkw, nsub, ot, oh, ow, a_tx;
   int sc_chunks, sc_cin;  // kh-trick pair kernel: fused 1x1x1 shortcut conv (64-channel chunks / channels of its input)
+  int tfold;              // kh-trick pair kernel, standard 3x3x3 taps: weights carry the folded first-frame taps (tfold_class)
 };
 
 constexpr int TC_THREADS = 192;
@@ -94,6 +95,14 @@ __device__ __forceinline__ MTile decode_mtile(const TcArgs& a, int64_t mt) {
   r.t = (int)(mt % a.To); r.b = (int)(mt / a.To);  // an invalid tile gets b >= B: TMA zero-fills it
   r.h0 = th * a.TH; r.w0 = tw * a.TW;
   return r;
+}
+
+// first-frame fold class (tcgen05.cuh tfold_class) of the m-tile pair (2 mg, 2 mg + 1) of the CTA-pair kernel: 32-bit
+// divisions only, because the MMA-issuing warp evaluates it per tile
+__device__ __forceinline__ int tile_fold_class(const TcArgs& a, int64_t mg) {
+  const uint32_t per_frame = (uint32_t)(a.tiles_h * a.tiles_w);
+  const uint32_t i0 = (uint32_t)(2 * mg), i1 = i0 + 1;
+  return tfold_class(1, (int)((i0 / per_frame) % (uint32_t)a.To), (int64_t)i0 < a.m_tiles, (int)((i1 / per_frame) % (uint32_t)a.To), (int64_t)i1 < a.m_tiles);
 }
 
 // Epilogue of one 128-voxel m-tile x BN channels held by this CTA: TMEM -> registers -> +bias (+residual) ->
@@ -381,18 +390,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int64_t mg = tile / a.n_tiles;
         const int n0 = ((a.probe & 2) ? 0 : nt * BN) + (int)rank * (BN / 2);
         const MTile m = decode_mtile(a, (a.probe & 2) ? (int64_t)rank : mg * 2 + rank);
-        for (int g = 0; g < ngroups; ++g) {
+        int cls = 2;
+        if (KHT && a.tfold) cls = tile_fold_class(a, mg);
+        const int ngroups_t = (KHT && a.tfold) ? (cls + 1) * a.nkw * kchunks : ngroups;
+        const int tshift = (KHT && a.tfold) ? 2 - cls : 0;
+        for (int g = 0; g < ngroups_t; ++g) {
           const int kc = g % kchunks, tg = g / kchunks;
           int kt, kh0, kw;
           if (KHT) { kt = tg / a.nkw; kw = tg % a.nkw; kh0 = 0; }
           else { kt = tg / (a.k * a.k); kh0 = (tg / a.k) % a.k; kw = tg % a.k; }
+          const int wkt = (KHT && a.tfold) ? tfold_wgroup(cls, kt) : kt;
           if (KHT) {
             mbar_wait(aempty_bar + 8 * sa, pa ^ 1);
             const bool skip = (a.probe & 1) && afills >= NA;
             ++afills;
             if (elect_one()) {
               if (leader) { if (skip) mbar_arrive(afull_bar + 8 * sa); else mbar_expect_tx(afull_bar + 8 * sa, 2 * a.a_tx); }
-              if (!skip) tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull_bar + 8 * sa, kc * 64, m.w0 + a.ow + kw, m.h0 + a.oh, m.t + a.ot + kt, m.b);
+              if (!skip) tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull_bar + 8 * sa, kc * 64, m.w0 + a.ow + kw, m.h0 + a.oh, m.t + a.ot + tshift + kt, m.b);
               if (!leader) mbar_arrive_leader(afull_bar + 8 * sa);
             }
             __syncwarp();
@@ -414,7 +428,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tma_load_5d_2sm(sA + sb * Cfg::A_BYTES, &tmA, bfull_bar + 8 * sb, kc * 64,
                                 m.w0 * a.sw + kw, m.h0 * a.sh + kh, m.t * a.st + kt, m.b);
               if (!skipb) tma_load_3d_2sm(sB + sb * Cfg::B_STAGE_BYTES, &tmB, bfull_bar + 8 * sb, kc * 64, n0,
-                                          KHT ? (kt * a.nsub + kh) * a.nkw + kw : (kt * a.k + kh) * a.k + kw);
+                                          KHT ? (wkt * a.nsub + kh) * a.nkw + kw : (kt * a.k + kh) * a.k + kw);
               if (!leader) mbar_arrive_leader(bfull_bar + 8 * sb);
             }
             __syncwarp();
@@ -457,7 +471,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int g = 0; g < ngroups; ++g) {
+        int ngroups_t = ngroups;
+        if (KHT && a.tfold) ngroups_t = (tile_fold_class(a, (int64_t)((uint32_t)tile / (uint32_t)a.n_tiles)) + 1) * a.nkw * kchunks;
+        for (int g = 0; g < ngroups_t; ++g) {
           if (KHT) { mbar_wait(afull_bar + 8 * sa, pa); }
 #pragma unroll
           for (int sub = 0; sub < NSUB; ++sub) {
@@ -767,6 +783,12 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
   { const char* pe = getenv("HYVAE_TC_PROBE"); a.probe = pe ? atoi(pe) : 0; }  // measurement only: results are garbage when set
   a.nkt = a.nkw = a.nsub = 3; a.ot = a.oh = a.ow = 0; a.a_tx = 18 * 1024;
   a.sc_chunks = a.sc_cin = 0;
+  // variant bit 8: `w` holds 45 tap slices, the 27 of the conv followed by the 18 folded first-frame taps (tfold_class);
+  // used by the halo and kh-trick kernels for stride-1 3x3x3 convs, ignored (first 27 slices) by every other kernel
+  const bool w_has_fold = (variant & 0x100) != 0 && k == 3 && st == 1 && sh == 1 && sw == 1;
+  variant &= 0xff;
+  const int w_taps = w_has_fold ? 45 : k * k * k;
+  a.tfold = 0;
 
   // ---- halo kernel (conv_halo.cu): every stride-1 3x3x3 conv with Cout <= 128 and a 16-bit output (variant 5 forces it)
   const bool halo_ok = k == 3 && st == 1 && sh == 1 && sw == 1 && y->C <= 128 && y->dtype == x->dtype &&
@@ -785,7 +807,7 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
     h.bias = bias; h.B = y->B; h.To = y->T; h.Ho = y->H; h.Wo = y->W; h.Cin = x->C; h.Cout = y->C;
     h.tiles_h = (y->H + 15) / 16; h.groups_w = (y->W + 15) / 16;
     h.total = (int64_t)y->B * y->T * h.tiles_h * h.groups_w;
-    h.has_res = 0; h.round_like_ref = 0; h.sc_chunks = h.sc_cin = 0; h.gn_part = nullptr; h.gn_groups = h.gn_cpg = h.gn_rows = 0; h.probe = a.probe;
+    h.has_res = 0; h.round_like_ref = 0; h.sc_chunks = h.sc_cin = 0; h.gn_part = nullptr; h.gn_groups = h.gn_cpg = h.gn_rows = 0; h.probe = a.probe; h.tfold = 0;
     const CUtensorMapDataType dt = x->dtype == HYVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUtensorMap tmA, tmB;
     {
@@ -829,6 +851,7 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
     h.has_res = residual != nullptr; h.round_like_ref = round_like_ref;
     h.sc_cin = sc_x ? sc_x->C : 0; h.sc_chunks = (h.sc_cin + 63) / 64;
     h.gn_part = gn_partials; h.gn_groups = gn_groups; h.gn_cpg = 0; h.gn_rows = num_sms() * 4; h.probe = a.probe;
+    h.tfold = (w_has_fold && !thin) ? 1 : 0;
     if (gn_partials) {
       HYVAE_CHECK_ARG(gn_groups > 0 && y->C % gn_groups == 0, "gn_groups=%d does not divide Cout=%d", gn_groups, y->C);
       h.gn_cpg = y->C / gn_groups;
@@ -846,7 +869,7 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
       if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(A halo) failed with %d", (int)r);
     }
     {
-      cuuint64_t dims[3] = {(cuuint64_t)x->C, (cuuint64_t)y->C, 27};
+      cuuint64_t dims[3] = {(cuuint64_t)x->C, (cuuint64_t)y->C, (cuuint64_t)w_taps};
       cuuint64_t strides[2] = {(cuuint64_t)x->C * 2, (cuuint64_t)x->C * y->C * 2};
       cuuint32_t box[3] = {(cuuint32_t)krow, (cuuint32_t)brows, (cuuint32_t)taps_per_b};
       cuuint32_t estr[3] = {1, 1, 1};
@@ -892,7 +915,9 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
     char tag[56];
     snprintf(tag, sizeof(tag), "k3 %d->%d %dx%dx%dx%d s111 BN%d halo%s%s%s", x->C, y->C, y->B, y->T, y->H, y->W, bn, pair ? "2" : "", sc_x ? "+sc" : "", thin ? " thin" : "");
     const double vox = (double)y->B * y->T * y->H * y->W;
-    ProfScope prof(PC_CONV_TC, 2.0 * vox * y->C * (x->C * 27.0 + (sc_x ? sc_x->C : 0)), stream, tag);
+    const double fold_saved = h.tfold ? 2.0 * (double)y->B * y->H * y->W * y->C * x->C * 27.0 * (y->T >= 2 ? 1.0 : 2.0 / 3.0) : 0.0;
+    const double work = 2.0 * vox * y->C * (x->C * 27.0 + (sc_x ? sc_x->C : 0));
+    ProfScope prof(PC_CONV_TC, work, stream, tag, work - fold_saved);  // executed: frames 0 / 1 run 1 / 2 of their 3 frame taps
     return launch_halo(x->dtype, bn, mt, pair, thin, tmA, tmB, tmY, tmR, tmX, tmW, h, (cudaStream_t)stream);
   }
 
@@ -967,7 +992,7 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
     if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(A) failed with %d", (int)r);
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)x->C, (cuuint64_t)y->C, (cuuint64_t)(k * k * k)};
+    cuuint64_t dims[3] = {(cuuint64_t)x->C, (cuuint64_t)y->C, (cuuint64_t)w_taps};
     cuuint64_t strides[2] = {(cuuint64_t)x->C * 2, (cuuint64_t)x->C * y->C * 2};
     cuuint32_t box[3] = {64, (cuuint32_t)(two_cta ? BN / 2 : BN), 1};
     cuuint32_t estr[3] = {1, 1, 1};
@@ -979,7 +1004,10 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
   char tag[56];
   snprintf(tag, sizeof(tag), "k%d %d->%d %dx%dx%dx%d s%d%d%d BN%d %s%d%s", k, x->C, y->C, y->B, y->T, y->H, y->W, st, sh, sw, BN,
            two_cta ? (kht ? "2ctaK" : "2cta") : "MT", MT, sc_x ? "+sc" : "");
-  ProfScope prof(PC_CONV_TC, 2.0 * (double)y->B * y->T * y->H * y->W * y->C * ((double)x->C * k * k * k + (sc_x ? sc_x->C : 0)), stream, tag);
+  a.tfold = (w_has_fold && two_cta && kht) ? 1 : 0;
+  const double work = 2.0 * (double)y->B * y->T * y->H * y->W * y->C * ((double)x->C * k * k * k + (sc_x ? sc_x->C : 0));
+  const double fold_saved = a.tfold ? 2.0 * (double)y->B * y->H * y->W * y->C * x->C * 27.0 * (y->T >= 2 ? 1.0 : 2.0 / 3.0) : 0.0;
+  ProfScope prof(PC_CONV_TC, work, stream, tag, work - fold_saved);
   const CUtensorMap* pX = sc_x ? &tmX : nullptr;
   const CUtensorMap* pW = sc_x ? &tmW : nullptr;
 #define HYVAE_TC_LAUNCH(T, OT)                                                                              \
@@ -1052,6 +1080,7 @@ extern "C" int hyvae_conv3d_upphase_tc(const hyvae_vol* x, const void* w, const 
   { const char* pe = getenv("HYVAE_TC_PROBE"); a.probe = pe ? atoi(pe) : 0; }
   a.nkt = nkt; a.nkw = 2; a.nsub = 2; a.ot = (up_t == 2 && pt == 1) ? 1 : 0; a.oh = ph; a.ow = pw; a.a_tx = 17 * 1024;
   a.sc_chunks = a.sc_cin = 0;
+  a.tfold = 0;
   a.TH = 16; a.TW = 8;
   a.tiles_h = (x->H + 15) / 16; a.tiles_w = (x->W + 7) / 8;
   const int BN = y->C > 128 ? 256 : (y->C > 64 ? 128 : 64);

@@ -578,7 +578,9 @@ int hyvae_groupnorm_apply(const hyvae_vol* x, const double* sums, const float* g
   HYVAE_CHECK_ARG(x->B == y->B && x->T == y->T && x->H == y->H && x->W == y->W && x->C == y->C, "shape mismatch");
   HYVAE_CHECK_ARG(groups > 0 && x->C % groups == 0 && x->C % 8 == 0, "bad C=%d / groups=%d", x->C, groups);
   Vol vx = make_vol(x), vy = make_vol(y);
-  ProfScope prof(PC_GN_APPLY, 2.0 * x->B * x->T * x->H * x->W * x->C * dtype_size(x->dtype), stream);
+  char tag[56];
+  snprintf(tag, sizeof(tag), "gn C%d %dx%dx%dx%d pad%d%d%d", x->C, x->B, x->T, x->H, x->W, y->pt, y->ph, y->pw);
+  ProfScope prof(PC_GN_APPLY, 2.0 * x->B * x->T * x->H * x->W * x->C * dtype_size(x->dtype), stream, tag);
   // rows of Wp*C contiguous elements; give each block >= ~64 KB of output, and keep >= ~8 blocks per SM when possible
   const int nrows = vy.Tp() * vy.Hp();
   const int64_t row_bytes = (int64_t)vy.Wp() * x->C * dtype_size(x->dtype);

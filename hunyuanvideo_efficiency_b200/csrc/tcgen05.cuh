@@ -301,6 +301,22 @@ __device__ __forceinline__ void epi_load_bias(const float* bias, int n0, int Cou
     default: epi_tile<T, BN, 32>(__VA_ARGS__); break;                  \
   }
 
+// ---------------------------------------------------------------------------------- first-frame temporal fold
+// A stride-1 causal conv pads TWO copies of frame 0 in front (unet_causal_3d_blocks.py:68,74), so output frame 0 sees the
+// same frame under all three kt taps and output frame 1 sees frame 0 under kt = 0 and 1.  With the packed weights extended
+// by two folded tap groups ([27..35] = W[kt=0]+W[1]+W[2], [36..44] = W[0]+W[1], summed in fp32 and rounded once) a tile of
+// output frame 0 needs ONE frame tap and a tile of frame 1 needs TWO: 1/T of the layer's MACs and operand loads are
+// never issued (2-11 % at T = 65 ... 9).  Class of a tile = min(t, 2); class 2 is the plain 3-tap schedule, which is also
+// valid for frames 0 and 1 (the halo holds the replicated frames) and is what a CTA pair runs when its two tiles differ.
+__device__ __forceinline__ int tfold_class(int tfold, int t0, bool v0, int t1, bool v1) {
+  if (!tfold) return 2;
+  const int c0 = t0 < 2 ? t0 : 2, c1 = t1 < 2 ? t1 : 2;
+  if (v0 && v1) return c0 == c1 ? c0 : 2;
+  return v0 ? c0 : (v1 ? c1 : 2);
+}
+// weight tap group (x 9 taps) of folded frame tap ktp, and the padded input frame it reads relative to t: t + (2 - cls) + ktp
+__device__ __forceinline__ int tfold_wgroup(int cls, int ktp) { return cls == 2 ? ktp : (cls == 1 ? (ktp == 0 ? 4 : 2) : 3); }
+
 // ---------------------------------------------------------------------------------- CTA-pair (cta_group::2) forms
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {

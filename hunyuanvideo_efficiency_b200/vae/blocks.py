@@ -69,20 +69,26 @@ class _Conv3dParams(nn.Module):
             return 16
         return -(-ci // 8) * 8
 
-    def packed(self, dtype, pad8: bool = False):
+    def packed(self, dtype, pad8: bool = False, tfold: bool = False):
         """[taps][Cout][Cin] weights in the activation dtype + fp32 bias (kernel layout), cached.  pad8 zero-pads
-        Cout up to a multiple of 8 and Cin up to cin_padded() (16-byte rows) for the tensor-core kernel."""
+        Cout up to a multiple of 8 and Cin up to cin_padded() (16-byte rows) for the tensor-core kernel.  tfold (3x3x3 only)
+        appends the 18 folded first-frame tap slices the halo / kh-trick kernels use for output frames 0 and 1 (csrc/tcgen05.cuh
+        tfold_class): [27..35] = W[kt=0] + W[1] + W[2], [36..44] = W[0] + W[1], summed in fp32 and rounded once."""
         w = self.weight
         key = (w._version, w.data_ptr(), dtype, w.device, None if self.bias is None else self.bias._version, pad8,
-               tuple(int(v) for v in self.stride))
+               tuple(int(v) for v in self.stride), tfold)
         if self._packed is None or self._packed[0] != key:
             k = self.kernel_size[0]
             co, ci = self.out_channels, self.in_channels
-            pw = w.detach().permute(2, 3, 4, 0, 1).reshape(k * k * k, co, ci).to(dtype)
+            w32 = w.detach().float().permute(2, 3, 4, 0, 1)                      # [kt][kh][kw][Cout][Cin]
+            if tfold:
+                assert k == 3
+                w32 = torch.cat([w32, w32.sum(0, keepdim=True), w32[0:1] + w32[1:2]], 0)
+            pw = w32.reshape(-1, co, ci).to(dtype)
             pb = None if self.bias is None else self.bias.detach().float()
             if pad8 and (co % 8 or ci != self.cin_padded()):
                 cop, cip = -(-co // 8) * 8, self.cin_padded()
-                full = torch.zeros((k * k * k, cop, cip), dtype=dtype, device=w.device)
+                full = torch.zeros((pw.shape[0], cop, cip), dtype=dtype, device=w.device)
                 full[:, :co, :ci] = pw
                 pw = full
                 if pb is not None:
@@ -153,11 +159,15 @@ class CausalConv3d(nn.Module):
         k, stride = c.kernel_size[0], tuple(int(s) for s in c.stride)
         rl = False  # one rounding per stored tensor: conv + bias + residual are summed in fp32, then stored
         if tc_eligible(x.dtype, c.in_channels, c.out_channels, stride, k):
-            w, b = c.packed(x.dtype, pad8=True)
+            # first-frame temporal fold: fp16 operands only (like the sub-pixel phases, the folded sums need fp16's mantissa)
+            tfold = (k == 3 and stride == (1, 1, 1) and x.dtype == torch.float16 and out_dtype in (None, torch.float16)
+                     and os.environ.get("HYVAE_TFOLD", "1") == "1")
+            w, b = c.packed(x.dtype, pad8=True, tfold=tfold)
             cin_p, cout_p = w.shape[2], w.shape[1]
             if x.pad != self.halo or up != (1, 1, 1) or x.C != cin_p:
                 x = N.pad_upsample(x, up, self.halo, channels=cin_p)
-            y = N.conv3d_tc(x, w, b, k, stride, cout_p, residual, out_dtype, rl, gn_groups=self.emit_gn_groups)
+            y = N.conv3d_tc(x, w, b, k, stride, cout_p, residual, out_dtype, rl, gn_groups=self.emit_gn_groups,
+                            variant=N.VARIANT_TFOLD if tfold else 0)
             y.c_valid = c.out_channels
             return y
         w, b = c.packed(x.dtype)

@@ -68,7 +68,11 @@ int hyvae_vol_to_ncthw(const hyvae_vol* src, void* dst, int32_t dst_dtype, int32
  * _direct: CUDA-core implicit GEMM, any shape/dtype; replicate padding by index clamping.
  * _tc:     tcgen05/TMEM implicit GEMM fed by TMA; needs bf16/f16, up_*==1 and
  *          x carrying the halo (pt,ph,pw) = (k-1,k/2,k/2).  Cin%8==0 and Cout%8==0 suffice (TMA zero-fills the
- *          rest); gn_partials != NULL additionally emits GroupNorm partial statistics of y from the epilogue. */
+ *          rest); gn_partials != NULL additionally emits GroupNorm partial statistics of y from the epilogue.
+ *          variant: 0 = automatic kernel choice (low byte 1..7 force a kernel, tests only).  Bit 8 (0x100), stride-1
+ *          3x3x3 only: `w` holds 45 tap slices — the 27 above, then W[kt=0]+W[1]+W[2] (9 slices, (kh,kw) order) and
+ *          W[0]+W[1] (9 slices).  Output frames 0 and 1 read frame 0 under three / two of their frame taps (causal
+ *          replicate padding :68,74), so the kernels that support it run them with one / two folded taps: 1/T fewer MACs. */
 int hyvae_conv3d_causal_direct(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
                                const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
                                int32_t up_t, int32_t up_h, int32_t up_w, int32_t round_like_ref, void* stream);

@@ -383,6 +383,43 @@ def test_tc_upsample_phase_decomposition_matches_reference(B, Cin, Cout, T, H, W
     assert torch.allclose(y.gn_sums[:, :, 1].cpu() / n, (g_ref ** 2).mean(-1), rtol=3e-3)
 
 
+@pytest.mark.parametrize("Cin,Cout,T,H,W,variant", [
+    (128, 128, 5, 32, 32, 5),     # halo kernel, 1 CTA
+    (128, 128, 4, 24, 40, 6),     # halo kernel, CTA pair; 6 groups per frame
+    (64, 128, 3, 16, 40, 6),      # CTA pair with 3 groups per frame: pairs straddle frames 0/1 and 1/2 -> unfolded for those
+    (128, 64, 2, 20, 28, 5),      # BN = 64: three taps per weight stage
+    (256, 256, 5, 32, 32, 4),     # kh-trick pair kernel
+    (128, 512, 3, 16, 24, 4),     # kh-trick, 3 m-tiles per frame (odd): straddling pairs
+    (256, 256, 1, 16, 16, 4),     # a single frame: every tile is class 0
+])
+def test_tc_first_frame_temporal_fold_matches_unfolded(Cin, Cout, T, H, W, variant):
+    """Folded first-frame taps (variant bit 8, 45 weight slices) against the plain 27-tap schedule of the same kernel and
+    against the fp32 reference conv: frames >= 2 are bit-identical, frames 0 and 1 agree to fp16 rounding of the folded
+    weights, residual and GroupNorm statistics included."""
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    from hunyuanvideo_efficiency_b200.vae.blocks import CausalConv3d
+    torch.manual_seed(Cin + T)
+    conv = CausalConv3d(Cin, Cout, 3).to(_dev())
+    x = torch.randn(1, Cin, T, H, W)
+    r = torch.randn(1, Cout, T, H, W)
+    xv, rv = _vol(x, torch.float16, pad=(2, 1, 1)), _vol(r, torch.float16)
+    w27, b = conv.conv.packed(torch.float16, pad8=True)
+    w27 = w27.clone()
+    w45, _ = conv.conv.packed(torch.float16, pad8=True, tfold=True)
+    assert w45.shape[0] == 45 and torch.equal(w45[:27], w27)
+    y0 = N.conv3d_tc(xv, w27, b, 3, (1, 1, 1), Cout, residual=rv, gn_groups=32, variant=variant)
+    y1 = N.conv3d_tc(xv, w45, b, 3, (1, 1, 1), Cout, residual=rv, gn_groups=32, variant=variant | N.VARIANT_TFOLD)
+    a0, a1 = y0.to_ncthw().float().cpu(), y1.to_ncthw().float().cpu()
+    assert torch.equal(a0[:, :, 2:], a1[:, :, 2:])
+    ref = torch.nn.functional.conv3d(torch.nn.functional.pad(x.half().float(), (1, 1, 1, 1, 2, 0), mode="replicate"),
+                                     conv.conv.weight.detach().half().float().cpu(), conv.conv.bias.detach().float().cpu()) + r.half().float()
+    assert O.rel_err(ref, a0) < 2e-3 and O.rel_err(ref, a1) < 2e-3
+    assert O.rel_err(a0[:, :, :2], a1[:, :, :2]) < 2e-3
+    assert torch.allclose(y0.gn_sums, y1.gn_sums, rtol=2e-3, atol=1.0)
+
+
 def test_tc_gemm_k1_residual_and_fp16():
     N = _N()
     if not N.device_supports_tc():
