@@ -41,7 +41,7 @@ _SIGNATURES = {
     "hyvae_vol_to_ncthw": [_VP, _vp, _i32, _i32, _vp],
     "hyvae_conv3d_causal_direct": [_VP, _vp, _vp, _VP, _VP, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "hyvae_conv3d_causal_tc": [_VP, _vp, _vp, _VP, _VP, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
-    "hyvae_conv3d_causal_tc_shortcut": [_VP, _vp, _vp, _VP, _vp, _VP, _vp, _i32, _vp],
+    "hyvae_conv3d_causal_tc_shortcut": [_VP, _vp, _vp, _VP, _vp, _VP, _vp, _i32, _i32, _vp],
     "hyvae_conv3d_upphase_tc": [_VP, _vp, _vp, _VP, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "hyvae_groupnorm_finalize": [_vp, _i32, _i64, _i32, _vp, _vp],
     "hyvae_groupnorm_stats": [_VP, _i32, _vp, _vp, _i64, _vp],
@@ -252,7 +252,8 @@ def conv3d_tc(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, residual
     return y
 
 
-def conv3d_tc_shortcut(x: Vol, w: torch.Tensor, bias: torch.Tensor, sc_x: Vol, sc_w: torch.Tensor, cout: int, gn_groups: int = 0) -> Vol:
+def conv3d_tc_shortcut(x: Vol, w: torch.Tensor, bias: torch.Tensor, sc_x: Vol, sc_w: torch.Tensor, cout: int, gn_groups: int = 0,
+                       tfold: bool = False) -> Vol:
     """y = conv3x3x3(x) + conv1x1x1(sc_x) + bias in one launch (the resnet block's conv2 with its conv_shortcut)."""
     y = Vol(x.B, x.T, x.H, x.W, cout, x.dtype, x.device)
     part, rows = None, 0
@@ -260,7 +261,7 @@ def conv3d_tc_shortcut(x: Vol, w: torch.Tensor, bias: torch.Tensor, sc_x: Vol, s
         rows = int(lib().hyvae_conv3d_tc_gn_rows())
         part = _gn_partials(x.B, rows, gn_groups, x.device)
     _check(lib().hyvae_conv3d_causal_tc_shortcut(x.ref(), w.data_ptr(), _ptr(bias), sc_x.ref(), sc_w.data_ptr(), y.ref(),
-                                                 _ptr(part), gn_groups if part is not None else 0, _stream()),
+                                                 _ptr(part), gn_groups if part is not None else 0, int(tfold), _stream()),
            "conv3d_causal_tc_shortcut")
     if part is not None:
         sums = torch.empty((x.B, gn_groups, 2), dtype=torch.float64, device=x.device)

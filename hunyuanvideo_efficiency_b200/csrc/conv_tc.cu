@@ -740,10 +740,10 @@ extern "C" int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const f
 // chunks of the same accumulator, so its output tensor is never written or re-read.
 extern "C" int hyvae_conv3d_causal_tc_shortcut(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* sc_x,
                                                const void* sc_w, const hyvae_vol* y, double* gn_partials, int32_t gn_groups,
-                                               void* stream) {
+                                               int32_t w_has_fold, void* stream) {
   if (int e = check_vol(sc_x, "sc_x")) return e;
   HYVAE_CHECK_ARG(sc_w != nullptr, "sc_w is null");
-  return conv_tc_entry(x, w, bias, nullptr, y, 3, 1, 1, 1, 0, 0, gn_partials, gn_groups, sc_x, sc_w, stream);
+  return conv_tc_entry(x, w, bias, nullptr, y, 3, 1, 1, 1, 0, w_has_fold ? 0x100 : 0, gn_partials, gn_groups, sc_x, sc_w, stream);
 }
 
 static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,

@@ -326,13 +326,14 @@ class ResnetBlockCausal3D(nn.Module):
 
     def _conv2_with_shortcut(self, h: Vol, x: Vol) -> Vol:
         c2, cs = self.conv2.conv, self.conv_shortcut.conv
-        w2, b2 = c2.packed(h.dtype, pad8=True)
+        tfold = h.dtype == torch.float16 and os.environ.get("HYVAE_TFOLD", "1") == "1"   # as in CausalConv3d.forward_vol
+        w2, b2 = c2.packed(h.dtype, pad8=True, tfold=tfold)
         ws, bs = cs.packed(h.dtype, pad8=True)
         key = (c2.bias._version, cs.bias._version, b2.data_ptr(), bs.data_ptr())
         if getattr(self, "_bias_sum", None) is None or self._bias_sum[0] != key:
             self._bias_sum = (key, (b2 + bs).contiguous())
         try:
-            return N.conv3d_tc_shortcut(h, w2, self._bias_sum[1], x, ws, c2.out_channels, gn_groups=self.conv2.emit_gn_groups)
+            return N.conv3d_tc_shortcut(h, w2, self._bias_sum[1], x, ws, c2.out_channels, gn_groups=self.conv2.emit_gn_groups, tfold=tfold)
         except N.HyvaeUnsupported:   # tile shape the fused kernels do not take: run the shortcut as its own k=1 conv
             return self.conv2.forward_vol(h, residual=self.conv_shortcut.forward_vol(x))
 

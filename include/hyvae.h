@@ -86,7 +86,7 @@ int hyvae_conv3d_causal_tc(const hyvae_vol* x, const void* w, const float* bias,
  * not take return HYVAE_EUNSUPPORTED and the caller runs the shortcut as its own k=1 conv feeding `residual`. */
 int hyvae_conv3d_causal_tc_shortcut(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* sc_x,
                                     const void* sc_w, const hyvae_vol* y, double* gn_partials, int32_t gn_groups,
-                                    void* stream);
+                                    int32_t w_has_fold /* 1: w holds the 45 slices of variant bit 8 above */, void* stream);
 /* One output-parity phase of UpsampleCausal3D.forward (nearest x2 + 3x3x3 CausalConv3d, unet_causal_3d_blocks.py:
  * 152-175) computed directly from the LOW-resolution volume: the 27 high-res taps collapse onto nkt x 2 x 2 low-res taps
  * (nkt = 2 if up_t == 2, else 3) whose weights are sums of the original ones.

@@ -14,6 +14,10 @@ if what in CASES:
     Cin, Cout, T, H, W, res, variant = CASES[what]
     x = N.Vol(1, T, H, W, Cin, torch.float16, dev, (2, 1, 1)); x.t.normal_()
     w = (torch.randn(27, Cout, Cin, device=dev) / (27 * Cin) ** 0.5).half()
+    if variant == 0 and Cout >= 64:   # as the model path does: 18 folded first-frame tap slices appended (variant bit 8)
+        w32 = w.float()
+        w = torch.cat([w32, w32[0:9] + w32[9:18] + w32[18:27], w32[0:9] + w32[9:18]]).half().contiguous()
+        variant = N.VARIANT_TFOLD
     b = torch.randn(Cout, device=dev)
     y = N.Vol(1, T, H, W, Cout, torch.float16, dev)
     r = None
