@@ -38,6 +38,7 @@ _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 # name -> argtypes; every entry returns int status (include/hyvae.h)
 _SIGNATURES = {
     "hyvae_ncthw_to_vol": [_vp, _i32, _i32, C.POINTER(_i64), _VP, _vp],
+    "hyvae_ncthw_to_vol_kw3": [_vp, _i32, _i32, C.POINTER(_i64), _VP, _vp],
     "hyvae_vol_to_ncthw": [_VP, _vp, _i32, _i32, _vp],
     "hyvae_conv3d_causal_direct": [_VP, _vp, _vp, _VP, _VP, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "hyvae_conv3d_causal_tc": [_VP, _vp, _vp, _VP, _VP, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
@@ -138,7 +139,7 @@ def device_supports_tc() -> bool:
 class Vol:
     """Channels-last activation volume [B][T+pt][H+2ph][W+2pw][C] in HBM (see hyvae_vol)."""
 
-    __slots__ = ("t", "B", "T", "H", "W", "C", "pad", "_c", "c_valid", "gn_sums", "gn_groups")
+    __slots__ = ("t", "B", "T", "H", "W", "C", "pad", "_c", "c_valid", "gn_sums", "gn_groups", "kw_packed")
 
     def __init__(self, B, T, H, W, Cn, dtype, device, pad: Tuple[int, int, int] = (0, 0, 0), tensor=None):
         pt, ph, pw = pad
@@ -154,6 +155,7 @@ class Vol:
         self.c_valid = Cn        # channels that carry data (C may be zero-padded up to a multiple of 8)
         self.gn_sums = None      # [B][groups][2] fp64 GroupNorm statistics emitted by the producing conv, if any
         self.gn_groups = 0
+        self.kw_packed = False   # channels are (kw, c) of a thin source (from_ncthw(kw_pack=True)): only conv_in reads such a volume
 
     @property
     def dtype(self):
@@ -180,14 +182,19 @@ class Vol:
 
     # ---- NCTHW <-> volume -------------------------------------------------------------------
     @staticmethod
-    def from_ncthw(x: torch.Tensor, dtype=None, pad=(0, 0, 0), channels: Optional[int] = None) -> "Vol":
-        """`channels` > x.shape[1] zero-pads the channel axis (3 -> 8 for the tensor-core conv_in)."""
+    def from_ncthw(x: torch.Tensor, dtype=None, pad=(0, 0, 0), channels: Optional[int] = None, kw_pack: bool = False) -> "Vol":
+        """`channels` > x.shape[1] zero-pads the channel axis (3 -> 8 for the tensor-core conv_in).  kw_pack: channel
+        kw * C + c of a voxel holds source channel c of its (w + kw - 1) neighbour (hyvae_ncthw_to_vol_kw3)."""
         assert x.ndim == 5
         B, Cn, T, H, W = x.shape
         v = Vol(B, T, H, W, channels or Cn, dtype or x.dtype, x.device, pad)
         v.c_valid = Cn
         strides = (_i64 * 5)(*x.stride())
-        _check(lib().hyvae_ncthw_to_vol(x.data_ptr(), _DT[x.dtype], Cn, strides, v.ref(), _stream()), "ncthw_to_vol")
+        if kw_pack:
+            _check(lib().hyvae_ncthw_to_vol_kw3(x.data_ptr(), _DT[x.dtype], Cn, strides, v.ref(), _stream()), "ncthw_to_vol_kw3")
+            v.kw_packed = True
+        else:
+            _check(lib().hyvae_ncthw_to_vol(x.data_ptr(), _DT[x.dtype], Cn, strides, v.ref(), _stream()), "ncthw_to_vol")
         return v
 
     def to_ncthw(self, dtype=None) -> torch.Tensor:
@@ -217,6 +224,7 @@ def conv3d_direct(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, resi
     return y
 
 
+VARIANT_KWPACK = 0x200  # hyvae_conv3d_causal_tc: x is a kw-packed thin volume (Vol.from_ncthw(kw_pack=True)), w is [9][Cout][16]
 VARIANT_TFOLD = 0x100  # hyvae_conv3d_causal_tc: `w` carries the 18 folded first-frame tap slices after the 27 (include/hyvae.h)
 _GN_PART = {}
 

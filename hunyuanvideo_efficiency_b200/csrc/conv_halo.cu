@@ -257,13 +257,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_stage = sA + sa * Cfg::A_BYTES;
+            if (a.kwpack) {  // the kw taps ride along the channel axis: three (kh) MMAs per frame tap, centre column
 #pragma unroll
-            for (int tap9 = 0; tap9 < 9; ++tap9) {
-              const int kh = tap9 / 3, kw = tap9 - 3 * kh;
-              const uint64_t bdesc = make_sw32_desc(sB + (uint32_t)((kt * 9 + tap9) * Cfg::B_TAP_BYTES), 256);
+              for (int kh = 0; kh < 3; ++kh) {
+                const uint64_t bdesc = make_sw32_desc(sB + (uint32_t)((kt * 3 + kh) * Cfg::B_TAP_BYTES), 256);
 #pragma unroll
-              for (int i = 0; i < MT; ++i)
-                mma(d_tmem + i * BN, make_sw32_desc(a_stage + (uint32_t)((kh * PITCH + kw + 8 * i) * 32), PITCH * 32), bdesc, (kt | tap9) != 0);
+                for (int i = 0; i < MT; ++i)
+                  mma(d_tmem + i * BN, make_sw32_desc(a_stage + (uint32_t)((kh * PITCH + 1 + 8 * i) * 32), PITCH * 32), bdesc, (kt | kh) != 0);
+              }
+            } else {
+#pragma unroll
+              for (int tap9 = 0; tap9 < 9; ++tap9) {
+                const int kh = tap9 / 3, kw = tap9 - 3 * kh;
+                const uint64_t bdesc = make_sw32_desc(sB + (uint32_t)((kt * 9 + tap9) * Cfg::B_TAP_BYTES), 256);
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+                  mma(d_tmem + i * BN, make_sw32_desc(a_stage + (uint32_t)((kh * PITCH + kw + 8 * i) * 32), PITCH * 32), bdesc, (kt | tap9) != 0);
+              }
             }
             commit(aempty + 8 * sa);
           }

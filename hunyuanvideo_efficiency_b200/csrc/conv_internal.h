@@ -24,6 +24,7 @@ struct HaloArgs {
   int gn_groups, gn_cpg, gn_rows;
   int probe;
   int tfold;              // weights carry the 18 folded first-frame taps (tfold_* in tcgen05.cuh)
+  int kwpack;             // THIN only: x holds the three kw taps along the channel axis, w is [9 = (kt, kh)][Cout][16]
 };
 
 void halo_geometry(int bn, int mt, bool pair, bool thin, int* twh, int* thh, int* taps_per_b, int* brows);

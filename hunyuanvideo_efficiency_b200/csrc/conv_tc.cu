@@ -786,8 +786,11 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
   // variant bit 8: `w` holds 45 tap slices, the 27 of the conv followed by the 18 folded first-frame taps (tfold_class);
   // used by the halo and kh-trick kernels for stride-1 3x3x3 convs, ignored (first 27 slices) by every other kernel
   const bool w_has_fold = (variant & 0x100) != 0 && k == 3 && st == 1 && sh == 1 && sw == 1;
+  // variant bit 9: kw-packed thin input (hyvae_ncthw_to_vol_kw3): x's 16 channels are (kw, c) of a <= 5-channel source and
+  // `w` is [9 = (kt, kh)][Cout][16]; only the thin halo kernel takes it
+  const bool kwpack = (variant & 0x200) != 0;
   variant &= 0xff;
-  const int w_taps = w_has_fold ? 45 : k * k * k;
+  const int w_taps = kwpack ? 9 : (w_has_fold ? 45 : k * k * k);
   a.tfold = 0;
 
   // ---- halo kernel (conv_halo.cu): every stride-1 3x3x3 conv with Cout <= 128 and a 16-bit output (variant 5 forces it)
@@ -807,7 +810,7 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
     h.bias = bias; h.B = y->B; h.To = y->T; h.Ho = y->H; h.Wo = y->W; h.Cin = x->C; h.Cout = y->C;
     h.tiles_h = (y->H + 15) / 16; h.groups_w = (y->W + 15) / 16;
     h.total = (int64_t)y->B * y->T * h.tiles_h * h.groups_w;
-    h.has_res = 0; h.round_like_ref = 0; h.sc_chunks = h.sc_cin = 0; h.gn_part = nullptr; h.gn_groups = h.gn_cpg = h.gn_rows = 0; h.probe = a.probe; h.tfold = 0;
+    h.has_res = 0; h.round_like_ref = 0; h.sc_chunks = h.sc_cin = 0; h.gn_part = nullptr; h.gn_groups = h.gn_cpg = h.gn_rows = 0; h.probe = a.probe; h.tfold = 0; h.kwpack = 0;
     const CUtensorMapDataType dt = x->dtype == HYVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUtensorMap tmA, tmB;
     {
@@ -852,6 +855,8 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
     h.sc_cin = sc_x ? sc_x->C : 0; h.sc_chunks = (h.sc_cin + 63) / 64;
     h.gn_part = gn_partials; h.gn_groups = gn_groups; h.gn_cpg = 0; h.gn_rows = num_sms() * 4; h.probe = a.probe;
     h.tfold = (w_has_fold && !thin) ? 1 : 0;
+    h.kwpack = kwpack ? 1 : 0;
+    HYVAE_CHECK_ARG(!kwpack || thin, "kw-packed input needs the thin halo kernel (Cin stored as 16, 64 < Cout <= 128)");
     if (gn_partials) {
       HYVAE_CHECK_ARG(gn_groups > 0 && y->C % gn_groups == 0, "gn_groups=%d does not divide Cout=%d", gn_groups, y->C);
       h.gn_cpg = y->C / gn_groups;
@@ -921,6 +926,7 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
     return launch_halo(x->dtype, bn, mt, pair, thin, tmA, tmB, tmY, tmR, tmX, tmW, h, (cudaStream_t)stream);
   }
 
+  HYVAE_CHECK_ARG(!kwpack, "kw-packed input is only supported by the thin halo kernel (stride-1 3x3x3, Cin stored as 16, 64 < Cout <= 128)");
   pick_tile(y->H, y->W, sh, sw, &a.TH, &a.TW);
   // variant: 0 = auto, 1 = 1-CTA kernel with MT=1, 2 = 1-CTA kernel, 3 = CTA-pair kernel without the kh trick
   const int BN_sel = y->C > 128 ? 256 : (y->C > 64 ? 128 : (y->C > 32 ? 64 : 32));

@@ -55,6 +55,37 @@ __global__ void ncthw_to_vol_kernel(const S* __restrict__ src, Vol d, int src_C,
   }
 }
 
+// conv_in operand with the three kw taps packed along the channel axis: destination channel kw * src_C + c of voxel
+// (t, h, w) = source channel c of voxel (t, h, clamp(w + kw - 1)); the remaining channels are zero.  A 3x3x3 conv over the
+// 3-channel clip then is a 3x3 (kt, kh) conv over 9 (of 16 stored) channels: one K = 16 MMA slice per (kt, kh) instead of
+// one per (kt, kh, kw) — a third of the MMAs for the same bytes (hyvae_conv3d_causal_tc, variant bit 9).
+template <typename S, typename D>
+__global__ void ncthw_to_vol_kw3_kernel(const S* __restrict__ src, Vol d, int src_C, int64_t sb, int64_t sc, int64_t st, int64_t sh, int64_t sw) {
+  const int64_t nvox = (int64_t)d.B * d.Tp() * d.Hp() * d.Wp();
+  D* dst = reinterpret_cast<D*>(d.p);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvox; i += (int64_t)gridDim.x * blockDim.x) {
+    int wp = (int)(i % d.Wp());
+    int64_t r = i / d.Wp();
+    int hp = (int)(r % d.Hp()); r /= d.Hp();
+    int tp = (int)(r % d.Tp());
+    int b = (int)(r / d.Tp());
+    int t = max(tp - d.pt, 0);
+    int h = min(max(hp - d.ph, 0), d.H - 1);
+    int w = min(max(wp - d.pw, 0), d.W - 1);
+    const S* s = src + b * sb + t * st + h * sh;
+    D* o = dst + i * d.C;
+    for (int c0 = 0; c0 < d.C; c0 += 8) {   // d.C % 8 == 0 (checked by the host)
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ch = c0 + j, kw = ch / src_C, c = ch - kw * src_C;
+        f[j] = kw < 3 ? to_f<S>(s[min(max(w + kw - 1, 0), d.W - 1) * sw + c * sc]) : 0.f;
+      }
+      Vec8<D> q; q.set(f); q.store(o + c0);
+    }
+  }
+}
+
 template <typename S, typename D>
 __global__ void vol_to_ncthw_kernel(Vol s, D* __restrict__ dst, int dst_C) {
   const int64_t thw = (int64_t)s.T * s.H * s.W;
@@ -514,6 +545,18 @@ int hyvae_ncthw_to_vol(const void* src, int32_t src_dtype, int32_t src_C, const 
   HYVAE_DISPATCH_DTYPE(src_dtype, S, HYVAE_DISPATCH_DTYPE(dst->dtype, D,
       (ncthw_to_vol_kernel<S, D><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const S*)src, d, src_C, ss[0], ss[1], ss[2], ss[3], ss[4]))));
   return check_launch("ncthw_to_vol");
+}
+
+int hyvae_ncthw_to_vol_kw3(const void* src, int32_t src_dtype, int32_t src_C, const int64_t* ss, const hyvae_vol* dst, void* stream) {
+  if (int e = check_vol(dst, "dst")) return e;
+  HYVAE_CHECK_ARG(src != nullptr && ss != nullptr, "src is null");
+  HYVAE_CHECK_ARG(src_C > 0 && 3 * src_C <= dst->C && dst->C % 8 == 0, "kw-packed layout needs 3*src_C=%d <= dst C=%d, a multiple of 8", 3 * src_C, dst->C);
+  Vol d = make_vol(dst);
+  int64_t n = (int64_t)d.B * d.Tp() * d.Hp() * d.Wp();
+  ProfScope prof(PC_LAYOUT, (double)n * (3.0 * src_C * dtype_size(src_dtype) + d.C * dtype_size(dst->dtype)), stream);
+  HYVAE_DISPATCH_DTYPE(src_dtype, S, HYVAE_DISPATCH_DTYPE(dst->dtype, D,
+      (ncthw_to_vol_kw3_kernel<S, D><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const S*)src, d, src_C, ss[0], ss[1], ss[2], ss[3], ss[4]))));
+  return check_launch("ncthw_to_vol_kw3");
 }
 
 int hyvae_vol_to_ncthw(const hyvae_vol* src, void* dst, int32_t dst_dtype, int32_t dst_C, void* stream) {

@@ -96,6 +96,25 @@ class _Conv3dParams(nn.Module):
             self._packed = (key, pw.contiguous(), None if pb is None else pb.contiguous())
         return self._packed[1], self._packed[2]
 
+    def kw_packable(self) -> bool:
+        """conv_in-like layer served by the thin halo kernel whose three kw taps fit one 16-channel row (3 * Cin <= 16)."""
+        return (self.cin_padded() == 16 and 3 * self.in_channels <= 16 and self.kernel_size[0] == 3
+                and os.environ.get("HYVAE_KWPACK", "1") == "1")
+
+    def packed_kw(self, dtype):
+        """[9 = kt*3+kh][Cout][16] weights for a kw-packed input (Vol.from_ncthw(kw_pack=True)): column kw * Cin + c of tap
+        (kt, kh) is W[:, c, kt, kh, kw]; the other columns are zero."""
+        w = self.weight
+        key = ("kw", w._version, w.data_ptr(), dtype, w.device, None if self.bias is None else self.bias._version)
+        cached = getattr(self, "_packed_kw", None)
+        if cached is None or cached[0] != key:
+            co, ci = self.out_channels, self.in_channels
+            pw = torch.zeros((9, co, 16), dtype=dtype, device=w.device)
+            pw[:, :, :3 * ci] = w.detach().permute(2, 3, 0, 4, 1).reshape(9, co, 3 * ci).to(dtype)   # [kt][kh][Cout][kw][Cin]
+            pb = None if self.bias is None else self.bias.detach().float().contiguous()
+            self._packed_kw = cached = (key, pw.contiguous(), pb)
+        return cached[1], cached[2]
+
     def phase_packed(self, dtype, up):
         """Weights of the sub-pixel phases of `nearest-upsample(up) -> this 3x3x3 conv` (hyvae_conv3d_upphase_tc):
         {(pt, ph, pw): [nkt*2*2][Cout][Cin]}.  Along an upsampled axis the three taps fold onto two low-res taps,
@@ -147,6 +166,12 @@ class CausalConv3d(nn.Module):
         c = self.conv
         return self.halo if tc_eligible(dtype, c.in_channels, c.out_channels, c.stride, c.kernel_size[0]) else (0, 0, 0)
 
+    def wants_kw_pack(self, dtype) -> bool:
+        """True when the producer (the NCTHW -> volume layout pass) should write the kw-packed operand (conv_in)."""
+        c = self.conv
+        return (c.kw_packable() and tuple(int(v) for v in c.stride) == (1, 1, 1) and 64 < c.out_channels <= 128
+                and tc_eligible(dtype, c.in_channels, c.out_channels, c.stride, 3))
+
     def input_layout(self, dtype):
         """(halo, channel count) a producer should write so that this conv needs no extra pad pass."""
         c = self.conv
@@ -158,6 +183,13 @@ class CausalConv3d(nn.Module):
         c = self.conv
         k, stride = c.kernel_size[0], tuple(int(s) for s in c.stride)
         rl = False  # one rounding per stored tensor: conv + bias + residual are summed in fp32, then stored
+        if x.kw_packed:   # conv_in on the operand the layout pass packed for it: 9 (kt, kh) taps of K = 16
+            assert self.wants_kw_pack(x.dtype) and x.pad == self.halo and x.C == 16 and residual is None and up == (1, 1, 1)
+            w, b = c.packed_kw(x.dtype)
+            y = N.conv3d_tc(x, w, b, 3, (1, 1, 1), c.out_channels, None, out_dtype, rl, gn_groups=self.emit_gn_groups,
+                            variant=N.VARIANT_KWPACK)
+            y.c_valid = c.out_channels
+            return y
         if tc_eligible(x.dtype, c.in_channels, c.out_channels, stride, k):
             # first-frame temporal fold: fp16 operands only (like the sub-pixel phases, the folded sums need fp16's mantissa)
             tfold = (k == 3 and stride == (1, 1, 1) and x.dtype == torch.float16 and out_dtype in (None, torch.float16)

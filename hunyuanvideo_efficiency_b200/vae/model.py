@@ -379,7 +379,7 @@ class AutoencoderKLCausal3D(nn.Module):
     def _encode_tile(self, x: torch.Tensor) -> torch.Tensor:
         act = self._act_dtype()
         pad, ch = self.encoder.conv_in.input_layout(act)   # tensor-core conv_in: halo + 3->8 channels written here
-        v = Vol.from_ncthw(x, dtype=act, pad=pad, channels=ch)
+        v = Vol.from_ncthw(x, dtype=act, pad=pad, channels=ch, kw_pack=self.encoder.conv_in.wants_kw_pack(act))
         return self.quant_conv.forward_vol(self.encoder.forward_vol(v)).to_ncthw(dtype=self.dtype)
 
     def _decode_tile(self, z: torch.Tensor) -> torch.Tensor:

@@ -53,6 +53,11 @@ int hyvae_device_supports_tc(void);
 int hyvae_ncthw_to_vol(const void* src, int32_t src_dtype, int32_t src_C, const int64_t* src_strides, const hyvae_vol* dst,
                        void* stream);
 int hyvae_vol_to_ncthw(const hyvae_vol* src, void* dst, int32_t dst_dtype, int32_t dst_C, void* stream);
+/* conv_in operand with the kw taps packed along the channel axis: dst channel kw*src_C + c of voxel (t,h,w) = source
+ * channel c of voxel (t,h,clamp(w+kw-1)), other channels zero (3*src_C <= dst->C, dst->C % 8 == 0).  With it the 3x3x3
+ * conv_in (vae.py:118-121) is a 9-tap (kt,kh) conv: hyvae_conv3d_causal_tc with variant bit 9 and w = [9][Cout][16]. */
+int hyvae_ncthw_to_vol_kw3(const void* src, int32_t src_dtype, int32_t src_C, const int64_t* src_strides, const hyvae_vol* dst,
+                           void* stream);
 
 /* ---- CausalConv3d ------------------------------------------------------------------------------
  * Replaces F.pad(replicate)+nn.Conv3d, unet_causal_3d_blocks.py:73-75 (k=3 or k=1; stride from
@@ -72,7 +77,8 @@ int hyvae_vol_to_ncthw(const hyvae_vol* src, void* dst, int32_t dst_dtype, int32
  *          variant: 0 = automatic kernel choice (low byte 1..7 force a kernel, tests only).  Bit 8 (0x100), stride-1
  *          3x3x3 only: `w` holds 45 tap slices — the 27 above, then W[kt=0]+W[1]+W[2] (9 slices, (kh,kw) order) and
  *          W[0]+W[1] (9 slices).  Output frames 0 and 1 read frame 0 under three / two of their frame taps (causal
- *          replicate padding :68,74), so the kernels that support it run them with one / two folded taps: 1/T fewer MACs. */
+ *          replicate padding :68,74), so the kernels that support it run them with one / two folded taps: 1/T fewer MACs.
+ *          Bit 9 (0x200): x is a kw-packed thin volume (hyvae_ncthw_to_vol_kw3) and `w` is [9 = kt*3+kh][Cout][16]. */
 int hyvae_conv3d_causal_direct(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
                                const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
                                int32_t up_t, int32_t up_h, int32_t up_w, int32_t round_like_ref, void* stream);

@@ -248,6 +248,37 @@ def test_tc_conv_matches_direct_bf16(B, Cin, Cout, T, H, W, stride):
     assert torch.equal(y16.to_ncthw().cpu(), y.to_ncthw().cpu().bfloat16()) or O.rel_err(ref, y16.to_ncthw().float().cpu()) < 4e-3
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,T,H,W", [(2, 5, 20, 24), (1, 3, 33, 17), (1, 1, 16, 16)])
+def test_tc_conv_in_kw_packed_matches_reference(dtype, B, T, H, W):
+    """conv_in (3 -> 128) on the kw-packed operand (hyvae_ncthw_to_vol_kw3 + variant bit 9: 9 taps of K = 16) against the
+    fp32 reference conv on the same 16-bit-rounded operands and against the unpacked thin kernel; the packed layout itself
+    is checked element by element."""
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    from hunyuanvideo_efficiency_b200.vae.blocks import CausalConv3d
+    g = torch.Generator().manual_seed(T * 100 + W)
+    conv = CausalConv3d(3, 128, 3).to(_dev())
+    conv.emit_gn_groups = 32
+    assert conv.wants_kw_pack(dtype)
+    x = torch.randn(B, 3, T, H, W, generator=g).to(dtype)
+    pad, ch = conv.input_layout(dtype)
+    vp = N.Vol.from_ncthw(x.to(_dev()), pad=pad, channels=ch, kw_pack=True)
+    xi = vp.interior().float().cpu()                                   # [B][T][H][W][16]
+    xl = x.float().permute(0, 2, 3, 4, 1)                              # [B][T][H][W][3]
+    idx = torch.arange(W)
+    for kw in range(3):
+        assert torch.equal(xi[..., 3 * kw:3 * kw + 3], xl[:, :, :, (idx + kw - 1).clamp(0, W - 1)])
+    assert torch.count_nonzero(xi[..., 9:]) == 0
+    y_p = conv.forward_vol(vp)
+    y_u = conv.forward_vol(N.Vol.from_ncthw(x.to(_dev()), pad=pad, channels=ch))
+    ref = O.causal_conv3d(x.float(), conv.conv.weight.detach().to(dtype).float().cpu(), conv.conv.bias.detach().float().cpu())
+    tol = 2e-3 if dtype == torch.float16 else 8e-3                      # one rounding of the stored output
+    assert O.rel_err(ref, y_p.to_ncthw().float().cpu()) < tol and O.rel_err(ref, y_u.to_ncthw().float().cpu()) < tol
+    assert torch.allclose(y_p.gn_sums, y_u.gn_sums, rtol=1e-3, atol=0.5)
+
+
 def test_tc_thin_layers_and_fused_gn_stats():
     """conv_in (3 -> C, channels zero-padded to 8), conv_out (C -> 3, Cout padded to 8) and the GroupNorm partial
     statistics emitted by the conv epilogue."""
