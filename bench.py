@@ -8,7 +8,13 @@ One "step" = one pass of the hot path over one synthetic clip: enable_tiling(); 
 mode() -> decode() (BASELINE config 4; 84 encoder + 84 decoder sub-model calls, 6467.8 conv TFLOP).  At N > 1
 the SAME clip is partitioned by tile over the ranks (strong scaling, hunyuanvideo_efficiency_b200/vae/tile_parallel.py).
 Prints ONE JSON line on rank 0.  `--impl reference` times the CPU restatement of the reference (oracle/) on the
-host cores on a bounded sample of the same workload, scaled by conv FLOPs.
+host cores on a bounded sample of the same workload (BASELINE config 1, one canonical tile), scaled by conv FLOPs.
+
+Timed region: K steps with the clip resident in HBM, device timed (CUDA events, max over ranks), tiles dealt over the
+model's `tile_streams` CUDA streams, no instrumentation.  `e2e`: the same K steps from a pinned fp32 host clip with the
+H2D copy, bf16 cast and D2H of the reconstruction inside the timed region.  `roofline` / `kernel_ms_per_step_rank0`:
+CUDA events around every C-ABI launch (hyvae_profile_begin/end) on extra steps right after the timed region with all
+kernels serialised on ONE stream, because event pairs of kernels that overlap across streams do not measure a kernel.
 """
 from __future__ import annotations
 
