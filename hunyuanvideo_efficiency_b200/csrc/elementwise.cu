@@ -206,17 +206,22 @@ __device__ __forceinline__ float gn_act(float u) {
 
 template <typename T, bool SILU, bool RLR>
 __global__ void __launch_bounds__(256, 3) gn_apply_kernel(Vol x, Vol y, const double* __restrict__ sums, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, int groups, float eps, int rows_per_block) {
+                                const float* __restrict__ beta, int groups, float eps, int rows_per_block, double inv_n) {
   extern __shared__ float sh[];  // scale[C], shift[C]
   const int C = x.C, CV = C / 8, b = blockIdx.y;
   const int cpg = C / groups;
-  const double n = (double)x.T * x.H * x.W * cpg;
+  // Every block derives scale / shift itself.  A large tensor has ~17 k blocks of ~130 KB each, so this prologue must
+  // stay short: with two fp64 divisions, an fp64 sqrt and an fp64 reciprocal per channel it took a few microseconds in
+  // which the block had no loads in flight — a quarter of a block's lifetime at the HBM rate.  Now: inv_n from the
+  // host, the variance (the one cancellation-prone step) in fp64, and an IEEE fp32 rsqrt for the 16-bit types.
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     int g = c / cpg;
-    double mean = sums[((int64_t)b * groups + g) * 2] / n;
-    double var = sums[((int64_t)b * groups + g) * 2 + 1] / n - mean * mean;
+    const double mean = sums[((int64_t)b * groups + g) * 2] * inv_n;
+    double var = fma(-mean, mean, sums[((int64_t)b * groups + g) * 2 + 1] * inv_n);
     if (var < 0) var = 0;
-    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float rstd;
+    if (FastMath<T>::value) rstd = __frsqrt_rn((float)(var + (double)eps));
+    else rstd = (float)(1.0 / sqrt(var + (double)eps));
     float sc = gamma[c] * rstd;
     sh[c] = sc;
     sh[C + c] = beta[c] - (float)mean * sc;
@@ -631,8 +636,9 @@ int hyvae_groupnorm_apply(const hyvae_vol* x, const double* sums, const float* g
   while (rpb > 1 && (int64_t)((nrows + rpb - 1) / rpb) * x->B < 8 * num_sms()) rpb >>= 1;
   dim3 grid((unsigned)((nrows + rpb - 1) / rpb), (unsigned)x->B);
   size_t smem = sizeof(float) * 2 * x->C;
+  const double inv_n = 1.0 / ((double)x->T * x->H * x->W * (x->C / groups));
 #define HYVAE_GN_LAUNCH(S, R) \
-  HYVAE_DISPATCH_DTYPE(x->dtype, T, (gn_apply_kernel<T, S, R><<<grid, 256, smem, (cudaStream_t)stream>>>(vx, vy, sums, gamma, beta, groups, eps, rpb)))
+  HYVAE_DISPATCH_DTYPE(x->dtype, T, (gn_apply_kernel<T, S, R><<<grid, 256, smem, (cudaStream_t)stream>>>(vx, vy, sums, gamma, beta, groups, eps, rpb, inv_n)))
   if (silu) { if (round_like_ref) { HYVAE_GN_LAUNCH(true, true); } else { HYVAE_GN_LAUNCH(true, false); } }
   else { if (round_like_ref) { HYVAE_GN_LAUNCH(false, true); } else { HYVAE_GN_LAUNCH(false, false); } }
 #undef HYVAE_GN_LAUNCH
