@@ -78,6 +78,9 @@ def lib():
             fn.argtypes = args
             fn.restype = C.c_int
         l.hyvae_version.restype = C.c_int
+        if l.hyvae_version() != ABI_VERSION:   # a stale build would be called with the wrong argument lists
+            raise HyvaeError(f"{LIB_PATH} is ABI version {l.hyvae_version()}, this package binds {ABI_VERSION}: rebuild it "
+                             f"(make -C {os.path.join(_HERE, 'csrc')})")
         l.hyvae_last_error.restype = C.c_char_p
         l.hyvae_device_supports_tc.restype = C.c_int
         l.hyvae_launch_count.restype = C.c_int64
@@ -224,6 +227,7 @@ def conv3d_direct(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, resi
     return y
 
 
+ABI_VERSION = 110      # HYVAE_VERSION of include/hyvae.h this module binds
 VARIANT_KWPACK = 0x200  # hyvae_conv3d_causal_tc: x is a kw-packed thin volume (Vol.from_ncthw(kw_pack=True)), w is [9][Cout][16]
 VARIANT_TFOLD = 0x100  # hyvae_conv3d_causal_tc: `w` carries the 18 folded first-frame tap slices after the 27 (include/hyvae.h)
 _GN_PART = {}

@@ -22,6 +22,14 @@ from .._native import Vol
 _16BIT = (torch.bfloat16, torch.float16)
 
 
+def _publish(t: torch.Tensor):
+    """Derived parameter tensors (packed weights, fp32 norm parameters, summed biases) are created lazily on whatever stream
+    first needs them and then read from EVERY tile stream (model.run_tiles) without further ordering: wait here, once per
+    parameter version, until the kernels that produced them have finished."""
+    if t.is_cuda:
+        torch.cuda.current_stream(t.device).synchronize()
+
+
 def _triple(v):
     return tuple(v) if isinstance(v, (tuple, list)) else (v, v, v)
 
@@ -94,6 +102,7 @@ class _Conv3dParams(nn.Module):
                 if pb is not None:
                     pb = torch.cat([pb, torch.zeros(cop - co, device=w.device)])
             self._packed = (key, pw.contiguous(), None if pb is None else pb.contiguous())
+            _publish(self._packed[1])
         return self._packed[1], self._packed[2]
 
     def kw_packable(self) -> bool:
@@ -113,6 +122,7 @@ class _Conv3dParams(nn.Module):
             pw[:, :, :3 * ci] = w.detach().permute(2, 3, 0, 4, 1).reshape(9, co, 3 * ci).to(dtype)   # [kt][kh][Cout][kw][Cin]
             pb = None if self.bias is None else self.bias.detach().float().contiguous()
             self._packed_kw = cached = (key, pw.contiguous(), pb)
+            _publish(cached[1])
         return cached[1], cached[2]
 
     def phase_packed(self, dtype, up):
@@ -135,6 +145,7 @@ class _Conv3dParams(nn.Module):
                         out[(pt, ph, pw)] = wp.reshape(-1, self.out_channels, self.in_channels).to(dtype).contiguous()
             pb = None if self.bias is None else self.bias.detach().float().contiguous()
             self._phase_packed = cached = (key, out, pb)
+            _publish(w)
         return cached[1], cached[2]
 
 
@@ -225,6 +236,7 @@ class _GroupNorm(nn.Module):
         key = (self.weight._version, self.bias._version, self.weight.data_ptr(), self.weight.device)
         if self._f32 is None or self._f32[0] != key:
             self._f32 = (key, self.weight.detach().float().contiguous(), self.bias.detach().float().contiguous())
+            _publish(self._f32[1])
         return self._f32[1], self._f32[2]
 
     def forward_vol(self, x: Vol, silu: bool, pad=(0, 0, 0)) -> Vol:
@@ -364,6 +376,7 @@ class ResnetBlockCausal3D(nn.Module):
         key = (c2.bias._version, cs.bias._version, b2.data_ptr(), bs.data_ptr())
         if getattr(self, "_bias_sum", None) is None or self._bias_sum[0] != key:
             self._bias_sum = (key, (b2 + bs).contiguous())
+            _publish(self._bias_sum[1])
         try:
             return N.conv3d_tc_shortcut(h, w2, self._bias_sum[1], x, ws, c2.out_channels, gn_groups=self.conv2.emit_gn_groups, tfold=tfold)
         except N.HyvaeUnsupported:   # tile shape the fused kernels do not take: run the shortcut as its own k=1 conv
@@ -388,6 +401,7 @@ class _Linear(nn.Module):
         key = (self.weight._version, self.bias._version, self.weight.data_ptr(), dtype)
         if self._packed is None or self._packed[0] != key:
             self._packed = (key, self.weight.detach().to(dtype).contiguous(), self.bias.detach().float().contiguous())
+            _publish(self._packed[1])
         return self._packed[1], self._packed[2]
 
 

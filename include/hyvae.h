@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HYVAE_VERSION 100 /* 0.1.0 */
+#define HYVAE_VERSION 110 /* 0.1.1: fused attention, metrics, kw-packed conv_in, temporal fold flag */
 
 typedef enum { HYVAE_OK = 0, HYVAE_EINVAL = -1, HYVAE_ECUDA = -2, HYVAE_EUNSUPPORTED = -3 } hyvae_status;
 typedef enum { HYVAE_BF16 = 0, HYVAE_F32 = 1, HYVAE_F16 = 2 } hyvae_dtype;
