@@ -48,6 +48,7 @@ _SIGNATURES = {
     "hyvae_groupnorm_stats": [_VP, _i32, _vp, _vp, _i64, _vp],
     "hyvae_groupnorm_apply": [_VP, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _VP, _vp],
     "hyvae_pad_upsample": [_VP, _VP, _i32, _i32, _i32, _vp],
+    "hyvae_halo_fill": [_VP, _vp],
     "hyvae_softmax_frame_causal": [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp],
     "hyvae_attn_block_causal": [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _f32, _vp],
     "hyvae_video_to_frames_u8": [_vp, _i32, C.POINTER(_i64), _i32, _i32, _i32, _i32, _i32, _vp, _vp],
@@ -265,9 +266,10 @@ def conv3d_tc(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, residual
 
 
 def conv3d_tc_shortcut(x: Vol, w: torch.Tensor, bias: torch.Tensor, sc_x: Vol, sc_w: torch.Tensor, cout: int, gn_groups: int = 0,
-                       tfold: bool = False) -> Vol:
-    """y = conv3x3x3(x) + conv1x1x1(sc_x) + bias in one launch (the resnet block's conv2 with its conv_shortcut)."""
-    y = Vol(x.B, x.T, x.H, x.W, cout, x.dtype, x.device)
+                       tfold: bool = False, out_pad=(0, 0, 0)) -> Vol:
+    """y = conv3x3x3(x) + conv1x1x1(sc_x) + bias in one launch (the resnet block's conv2 with its conv_shortcut).
+    out_pad: y is allocated with that halo and only its interior is written (the caller runs halo_fill)."""
+    y = Vol(x.B, x.T, x.H, x.W, cout, x.dtype, x.device, out_pad)
     part, rows = None, 0
     if gn_groups > 0 and cout % gn_groups == 0 and (cout // gn_groups) in (2, 4, 8, 16, 32):
         rows = int(lib().hyvae_conv3d_tc_gn_rows())
@@ -317,6 +319,13 @@ def groupnorm(x: Vol, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps:
     y = x.like(pad=pad)
     _check(lib().hyvae_groupnorm_apply(x.ref(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), groups, eps, int(silu),
                                        int(round_like_ref), y.ref(), _stream()), "groupnorm_apply")
+    return y
+
+
+def halo_fill(y: Vol) -> Vol:
+    """Replicate halo of a padded volume whose interior a conv has just written (hyvae_halo_fill)."""
+    if y.pad != (0, 0, 0):
+        _check(lib().hyvae_halo_fill(y.ref(), _stream()), "halo_fill")
     return y
 
 

@@ -318,6 +318,32 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(double* __restrict__ p
 }
 
 // ------------------------------------------------------------------------------------------------
+// replicate halo of a volume whose INTERIOR was written in place (by a conv epilogue): instead of a pad pass that copies
+// the whole tensor (1 read + 1 write), only the halo voxels are written — 4-6 % of the tensor at the big shapes.
+// grid = (Tp * Hp destination rows, B); a halo row copies its clamped interior row (Wp voxels), an interior row only its
+// 2 * pw edge voxels.  Sources are interior voxels only, so the order of the writes does not matter.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) halo_fill_kernel(Vol y) {
+  const int CV = y.C / 8, b = blockIdx.y;
+  const int Hp = y.Hp(), Wp = y.Wp();
+  const int tp = blockIdx.x / Hp, hp = blockIdx.x - tp * Hp;
+  const bool halo_row = tp < y.pt || hp < y.ph || hp >= y.ph + y.H;
+  const int t = max(tp - y.pt, 0), h = min(max(hp - y.ph, 0), y.H - 1);
+  T* base = reinterpret_cast<T*>(y.p);
+  const T* srow = base + y.at(b, t, h, 0);
+  T* drow = base + (int64_t)b * y.sB + (int64_t)tp * y.sT + (int64_t)hp * y.sH;
+  const int nvox = halo_row ? Wp : 2 * y.pw;
+  for (int i = threadIdx.x; i < nvox * CV; i += blockDim.x) {
+    const int v = i / CV, cv = i - v * CV;
+    const int wp = halo_row ? v : (v < y.pw ? v : y.W + v);  // interior rows: left pw voxels, then the right pw voxels
+    const int w = min(max(wp - y.pw, 0), y.W - 1);
+    Vec8<T> q; q.load(srow + (int64_t)w * y.sW + cv * 8);
+    q.store(drow + (int64_t)wp * y.sW + cv * 8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // replicate pad / nearest upsample (first frame not upsampled in T)
 // ------------------------------------------------------------------------------------------------
 // grid = (row chunks, B): a block walks destination rows (tp, hp) of Wp voxels, so the per-vector index math is 32-bit
@@ -650,6 +676,21 @@ int hyvae_groupnorm_finalize(double* partials, int32_t B, int64_t rows, int32_t 
   ProfScope prof(PC_GN_STATS, (double)B * rows * groups * 8, stream);
   gn_finalize_kernel<<<dim3((unsigned)groups, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(partials, rows, groups, sums);
   return check_launch("groupnorm_finalize");
+}
+
+int hyvae_halo_fill(const hyvae_vol* y, void* stream) {
+  if (int e = check_vol(y, "y")) return e;
+  HYVAE_CHECK_ARG(y->dtype != HYVAE_F32 && y->C % 8 == 0, "halo_fill: 16-bit volumes with C %% 8 == 0 (C=%d)", y->C);
+  if (y->pt == 0 && y->ph == 0 && y->pw == 0) return HYVAE_OK;
+  Vol vy = make_vol(y);
+  const int64_t rows = (int64_t)vy.Tp() * vy.Hp();
+  HYVAE_CHECK_ARG(rows < (1ll << 31) && y->B <= 65535, "halo_fill: volume too large");
+  const double halo_vox = (double)y->B * ((double)vy.Tp() * vy.Hp() * vy.Wp() - (double)y->T * y->H * y->W);
+  ProfScope prof(PC_PAD_UPSAMPLE, 2.0 * halo_vox * y->C * dtype_size(y->dtype), stream, "halo_fill");
+  dim3 grid((unsigned)rows, (unsigned)y->B);
+  if (y->dtype == HYVAE_BF16) halo_fill_kernel<__nv_bfloat16><<<grid, 128, 0, (cudaStream_t)stream>>>(vy);
+  else halo_fill_kernel<__half><<<grid, 128, 0, (cudaStream_t)stream>>>(vy);
+  return check_launch("halo_fill");
 }
 
 int hyvae_pad_upsample(const hyvae_vol* x, const hyvae_vol* y, int32_t up_t, int32_t up_h, int32_t up_w, void* stream) {

@@ -190,7 +190,9 @@ class CausalConv3d(nn.Module):
             return self.halo, c.cin_padded()
         return (0, 0, 0), c.in_channels
 
-    def forward_vol(self, x: Vol, residual: Optional[Vol] = None, up=(1, 1, 1), out_dtype=None) -> Vol:
+    def forward_vol(self, x: Vol, residual: Optional[Vol] = None, up=(1, 1, 1), out_dtype=None, out_pad=(0, 0, 0)) -> Vol:
+        """out_pad (tensor-core path only): write the result into the interior of a volume with that halo and replicate
+        the halo afterwards (N.halo_fill), so that the next CausalConv3d needs no full-tensor pad pass."""
         c = self.conv
         k, stride = c.kernel_size[0], tuple(int(s) for s in c.stride)
         rl = False  # one rounding per stored tensor: conv + bias + residual are summed in fp32, then stored
@@ -209,8 +211,13 @@ class CausalConv3d(nn.Module):
             cin_p, cout_p = w.shape[2], w.shape[1]
             if x.pad != self.halo or up != (1, 1, 1) or x.C != cin_p:
                 x = N.pad_upsample(x, up, self.halo, channels=cin_p)
+            out = None
+            if tuple(out_pad) != (0, 0, 0):
+                To, Ho, Wo = N.conv_out_dims(x.T, x.H, x.W, stride)
+                out = Vol(x.B, To, Ho, Wo, cout_p, out_dtype or x.dtype, x.device, tuple(out_pad))
             y = N.conv3d_tc(x, w, b, k, stride, cout_p, residual, out_dtype, rl, gn_groups=self.emit_gn_groups,
-                            variant=N.VARIANT_TFOLD if tfold else 0)
+                            variant=N.VARIANT_TFOLD if tfold else 0, out=out)
+            N.halo_fill(y)
             y.c_valid = c.out_channels
             return y
         w, b = c.packed(x.dtype)
@@ -270,6 +277,20 @@ class UpsampleCausal3D(nn.Module):
         else:
             self.Conv2d_0 = conv
 
+    def _uses_phases(self, dtype) -> bool:
+        up = self.upsample_factor if self.interpolate else (1, 1, 1)
+        conv = self.conv if self.name == "conv" else self.Conv2d_0
+        if conv is None:
+            return False
+        c = conv.conv
+        return (self.phase_decomposition and dtype == torch.float16 and up[1:] == (2, 2) and c.kernel_size[0] == 3
+                and tuple(int(v) for v in c.stride) == (1, 1, 1) and c.in_channels % 8 == 0 and c.out_channels % 8 == 0
+                and c.out_channels >= 64 and tc_eligible(dtype, c.in_channels, c.out_channels, (1, 1, 1), 3))
+
+    def wants_halo(self, dtype) -> Tuple[int, int, int]:
+        """Halo of the LOW-res input the sub-pixel phase path reads through TMA ((0,0,0): the pad+upsample pass builds it)."""
+        return (1 if self.upsample_factor[0] == 2 else 2, 1, 1) if self._uses_phases(dtype) else (0, 0, 0)
+
     def forward_vol(self, x: Vol) -> Vol:
         assert x.C == self.channels
         up = self.upsample_factor if self.interpolate else (1, 1, 1)
@@ -277,12 +298,10 @@ class UpsampleCausal3D(nn.Module):
         if conv is None:
             return N.pad_upsample(x, up)
         c = conv.conv
-        if (self.phase_decomposition and x.dtype == torch.float16 and up[1:] == (2, 2) and c.kernel_size[0] == 3
-                and tuple(int(v) for v in c.stride) == (1, 1, 1) and c.in_channels % 8 == 0 and c.out_channels % 8 == 0
-                and c.out_channels >= 64 and tc_eligible(x.dtype, c.in_channels, c.out_channels, (1, 1, 1), 3)):
+        if self._uses_phases(x.dtype):
             # sub-pixel phases over the low-res tensor: 3.4x (2.25x) fewer MACs, no 8x upsampled intermediate
             pw, pb = c.phase_packed(x.dtype, up)
-            halo = (1 if up[0] == 2 else 2, 1, 1)
+            halo = self.wants_halo(x.dtype)
             xp = x if x.pad == halo else N.pad_upsample(x, (1, 1, 1), halo)
             return N.conv3d_upsample_phases(xp, pw, pb, up, c.out_channels, gn_groups=conv.emit_gn_groups)
         return conv.forward_vol(x, up=up)
@@ -347,16 +366,17 @@ class ResnetBlockCausal3D(nn.Module):
         self.conv1.emit_gn_groups = self.norm2.num_groups
         self.conv2.emit_gn_groups = groups
 
-    def forward_vol(self, x: Vol) -> Vol:
+    def forward_vol(self, x: Vol, out_pad=(0, 0, 0)) -> Vol:
+        """out_pad: halo the block's consumer (a down / upsampler conv) wants on the result; see CausalConv3d.forward_vol."""
         if self.output_scale_factor != 1.0:
             raise NotImplementedError("output_scale_factor != 1")
         h = self.norm1.forward_vol(x, True, self.conv1.wants_halo(x.dtype))
         h = self.conv1.forward_vol(h)
         h = self.norm2.forward_vol(h, True, self.conv2.wants_halo(x.dtype))
         if self.conv_shortcut is not None and self._can_fuse_shortcut(h, x):
-            return self._conv2_with_shortcut(h, x)
+            return self._conv2_with_shortcut(h, x, out_pad)
         skip = x if self.conv_shortcut is None else self.conv_shortcut.forward_vol(x)
-        return self.conv2.forward_vol(h, residual=skip)
+        return self.conv2.forward_vol(h, residual=skip, out_pad=out_pad)
 
     def _can_fuse_shortcut(self, h: Vol, x: Vol) -> bool:
         """The 1x1x1 conv_shortcut runs as extra K chunks of conv2's accumulator (hyvae_conv3d_causal_tc_shortcut) when
@@ -368,7 +388,7 @@ class ResnetBlockCausal3D(nn.Module):
                 and h.C == c2.in_channels and c2.bias is not None and cs.bias is not None
                 and tc_eligible(h.dtype, c2.in_channels, c2.out_channels, (1, 1, 1), 3))
 
-    def _conv2_with_shortcut(self, h: Vol, x: Vol) -> Vol:
+    def _conv2_with_shortcut(self, h: Vol, x: Vol, out_pad=(0, 0, 0)) -> Vol:
         c2, cs = self.conv2.conv, self.conv_shortcut.conv
         tfold = h.dtype == torch.float16 and os.environ.get("HYVAE_TFOLD", "1") == "1"   # as in CausalConv3d.forward_vol
         w2, b2 = c2.packed(h.dtype, pad8=True, tfold=tfold)
@@ -378,9 +398,10 @@ class ResnetBlockCausal3D(nn.Module):
             self._bias_sum = (key, (b2 + bs).contiguous())
             _publish(self._bias_sum[1])
         try:
-            return N.conv3d_tc_shortcut(h, w2, self._bias_sum[1], x, ws, c2.out_channels, gn_groups=self.conv2.emit_gn_groups, tfold=tfold)
+            return N.halo_fill(N.conv3d_tc_shortcut(h, w2, self._bias_sum[1], x, ws, c2.out_channels, gn_groups=self.conv2.emit_gn_groups,
+                                                    tfold=tfold, out_pad=tuple(out_pad)))
         except N.HyvaeUnsupported:   # tile shape the fused kernels do not take: run the shortcut as its own k=1 conv
-            return self.conv2.forward_vol(h, residual=self.conv_shortcut.forward_vol(x))
+            return self.conv2.forward_vol(h, residual=self.conv_shortcut.forward_vol(x), out_pad=out_pad)
 
     def forward(self, input_tensor, temb=None, scale: float = 1.0):
         return self.forward_vol(Vol.from_ncthw(input_tensor)).to_ncthw()
@@ -573,7 +594,9 @@ class DownEncoderBlockCausal3D(nn.Module):
             pc = self.resnet_pool_configs[i] or {}
             if pc.get("enable_before", False):
                 x = N.avgpool_t(x, pc["kernel"], pc["stride"])
-            x = resnet.forward_vol(x)
+            last = i == len(self.resnets) - 1 and self.downsamplers is not None and not pc.get("enable_after", False)
+            # the last resnet writes straight into the halo'd operand of the downsampler conv (no pad pass in between)
+            x = resnet.forward_vol(x, out_pad=self.downsamplers[0].conv.wants_halo(x.dtype) if last else (0, 0, 0))
             if pc.get("enable_after", False):
                 x = N.avgpool_t(x, pc["kernel"], pc["stride"])
         if self.downsamplers is not None:
@@ -625,7 +648,8 @@ class UpDecoderBlockCausal3D(nn.Module):
             ic = self.resnet_interp_configs[i] or {}
             if ic.get("enable_before", False):
                 x = self._interp(x, ic)
-            x = resnet.forward_vol(x)
+            last = i == len(self.resnets) - 1 and self.upsamplers is not None and not ic.get("enable_after", False)
+            x = resnet.forward_vol(x, out_pad=self.upsamplers[0].wants_halo(x.dtype) if last else (0, 0, 0))
             if ic.get("enable_after", False):
                 x = self._interp(x, ic)
         if self.upsamplers is not None:

@@ -131,6 +131,10 @@ int hyvae_groupnorm_finalize(double* partials, int32_t B, int64_t rows, int32_t 
  * Replaces F.pad(replicate) :74 and F.interpolate(nearest)+cat of UpsampleCausal3D.forward :152-171:
  * y (T' = 1+up_t*(T-1) if up_t==2, H*up_h, W*up_w, with any halo) <- x.  y->C may exceed x->C (zero channels). */
 int hyvae_pad_upsample(const hyvae_vol* x, const hyvae_vol* y, int32_t up_t, int32_t up_h, int32_t up_w, void* stream);
+/* Replicate halo of a volume whose interior was written in place (a conv may write into the interior of a padded `y`:
+ * every entry point honours y->pt/ph/pw): only the halo voxels are written, from the clamped interior voxel.  Spares the
+ * full-tensor pad pass (F.pad of the NEXT CausalConv3d, :74) between a resnet block and a down/upsampler. */
+int hyvae_halo_fill(const hyvae_vol* y, void* stream);
 
 /* ---- mid-block attention softmax ---------------------------------------------------------------
  * Replaces prepare_causal_attention_mask :38-46 + the softmax inside F.scaled_dot_product_attention

@@ -76,6 +76,28 @@ def test_pad_upsample_matches_reference():
         assert torch.equal(y.t.cpu(), ref)
 
 
+@pytest.mark.parametrize("pad", [(2, 1, 1), (1, 1, 1), (2, 0, 0)])
+def test_halo_fill_replicates_the_interior(pad):
+    """hyvae_halo_fill on a volume whose interior was written in place == F.pad(replicate) of that interior; and a conv that
+    writes into the interior of a padded output followed by halo_fill == the same conv followed by the pad pass."""
+    N = _N()
+    x = torch.randn(2, 16, 3, 6, 7).half()
+    v = N.Vol(2, 3, 6, 7, 16, torch.float16, _dev(), pad)
+    v.t.fill_(float("nan"))
+    v.interior().copy_(x.permute(0, 2, 3, 4, 1).to(_dev()))
+    N.halo_fill(v)
+    ref = torch.nn.functional.pad(x.float(), (pad[2], pad[2], pad[1], pad[1], pad[0], 0), mode="replicate").permute(0, 2, 3, 4, 1).half()
+    assert torch.equal(v.t.cpu(), ref)
+    if pad == (2, 1, 1) and N.device_supports_tc():
+        from hunyuanvideo_efficiency_b200.vae.blocks import CausalConv3d
+        torch.manual_seed(1)
+        conv = CausalConv3d(64, 128, 3).half().to(_dev())
+        xin = _vol(torch.randn(1, 64, 4, 20, 24), torch.float16, pad=(2, 1, 1))
+        y_pad = conv.forward_vol(xin, out_pad=pad)
+        y_ref = N.pad_upsample(conv.forward_vol(xin), (1, 1, 1), pad)
+        assert y_pad.pad == pad and torch.equal(y_pad.t, y_ref.t)
+
+
 def test_groupnorm_silu_fp32_and_halo():
     N = _N()
     g = torch.Generator().manual_seed(3)
