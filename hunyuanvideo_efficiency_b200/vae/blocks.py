@@ -427,11 +427,12 @@ class _Linear(nn.Module):
 
 
 def _gemm_nt(x: Vol, w: torch.Tensor, bias, cout: int, residual: Optional[Vol] = None, out_dtype=None,
-             out: Optional[Vol] = None) -> Vol:
-    """y[m][n] = sum_k x[m][k] * w[n][k] (+bias[n]) (+residual): a 1x1x1 'conv' on either kernel."""
+             out: Optional[Vol] = None, gn_groups: int = 0) -> Vol:
+    """y[m][n] = sum_k x[m][k] * w[n][k] (+bias[n]) (+residual): a 1x1x1 'conv' on either kernel.  gn_groups > 0 (tensor-core
+    path): GroupNorm statistics of y from the epilogue (y.gn_sums)."""
     rl = False
     if tc_eligible(x.dtype, x.C, cout, (1, 1, 1), 1) and x.pad == (0, 0, 0) and x.C % 8 == 0 and cout % 8 == 0:
-        return N.conv3d_tc(x, w, bias, 1, (1, 1, 1), cout, residual, out_dtype, rl, out=out)
+        return N.conv3d_tc(x, w, bias, 1, (1, 1, 1), cout, residual, out_dtype, rl, out=out, gn_groups=gn_groups)
     return N.conv3d_direct(x, w, bias, 1, (1, 1, 1), cout, residual, (1, 1, 1), out_dtype, rl, out=out)
 
 
@@ -454,6 +455,7 @@ class Attention(nn.Module):
         self.group_norm = _GroupNorm(norm_num_groups, query_dim, eps)
         self.to_q, self.to_k, self.to_v = _Linear(query_dim, dim_head), _Linear(query_dim, dim_head), _Linear(query_dim, dim_head)
         self.to_out = nn.ModuleList([_Linear(dim_head, query_dim), nn.Identity()])
+        self.emit_gn_groups = norm_num_groups or 0   # the consumer is the mid block's second resnet (same group count)
 
     @staticmethod
     def fused_eligible(dtype, L: int, Cn: int) -> bool:
@@ -492,7 +494,11 @@ class Attention(nn.Module):
                 o = _gemm_nt(pv, vt.t.reshape(Cn, L), bv, Cn)                             # rows of P sum to 1 => + bv
             res = Vol(1, 1, 1, L, Cn, x.dtype, x.device, tensor=x.t[b].reshape(1, 1, 1, L, Cn)) if self.residual_connection else None
             ob = Vol(1, 1, 1, L, Cn, x.dtype, x.device, tensor=out.t[b].reshape(1, 1, 1, L, Cn))
-            _gemm_nt(o, wo, bo, Cn, residual=res, out=ob)
+            # B == 1 (every tiled call): the out-projection's epilogue also emits the GroupNorm statistics that the next
+            # resnet's norm1 needs, so no separate statistics pass reads the result back
+            yb = _gemm_nt(o, wo, bo, Cn, residual=res, out=ob, gn_groups=self.emit_gn_groups if B == 1 else 0)
+            if B == 1 and yb.gn_sums is not None:
+                out.gn_sums, out.gn_groups = yb.gn_sums, yb.gn_groups
         return out
 
 

@@ -90,3 +90,21 @@ def test_posterior_matches_oracle():
     s = p.sample(g1)
     assert torch.equal(s, mean + torch.exp(0.5 * logvar) * torch.randn(mean.shape, generator=g2))
     assert p.kl().shape == (2,) and p.nll(s, dims=[1, 2, 3, 4]).shape == (2,)
+
+
+def test_run_tiles_keeps_order_and_degrades_to_sequential_without_cuda():
+    """run_tiles returns results in thunk order; with one stream (or no CUDA device, as here) it is a plain loop."""
+    from hunyuanvideo_efficiency_b200.vae.model import run_tiles
+    calls = []
+
+    def mk(i):
+        def f():
+            calls.append(i)
+            return torch.full((2,), float(i))
+        return f
+
+    for n_streams in (1, 2, 3):
+        calls.clear()
+        outs = run_tiles([mk(i) for i in range(5)], n_streams)
+        assert [int(o[0]) for o in outs] == list(range(5)) and calls == list(range(5))
+    assert run_tiles([], 2) == []
