@@ -82,3 +82,14 @@ def test_snapshot_restore_of_t_ops_state(tmp_path):
     assert all(c is None for c in m.decoder.up_blocks[0].resnet_interp_configs)
     p = S.write_metrics({"PSNR": 31.5, "SSIM": 0.9}, "in", "out", str(tmp_path / "exp_1"))
     assert open(p).read().splitlines()[1:5] == ["Root1: in", "Root2: out", "PSNR: 31.5", "SSIM: 0.9"]
+
+
+def test_metrics_refuse_cpu_tensors_and_sweep_cli_defaults():
+    """The product path has no CPU fallback: the GPU metrics raise on host tensors instead of silently using the oracle."""
+    import torch
+    from hunyuanvideo_efficiency_b200 import _native as N
+    from hunyuanvideo_efficiency_b200 import metrics as M
+    with pytest.raises(N.HyvaeError):
+        M.video_to_frames_u8(torch.zeros(3, 2, 8, 8))
+    args = S.parse_args(["--tensor-dir", "in", "--metrics-dir", "out"])
+    assert (args.mode, args.max_files, args.vae_precision, args.base_config) == ("pool", 100, "fp16", "t_ops_config.json")
