@@ -1,7 +1,7 @@
 """CPU study: which storage / operand rounding points dominate the 16-bit error of the VAE decoder.
 Emulates the GPU pipeline (fp32 accumulation everywhere) with explicit rounding hooks."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, torch.nn.functional as F
 from oracle import vae_oracle as O, weights as W
 torch.set_grad_enabled(False)

@@ -618,7 +618,7 @@ def test_model_16bit_vs_reference(name, dtype):
     assert O.rel_err(dec_exact, dec) < BF16_TOL and O.psnr(dec_exact, dec) > PSNR_MIN
     # (b) vs the fp32-weight golden: this also contains the error of rounding the WEIGHTS to 16 bits, which belongs
     # to the model the caller built (vae.to(dtype)), not to the implementation; fp16 still meets the tolerance,
-    # bf16 weights alone cost ~1e-2 / ~40 dB on random-init weights (tools/precision_study.py).
+    # bf16 weights alone cost ~1e-2 / ~40 dB on random-init weights (tests/dev/precision_study.py).
     mean_gold, _ = O.posterior_mean_logvar(a["moments"])
     dec_g = m.decode(mean_gold.to(_dev(), dtype)).sample.float().cpu()
     if dtype == torch.float16:
