@@ -63,3 +63,21 @@ def test_spec_has_248_keys():
     assert len(W.state_dict_spec(W.HY_VAE_CONFIG)) == 248
     n = sum(torch.Size(s).numel() for s in W.state_dict_spec(W.HY_VAE_CONFIG).values())
     assert n == 246_478_803  # SURVEY.md §8c [measured]
+
+
+def test_sdpa_restatement_matches_torch_sdpa_with_the_reference_mask():
+    """diffusers' AttnProcessor2_0 (third-party, not vendored) calls torch's F.scaled_dot_product_attention with the additive
+    mask of prepare_causal_attention_mask (unet_causal_3d_blocks.py:38-46, call site :661).  The oracle's restatement is
+    pinned here against that torch function itself, with the mask built the reference's way (row by row)."""
+    import torch
+    T, hw, D = 4, 6, 32
+    L = T * hw
+    g = torch.Generator().manual_seed(3)
+    q, k, v = (torch.randn(L, D, generator=g) for _ in range(3))
+    mask = torch.full((L, L), float("-inf"))
+    for i in range(L):                      # the reference's loop: mask[i, :(i // n_hw + 1) * n_hw] = 0
+        mask[i, :(i // hw + 1) * hw] = 0
+    ref = torch.nn.functional.scaled_dot_product_attention(q[None, None], k[None, None], v[None, None], attn_mask=mask[None, None])[0, 0]
+    out = O.sdpa_frame_causal(q, k, v, T, hw, D ** -0.5)
+    assert torch.allclose(out, ref, atol=1e-6, rtol=1e-5)
+    assert torch.equal(O.frame_causal_mask(T, hw), mask)
