@@ -24,6 +24,7 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "conv_internal.h"
@@ -57,18 +58,27 @@ template <int D> struct AttnCfg {
 
 struct AttnItem { int r0, half, nblk, lim_min; };
 
-// wave w of the snake deal: even waves run left to right over the CTAs, odd waves right to left
-template <int NSPLIT>
+// wave w of the snake deal: even waves run left to right over the CTAs, odd waves right to left.
+// MC (multicast pair): the unit that is dealt is a PAIR of adjacent query tiles (cluster rank r takes tile 2 qp + r); both
+// CTAs walk the key blocks of the later tile in lockstep, because each of them loads half of every K / V^T box and
+// multicasts it to both.  Blocks the earlier tile cannot see come out fully masked (P = 0) there.
+template <int NSPLIT, bool MC>
 __device__ __forceinline__ bool attn_item(const AttnArgs& a, int w, AttnItem& it) {
-  const int G = (int)gridDim.x, b = (int)blockIdx.x;
+  const int G = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x, b = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int i = w * G + ((w & 1) ? (G - 1 - b) : b);
   if (i >= a.n_items) return false;
-  const int qt = a.n_qt - 1 - i / NSPLIT;  // late query tiles see the most keys: they go first
   it.half = i % NSPLIT;
-  it.r0 = qt * 128;
-  const int rlast = min(it.r0 + 127, a.L - 1);
+  int rlast;
+  if (MC) {
+    const int qp = (a.n_qt + 1) / 2 - 1 - i / NSPLIT;
+    it.r0 = (2 * qp + (int)cluster_ctarank()) * 128;
+    rlast = min(2 * qp * 128 + 255, a.L - 1);
+  } else {
+    it.r0 = (a.n_qt - 1 - i / NSPLIT) * 128;  // late query tiles see the most keys: they go first
+    rlast = min(it.r0 + 127, a.L - 1);
+  }
   const int lim_max = (rlast / a.n_hw + 1) * a.n_hw;
-  it.lim_min = (it.r0 / a.n_hw + 1) * a.n_hw;
+  it.lim_min = (min(it.r0, a.L - 1) / a.n_hw + 1) * a.n_hw;
   it.nblk = (lim_max + 127) / 128;
   return true;
 }
@@ -83,7 +93,7 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, fl
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <typename T, int D>
+template <typename T, int D, bool MC>
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
@@ -110,7 +120,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    for (int s = 0; s < NSLOT; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    // MC: a slot is refilled by BOTH CTAs' multicasts, so it is free only when both CTAs' MMAs have read it
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, MC ? 2 : 1); }
     mbar_init(q_full, 1); mbar_init(q_free, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(s_full + 8 * s, 1); mbar_init(s_free + 8 * s, 128); }
     mbar_init(p_full, 128); mbar_init(p_free, 1);
@@ -121,10 +132,12 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();  // the peer's barriers exist before anything remote (multicast TMA, commit) touches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t t_o = tmem_base, t_s = tmem_base + 256;  // O: columns [0, DVH); S buffers: [256, 384), [384, 512)
-  const int G = (int)gridDim.x;
+  const int G = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
 
   if (warp == 0) {
     // ================= TMA producer: the ring order is exactly the MMA issue order =================
@@ -132,7 +145,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     int it = 0;
     for (int w = 0; w * G < a.n_items; ++w) {
       AttnItem im;
-      if (!attn_item<Cfg::NSPLIT>(a, w, im)) continue;
+      if (!attn_item<Cfg::NSPLIT, MC>(a, w, im)) continue;
       mbar_wait(q_free, (uint32_t)((it & 1) ^ 1));  // every S MMA of the previous item has read the old Q tile
       if (elect_one()) {
         mbar_expect_tx(q_full, Cfg::Q_BYTES);
@@ -144,8 +157,11 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const uint32_t slot = cnt % NSLOT, ph = (cnt / NSLOT) & 1;
         mbar_wait(empty_bar + 8 * slot, ph ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(full_bar + 8 * slot, SLOT_BYTES);
-          tma_load_2d(ring + slot * SLOT_BYTES, tm, full_bar + 8 * slot, c0, c1);
+          mbar_expect_tx(full_bar + 8 * slot, SLOT_BYTES);  // MC: 8 KB from this CTA's load + 8 KB from the peer's
+          if constexpr (MC)  // `tm` has a 64-row box: this CTA fetches rows [64 r, 64 r + 64) of the box for both CTAs
+            tma_load_2d_mc(ring + slot * SLOT_BYTES + crank * (SLOT_BYTES / 2), tm, full_bar + 8 * slot, c0, c1 + (int)crank * 64, (uint16_t)3);
+          else
+            tma_load_2d(ring + slot * SLOT_BYTES, tm, full_bar + 8 * slot, c0, c1);
         }
         __syncwarp();
         ++cnt;
@@ -172,7 +188,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     int it = 0;
     for (int w = 0; w * G < a.n_items; ++w) {
       AttnItem im;
-      if (!attn_item<Cfg::NSPLIT>(a, w, im)) continue;
+      if (!attn_item<Cfg::NSPLIT, MC>(a, w, im)) continue;
       mbar_wait(q_full, (uint32_t)(it & 1));
       tc_fence_after();
       auto issue_s = [&](int j) {
@@ -189,7 +205,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             const uint64_t bdesc = make_kmajor_sw128_desc(ring + slot * SLOT_BYTES);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, (kc | k) != 0);
-            umma_commit(empty_bar + 8 * slot);
+            if constexpr (MC) umma_commit_mc(empty_bar + 8 * slot, (uint16_t)3); else umma_commit(empty_bar + 8 * slot);
           }
           __syncwarp();
           ++cnt;
@@ -216,7 +232,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16(t_o, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_o, (j | c | k) != 0);
 #pragma unroll
-            for (int v = 0; v < VS; ++v) umma_commit(empty_bar + 8 * (slot + v));
+            for (int v = 0; v < VS; ++v) {
+              if constexpr (MC) umma_commit_mc(empty_bar + 8 * (slot + v), (uint16_t)3); else umma_commit(empty_bar + 8 * (slot + v));
+            }
           }
           __syncwarp();
           cnt += VS;
@@ -247,7 +265,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     T* od = reinterpret_cast<T*>(a.o);
     for (int w = 0; w * G < a.n_items; ++w) {
       AttnItem im;
-      if (!attn_item<Cfg::NSPLIT>(a, w, im)) continue;
+      if (!attn_item<Cfg::NSPLIT, MC>(a, w, im)) continue;
       const int grow = im.r0 + row;
       const int lim_r = grow < a.L ? (grow / a.n_hw + 1) * a.n_hw : a.L;
       float m_run = 0.f, l = 0.f;
@@ -366,6 +384,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -388,30 +407,43 @@ static EncodeTiledFn attn_encode_fn() {
   return fn;
 }
 
-// row-major [rows][cols] 16-bit matrix, box {64 columns, 128 rows}; rows / columns beyond the matrix are zero-filled
-static int encode_rows_map(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, int64_t rows, int64_t cols, const char* what) {
+// row-major [rows][cols] 16-bit matrix, box {64 columns, box_rows rows}; rows / columns beyond the matrix are zero-filled
+static int encode_rows_map(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, int64_t rows, int64_t cols, const char* what,
+                           int box_rows = 128) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {64, 128};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = attn_encode_fn()(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(%s) failed with %d", what, (int)r);
 }
 
-template <typename T, int D>
+template <typename T, int D, bool MC>
 static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, AttnArgs a, cudaStream_t stream) {
   using Cfg = AttnCfg<D>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn_fused_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(attn_fused_kernel<T, D, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
       return fail(HYVAE_ECUDA, "attn_fused: cannot opt in to %d bytes of shared memory", Cfg::SMEM_BYTES);
     attr_set = true;
   }
-  a.n_items = a.n_qt * Cfg::NSPLIT;
-  const int grid = a.n_items < num_sms() ? a.n_items : num_sms();
-  attn_fused_kernel<T, D><<<(unsigned)grid, ATTN_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
-  return check_launch("attn_block_causal");
+  if (!MC) {
+    a.n_items = a.n_qt * Cfg::NSPLIT;
+    const int grid = a.n_items < num_sms() ? a.n_items : num_sms();
+    attn_fused_kernel<T, D, false><<<(unsigned)grid, ATTN_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, a);
+    return check_launch("attn_block_causal");
+  }
+  // multicast pair form: clusters of two CTAs, one PAIR of query tiles per item
+  a.n_items = ((a.n_qt + 1) / 2) * Cfg::NSPLIT;
+  const int pairs = a.n_items < num_sms() / 2 ? a.n_items : num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs)); cfg.blockDim = dim3(ATTN_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, attn_fused_kernel<T, D, true>, tmQ, tmK, tmV, a) != cudaSuccess) { /* reported by check_launch */ }
+  return check_launch("attn_block_causal (multicast pair)");
 }
 
 }  // namespace hyvae
@@ -429,10 +461,17 @@ extern "C" int hyvae_attn_block_causal(const void* q, const void* k, const void*
     return fail(HYVAE_EUNSUPPORTED, "attn_block_causal: D=%d / L=%lld not covered by the fused kernel (D in {128,256,512}, L %% 8 == 0)", D, (long long)L);
   if (!attn_encode_fn()) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const CUtensorMapDataType dt = dtype == HYVAE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  // HYVAE_ATTN_MULTICAST=1 (experiment, default off): CTA pairs that multicast the K / V^T boxes to each other, halving the
+  // L2 -> SM TMA traffic (3.9 GB per launch at L = 17408, profiles/r01_ncu_attn_fused_512.txt).  Measured: correct, but only
+  // 0.428 -> 0.415 ms — the kernel is not bound by L2 bandwidth but by the shared-memory port (an N = 128 MMA reads its
+  // 8 KB of operands in 64 cycles = the whole port, and the TMA fill of the ring competes with it), which multicast does
+  // not relieve; cta_group::2 MMAs (half of the B operand per CTA) would.
+  static const bool mc_env = [] { const char* e = getenv("HYVAE_ATTN_MULTICAST"); return e != nullptr && e[0] == '1'; }();
+  const bool mc = mc_env && D == 512;  // the pair form is only instantiated for the production head width
   CUtensorMap tmQ, tmK, tmV;
   if (int e = encode_rows_map(&tmQ, dt, q, L, D, "Q")) return e;
-  if (int e = encode_rows_map(&tmK, dt, k, L, D, "K")) return e;
-  if (int e = encode_rows_map(&tmV, dt, vt, D, L, "V^T")) return e;
+  if (int e = encode_rows_map(&tmK, dt, k, L, D, "K", mc ? 64 : 128)) return e;
+  if (int e = encode_rows_map(&tmV, dt, vt, D, L, "V^T", mc ? 64 : 128)) return e;
   AttnArgs a;
   a.o = o; a.bv = bv; a.L = (int)L; a.n_hw = n_hw; a.n_qt = (int)((L + 127) / 128); a.n_items = 0;
   a.c = scale * 1.4426950408889634f;
@@ -440,12 +479,16 @@ extern "C" int hyvae_attn_block_causal(const void* q, const void* k, const void*
   snprintf(tag, sizeof(tag), "attn fused L=%lld n_hw=%d D=%d", (long long)L, n_hw, D);
   ProfScope prof(PC_ATTN, 4.0 * (double)L * (double)L * D, stream, tag);  // dense SDPA flops, not halved for causality
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == HYVAE_F16) {
-    if (D == 512) return launch_attn<__half, 512>(tmQ, tmK, tmV, a, st);
-    if (D == 256) return launch_attn<__half, 256>(tmQ, tmK, tmV, a, st);
-    return launch_attn<__half, 128>(tmQ, tmK, tmV, a, st);
+  if (mc) {
+    if (dtype == HYVAE_F16) return launch_attn<__half, 512, true>(tmQ, tmK, tmV, a, st);
+    return launch_attn<__nv_bfloat16, 512, true>(tmQ, tmK, tmV, a, st);
   }
-  if (D == 512) return launch_attn<__nv_bfloat16, 512>(tmQ, tmK, tmV, a, st);
-  if (D == 256) return launch_attn<__nv_bfloat16, 256>(tmQ, tmK, tmV, a, st);
-  return launch_attn<__nv_bfloat16, 128>(tmQ, tmK, tmV, a, st);
+  if (dtype == HYVAE_F16) {
+    if (D == 512) return launch_attn<__half, 512, false>(tmQ, tmK, tmV, a, st);
+    if (D == 256) return launch_attn<__half, 256, false>(tmQ, tmK, tmV, a, st);
+    return launch_attn<__half, 128, false>(tmQ, tmK, tmV, a, st);
+  }
+  if (D == 512) return launch_attn<__nv_bfloat16, 512, false>(tmQ, tmK, tmV, a, st);
+  if (D == 256) return launch_attn<__nv_bfloat16, 256, false>(tmQ, tmK, tmV, a, st);
+  return launch_attn<__nv_bfloat16, 128, false>(tmQ, tmK, tmV, a, st);
 }
