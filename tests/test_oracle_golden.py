@@ -81,3 +81,24 @@ def test_sdpa_restatement_matches_torch_sdpa_with_the_reference_mask():
     out = O.sdpa_frame_causal(q, k, v, T, hw, D ** -0.5)
     assert torch.allclose(out, ref, atol=1e-6, rtol=1e-5)
     assert torch.equal(O.frame_causal_mask(T, hw), mask)
+
+
+def test_winograd_t_algebra_matches_the_causal_conv():
+    """oracle/winograd.py (the F(2,3)-along-T form a round-2 kernel has to follow) == the plain causal conv, in fp64, for even,
+    odd and single-frame T; with fp16-rounded transformed operands it stays within 2x of the direct fp16 evaluation."""
+    import torch
+    from oracle import winograd as WG
+    torch.manual_seed(0)
+    for T in (1, 2, 5, 8):
+        x = torch.randn(2, 6, T, 7, 9, dtype=torch.float64)
+        w = torch.randn(5, 6, 3, 3, 3, dtype=torch.float64) / 10
+        b = torch.randn(5, dtype=torch.float64)
+        ref = O.causal_conv3d(x, w, b)
+        assert torch.allclose(WG.causal_conv3d_winograd_t(x, w, b), ref, atol=1e-12, rtol=1e-10)
+    x = torch.nn.functional.silu(torch.randn(1, 32, 6, 10, 10))
+    w = torch.randn(32, 32, 3, 3, 3) / (27 * 32) ** 0.5
+    ref = O.causal_conv3d(x, w, None)
+    h = lambda t: t.half().float()
+    e_direct = O.rel_err(ref, O.causal_conv3d(h(x), h(w), None))
+    e_wino = O.rel_err(ref, WG.causal_conv3d_winograd_t(x, w, None, rnd=h))
+    assert e_wino < 2 * e_direct + 1e-4, (e_wino, e_direct)
