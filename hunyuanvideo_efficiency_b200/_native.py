@@ -57,7 +57,8 @@ _SIGNATURES = {
     "hyvae_interp_t_nearest": [_VP, _VP, _f32, _vp],
     "hyvae_image_postprocess": [_vp, _i32, _vp, _i64, _vp],
     "hyvae_blend_crop_scatter": [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32,
-                                 _i32, _i32, _i32, _i32, C.POINTER(_i64), _vp],
+                                 _i32, _i32, _i32, _i32, C.POINTER(_i64), _i32, _vp],
+    "hyvae_profile_class_override": [_i32],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["hyvae_version", "hyvae_last_error", "hyvae_device_supports_tc", "hyvae_launch_count",
                                        "hyvae_groupnorm_workspace_bytes", "hyvae_profile_begin", "hyvae_profile_end", "hyvae_profile_executed_flops",
@@ -107,7 +108,7 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-PROFILE_CLASSES = ("conv_tc", "conv_direct", "gn_stats", "gn_apply", "pad_upsample", "softmax", "layout", "blend", "temporal", "attn")
+PROFILE_CLASSES = ("conv_tc", "conv_direct", "gn_stats", "gn_apply", "pad_upsample", "softmax", "layout", "blend", "temporal", "attn", "attn_proj")
 
 
 def profile_begin():
@@ -124,6 +125,20 @@ def profile_end() -> dict:
     out = {k: {"ms": ms[i], "work": work[i], "launches": int(cnt[i])} for i, k in enumerate(PROFILE_CLASSES)}
     out["conv_tc"]["executed"] = float(lib().hyvae_profile_executed_flops())
     return out
+
+
+class profile_class:
+    """with profile_class("attn_proj"): conv launches inside are booked under that profile class (measurement only)."""
+
+    def __init__(self, name: str):
+        self.idx = PROFILE_CLASSES.index(name)
+
+    def __enter__(self):
+        lib().hyvae_profile_class_override(self.idx)
+
+    def __exit__(self, *exc):
+        lib().hyvae_profile_class_override(-1)
+        return False
 
 
 def launch_count() -> int:
@@ -228,7 +243,7 @@ def conv3d_direct(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, resi
     return y
 
 
-ABI_VERSION = 110      # HYVAE_VERSION of include/hyvae.h this module binds
+ABI_VERSION = 120      # HYVAE_VERSION of include/hyvae.h this module binds
 VARIANT_KWPACK = 0x200  # hyvae_conv3d_causal_tc: x is a kw-packed thin volume (Vol.from_ncthw(kw_pack=True)), w is [9][Cout][16]
 VARIANT_TFOLD = 0x100  # hyvae_conv3d_causal_tc: `w` carries the 18 folded first-frame tap slices after the 27 (include/hyvae.h)
 _GN_PART = {}
@@ -244,25 +259,52 @@ def _gn_partials(B: int, rows: int, groups: int, device) -> torch.Tensor:
     return buf
 
 
+class _GnEpilogue:
+    """GroupNorm statistics of a conv's output from its epilogue.  `sums` is allocated BEFORE any launch, and a failure
+    between the first conv launch and hyvae_groupnorm_finalize (which re-zeroes the partial buffer) drops the cached
+    buffer, so a failed call (e.g. an out-of-memory error the caller catches before retrying with tiling) cannot leave
+    partial sums behind that would poison every later statistic on that stream."""
+
+    def __init__(self, x: Vol, cout: int, gn_groups: int, min_cpg: int):
+        self.part = self.sums = None
+        self.rows, self.groups, self.B, self.device = 0, 0, x.B, x.device
+        if gn_groups > 0 and cout % gn_groups == 0 and (cout // gn_groups) in (1, 2, 4, 8, 16, 32) and cout // gn_groups >= min_cpg:
+            self.sums = torch.empty((x.B, gn_groups, 2), dtype=torch.float64, device=x.device)
+            self.rows = int(lib().hyvae_conv3d_tc_gn_rows())
+            self.groups = gn_groups
+            self.part = _gn_partials(x.B, self.rows, gn_groups, x.device)
+
+    def args(self):
+        return _ptr(self.part), self.groups
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is not None and self.part is not None:
+            _GN_PART.pop((self.device, torch.cuda.current_stream(self.device).cuda_stream, self.B, self.rows, self.groups), None)
+        return False
+
+    def finalize(self, y: Vol):
+        if self.part is not None:
+            _check(lib().hyvae_groupnorm_finalize(self.part.data_ptr(), self.B, self.rows, self.groups, self.sums.data_ptr(), _stream()),
+                   "groupnorm_finalize")
+            y.gn_sums, y.gn_groups = self.sums, self.groups
+        return y
+
+
 def conv3d_tc(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, residual: Optional[Vol] = None,
               out_dtype=None, round_like_ref=True, variant=0, out: Optional[Vol] = None, gn_groups: int = 0) -> Vol:
     """gn_groups > 0: the epilogue also emits GroupNorm partial statistics of y; they are reduced here
     (hyvae_groupnorm_finalize) and travel with the returned volume (y.gn_sums), sparing the consumer's stats pass."""
     To, Ho, Wo = conv_out_dims(x.T, x.H, x.W, stride)
     y = out if out is not None else Vol(x.B, To, Ho, Wo, cout, out_dtype or x.dtype, x.device)
-    part, rows = None, 0
-    if gn_groups > 0 and cout % gn_groups == 0 and (cout // gn_groups) in (1, 2, 4, 8, 16, 32):
-        rows = int(lib().hyvae_conv3d_tc_gn_rows())
-        part = _gn_partials(x.B, rows, gn_groups, x.device)
-    _check(lib().hyvae_conv3d_causal_tc(x.ref(), w.data_ptr(), _ptr(bias), residual.ref() if residual else None, y.ref(),
-                                        k, stride[0], stride[1], stride[2], int(round_like_ref), variant,
-                                        _ptr(part), gn_groups if part is not None else 0, _stream()),
-           "conv3d_causal_tc")
-    if part is not None:
-        sums = torch.empty((x.B, gn_groups, 2), dtype=torch.float64, device=x.device)
-        _check(lib().hyvae_groupnorm_finalize(part.data_ptr(), x.B, rows, gn_groups, sums.data_ptr(), _stream()), "groupnorm_finalize")
-        y.gn_sums, y.gn_groups = sums, gn_groups
-    return y
+    with _GnEpilogue(x, cout, gn_groups, 1) as gn:
+        part, groups = gn.args()
+        _check(lib().hyvae_conv3d_causal_tc(x.ref(), w.data_ptr(), _ptr(bias), residual.ref() if residual else None, y.ref(),
+                                            k, stride[0], stride[1], stride[2], int(round_like_ref), variant, part, groups, _stream()),
+               "conv3d_causal_tc")
+        return gn.finalize(y)
 
 
 def conv3d_tc_shortcut(x: Vol, w: torch.Tensor, bias: torch.Tensor, sc_x: Vol, sc_w: torch.Tensor, cout: int, gn_groups: int = 0,
@@ -270,18 +312,11 @@ def conv3d_tc_shortcut(x: Vol, w: torch.Tensor, bias: torch.Tensor, sc_x: Vol, s
     """y = conv3x3x3(x) + conv1x1x1(sc_x) + bias in one launch (the resnet block's conv2 with its conv_shortcut).
     out_pad: y is allocated with that halo and only its interior is written (the caller runs halo_fill)."""
     y = Vol(x.B, x.T, x.H, x.W, cout, x.dtype, x.device, out_pad)
-    part, rows = None, 0
-    if gn_groups > 0 and cout % gn_groups == 0 and (cout // gn_groups) in (2, 4, 8, 16, 32):
-        rows = int(lib().hyvae_conv3d_tc_gn_rows())
-        part = _gn_partials(x.B, rows, gn_groups, x.device)
-    _check(lib().hyvae_conv3d_causal_tc_shortcut(x.ref(), w.data_ptr(), _ptr(bias), sc_x.ref(), sc_w.data_ptr(), y.ref(),
-                                                 _ptr(part), gn_groups if part is not None else 0, int(tfold), _stream()),
-           "conv3d_causal_tc_shortcut")
-    if part is not None:
-        sums = torch.empty((x.B, gn_groups, 2), dtype=torch.float64, device=x.device)
-        _check(lib().hyvae_groupnorm_finalize(part.data_ptr(), x.B, rows, gn_groups, sums.data_ptr(), _stream()), "groupnorm_finalize")
-        y.gn_sums, y.gn_groups = sums, gn_groups
-    return y
+    with _GnEpilogue(x, cout, gn_groups, 2) as gn:
+        part, groups = gn.args()
+        _check(lib().hyvae_conv3d_causal_tc_shortcut(x.ref(), w.data_ptr(), _ptr(bias), sc_x.ref(), sc_w.data_ptr(), y.ref(),
+                                                     part, groups, int(tfold), _stream()), "conv3d_causal_tc_shortcut")
+        return gn.finalize(y)
 
 
 def conv3d_upsample_phases(x: Vol, phase_w, bias, up, cout: int, gn_groups: int = 0) -> Vol:
@@ -290,19 +325,12 @@ def conv3d_upsample_phases(x: Vol, phase_w, bias, up, cout: int, gn_groups: int 
     assert up[1] == 2 and up[2] == 2 and up[0] in (1, 2)
     T = 2 * x.T - 1 if up[0] == 2 else x.T
     y = Vol(x.B, T, 2 * x.H, 2 * x.W, cout, x.dtype, x.device)
-    part, rows = None, 0
-    if gn_groups > 0 and cout % gn_groups == 0 and (cout // gn_groups) in (2, 4, 8, 16, 32):
-        rows = int(lib().hyvae_conv3d_tc_gn_rows())
-        part = _gn_partials(x.B, rows, gn_groups, x.device)
-    for (pt, ph, pw), w in phase_w.items():
-        _check(lib().hyvae_conv3d_upphase_tc(x.ref(), w.data_ptr(), _ptr(bias), y.ref(), up[0], pt, ph, pw,
-                                             _ptr(part), gn_groups if part is not None else 0, _stream()),
-               "conv3d_upphase_tc")
-    if part is not None:
-        sums = torch.empty((x.B, gn_groups, 2), dtype=torch.float64, device=x.device)
-        _check(lib().hyvae_groupnorm_finalize(part.data_ptr(), x.B, rows, gn_groups, sums.data_ptr(), _stream()), "groupnorm_finalize")
-        y.gn_sums, y.gn_groups = sums, gn_groups
-    return y
+    with _GnEpilogue(x, cout, gn_groups, 2) as gn:
+        part, groups = gn.args()
+        for (pt, ph, pw), w in phase_w.items():
+            _check(lib().hyvae_conv3d_upphase_tc(x.ref(), w.data_ptr(), _ptr(bias), y.ref(), up[0], pt, ph, pw, part, groups, _stream()),
+                   "conv3d_upphase_tc")
+        return gn.finalize(y)
 
 
 def groupnorm(x: Vol, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
@@ -401,17 +429,22 @@ def interp_t_nearest(x: Vol, scale: float) -> Vol:
 
 
 def blend_crop_scatter(cur: torch.Tensor, above, left, N: int, Yc: int, Xc: int, Ya: int, Xl: int, ev: int, eh: int,
-                       out, Yo: int, Xo: int, y0: int, x0: int, crop_y: int, crop_x: int, n_strides=None):
+                       out, Yo: int, Xo: int, y0: int, x0: int, crop_y: int, crop_x: int, n_strides=None, post: bool = False):
+    """post: `out` is an fp32 tensor that receives float((v / 2 + 0.5).clamp(0, 1)) (the pipeline tail's image)."""
     ns = (_i64 * 4)(*n_strides) if n_strides is not None else None
+    if post and (out is None or out.dtype != torch.float32):
+        raise HyvaeError("blend_crop_scatter(post=True) writes an fp32 image")
+    if not post and out is not None and out.dtype != cur.dtype:
+        raise HyvaeError("blend_crop_scatter: out must have the tile dtype")
     _check(lib().hyvae_blend_crop_scatter(cur.data_ptr(), _ptr(above), _ptr(left), _DT[cur.dtype], N, Yc, Xc, Ya, Xl, ev, eh,
-                                          _ptr(out), Yo, Xo, y0, x0, crop_y, crop_x, ns, _stream()), "blend_crop_scatter")
+                                          _ptr(out), Yo, Xo, y0, x0, crop_y, crop_x, ns, int(post), _stream()), "blend_crop_scatter")
 
 
 def image_postprocess(image: torch.Tensor) -> torch.Tensor:
     """float((image / 2 + 0.5).clamp(0, 1)) in one pass (pipeline_hunyuan_video.py:1090-1092); returns fp32 on the device."""
-    assert image.is_cuda and image.is_contiguous()
-    if image.numel() % 8 or image.dtype == torch.float32:
-        return (image / 2 + 0.5).clamp(0, 1).float()
+    if not image.is_cuda:
+        raise HyvaeError("image_postprocess runs on CUDA tensors; there is no CPU execution path")
+    image = image.contiguous()
     out = torch.empty(image.shape, dtype=torch.float32, device=image.device)
     _check(lib().hyvae_image_postprocess(image.data_ptr(), _DT[image.dtype], out.data_ptr(), image.numel(), _stream()), "image_postprocess")
     return out

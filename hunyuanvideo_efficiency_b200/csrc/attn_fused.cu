@@ -422,11 +422,11 @@ static int encode_rows_map(CUtensorMap* tm, CUtensorMapDataType dt, const void* 
 template <typename T, int D, bool MC>
 static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, AttnArgs a, cudaStream_t stream) {
   using Cfg = AttnCfg<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     if (cudaFuncSetAttribute(attn_fused_kernel<T, D, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
       return fail(HYVAE_ECUDA, "attn_fused: cannot opt in to %d bytes of shared memory", Cfg::SMEM_BYTES);
-    attr_set = true;
+    attr_once.done();
   }
   if (!MC) {
     a.n_items = a.n_qt * Cfg::NSPLIT;

@@ -40,7 +40,8 @@ inline int check_launch(const char* what) {
 
 // ---- optional per-kernel-class timing (CUDA events on the launching stream; bench.py's roofline leg) ----
 enum ProfClass { PC_CONV_TC = 0, PC_CONV_DIRECT, PC_GN_STATS, PC_GN_APPLY, PC_PAD_UPSAMPLE, PC_SOFTMAX, PC_LAYOUT, PC_BLEND,
-                 PC_TEMPORAL, PC_ATTN, PC_COUNT };
+                 PC_TEMPORAL, PC_ATTN, PC_ATTN_PROJ, PC_COUNT };
+extern int g_prof_class_override;  // >= 0: conv launches are booked under this class (hyvae_profile_class_override)
 struct ProfRec { cudaEvent_t a, b; int cls; double work; char tag[56]; };
 extern bool g_prof_on;
 extern double g_prof_exec_flops;  // tensor-core MACs*2 actually issued while profiling (<= algorithmic work: sub-pixel phases)
@@ -57,6 +58,7 @@ struct ProfScope {
   bool on; cudaStream_t st; ProfRec r;
   ProfScope(int cls, double work, void* stream, const char* tag = "", double executed = -1.0) : on(g_prof_on), st((cudaStream_t)stream) {
     if (on) {
+      if ((cls == PC_CONV_TC || cls == PC_CONV_DIRECT) && g_prof_class_override >= 0) cls = g_prof_class_override;
       if (cls == PC_CONV_TC) g_prof_exec_flops += executed >= 0.0 ? executed : work;
       r.cls = cls; r.work = work; r.a = prof_event(); r.b = prof_event();
       snprintf(r.tag, sizeof(r.tag), "%s", tag);
@@ -164,15 +166,29 @@ template <> struct Vec8<__half> {
     else { using T = float; __VA_ARGS__; }                              \
   } while (0)
 
-inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+// Per-DEVICE caches: function attributes (the >48 KB shared-memory opt-in) and the SM count belong to the device a call
+// runs on, not to the process (a model moved to cuda:1, or a single-process multi-GPU driver).
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
+inline int num_sms() {
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
+  }
+  return n[dev];
+}
+// `static DeviceOnce once; if (once.first()) { cudaFuncSetAttribute(...) ... once.done(); }`
+struct DeviceOnce {
+  bool set[kMaxDevices] = {};
+  int dev = 0;
+  bool first() { dev = current_device(); return !set[dev]; }
+  void done() { set[dev] = true; }
+};
 
 }  // namespace hyvae

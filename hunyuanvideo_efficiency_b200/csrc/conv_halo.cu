@@ -441,11 +441,11 @@ template <typename T, int BN, int MT, bool PAIR, bool THIN = false>
 static int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
                          const CUtensorMap& tmX, const CUtensorMap& tmW, const HaloArgs& a, cudaStream_t stream) {
   using Cfg = HaloCfg<BN, MT, PAIR, THIN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     if (cudaFuncSetAttribute(conv_halo_kernel<T, BN, MT, PAIR, THIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
       return fail(HYVAE_ECUDA, "conv_halo: cannot opt in to %d bytes of shared memory", Cfg::SMEM_BYTES);
-    attr_set = true;
+    attr_once.done();
   }
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];

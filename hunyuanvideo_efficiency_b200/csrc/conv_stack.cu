@@ -206,11 +206,11 @@ int launch_conv_stack(int dtype, const CUtensorMap& tmA, const CUtensorMap& tmB,
   const int64_t grid = a.total < num_sms() ? a.total : num_sms();
 #define HYVAE_STACK_LAUNCH(T)                                                                                                        \
   {                                                                                                                                  \
-    static bool attr_set = false;                                                                                                    \
-    if (!attr_set) {                                                                                                                 \
+    static DeviceOnce attr_once;                                                                                                    \
+    if (attr_once.first()) {                                                                                                                 \
       if (cudaFuncSetAttribute(conv_stack_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, stack::SMEM_BYTES) != cudaSuccess) \
         return fail(HYVAE_ECUDA, "conv_stack: cannot opt in to %d bytes of shared memory", stack::SMEM_BYTES);                       \
-      attr_set = true;                                                                                                               \
+      attr_once.done();                                                                                                               \
     }                                                                                                                                \
     conv_stack_kernel<T><<<(unsigned)grid, stack::THREADS, stack::SMEM_BYTES, stream>>>(tmA, tmB, a, (T*)y, ysB, ysT, ysH, ysW, yoff); \
   }

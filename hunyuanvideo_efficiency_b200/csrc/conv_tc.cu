@@ -656,11 +656,11 @@ static EncodeTiledFn get_encode_fn() {
 template <typename T, typename OT, int BN, int MT>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
   using Cfg = TcCfg<BN, MT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     if (cudaFuncSetAttribute(conv_tc_kernel<T, OT, BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
       return fail(HYVAE_ECUDA, "conv_tc: cannot opt in to %d bytes of shared memory", Cfg::SMEM_BYTES);
-    attr_set = true;
+    attr_once.done();
   }
   int64_t grid = a.total_tiles < num_sms() ? a.total_tiles : num_sms();
   conv_tc_kernel<T, OT, BN, MT><<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, a);
@@ -685,11 +685,11 @@ template <typename T, typename OT, int BN, bool KHT>
 static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream,
                       const CUtensorMap* tmX = nullptr, const CUtensorMap* tmW = nullptr) {
   using Cfg = Tc2Cfg<BN, KHT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     if (cudaFuncSetAttribute(conv_tc2_kernel<T, OT, BN, KHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
       return fail(HYVAE_ECUDA, "conv_tc2: cannot opt in to %d bytes of shared memory", Cfg::SMEM_BYTES);
-    attr_set = true;
+    attr_once.done();
   }
   const int64_t max_pairs = num_sms() / 2;
   const int64_t pairs = a.total_tiles < max_pairs ? a.total_tiles : max_pairs;

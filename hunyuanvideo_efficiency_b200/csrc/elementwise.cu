@@ -5,6 +5,8 @@
 // reference's F.pad(replicate) copies (unet_causal_3d_blocks.py:74) into index arithmetic.
 #include <cstdlib>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace hyvae {
@@ -12,6 +14,7 @@ namespace hyvae {
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 bool g_prof_on = false;
+int g_prof_class_override = -1;
 double g_prof_exec_flops = 0.0;
 std::vector<ProfRec> g_prof;
 std::vector<cudaEvent_t> g_prof_pool;
@@ -476,11 +479,16 @@ __device__ __forceinline__ float blend2(float a, float b, int y, int e) {
   return rnd<T>(__fadd_rn(rnd<T>(__fmul_rn(a, wa)), rnd<T>(__fmul_rn(b, wb))));
 }
 
-template <typename T>
+// POST: the scattered output is the pipeline tail's image, float((v / 2 + 0.5).clamp(0, 1)) with the sum rounded in the tile
+// dtype like the tensor op (pipeline_hunyuan_video.py:1090-1092), written as fp32: the last assembly kernel of a decode
+// then emits the final image and no separate post-process pass reads the video back.
+template <typename T> __device__ __forceinline__ float post_image(float v) { return fminf(fmaxf(rnd<T>(fmaf(v, 0.5f, 0.5f)), 0.f), 1.f); }
+
+template <typename T, bool POST>
 __global__ void blend_crop_scatter_kernel(T* __restrict__ cur, const T* __restrict__ above, const T* __restrict__ left,
                                           int64_t N, int Yc, int Xc, int Ya, int Xl, int ev, int eh,
-                                          T* __restrict__ out, int Yo, int Xo, int y0, int x0, int crop_y, int crop_x,
-                                          int64_t cur_ns, int64_t above_ns, int64_t left_ns, int64_t out_ns) {
+                                          typename std::conditional<POST, float, T>::type* __restrict__ out, int Yo, int Xo, int y0, int x0,
+                                          int crop_y, int crop_x, int64_t cur_ns, int64_t above_ns, int64_t left_ns, int64_t out_ns) {
   const int64_t total = N * Yc * Xc;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int x = (int)(i % Xc); int64_t r = i / Xc;
@@ -497,7 +505,10 @@ __global__ void blend_crop_scatter_kernel(T* __restrict__ cur, const T* __restri
       mod = true;
     }
     if (mod) cur[ci] = from_f<T>(v);
-    if (out != nullptr && y < crop_y && x < crop_x) out[n * out_ns + (int64_t)(y0 + y) * Xo + (x0 + x)] = from_f<T>(v);
+    if (out != nullptr && y < crop_y && x < crop_x) {
+      if constexpr (POST) out[n * out_ns + (int64_t)(y0 + y) * Xo + (x0 + x)] = post_image<T>(v);
+      else out[n * out_ns + (int64_t)(y0 + y) * Xo + (x0 + x)] = from_f<T>(v);
+    }
   }
 }
 
@@ -506,14 +517,16 @@ __global__ void blend_crop_scatter_kernel(T* __restrict__ cur, const T* __restri
 // (pipeline_hunyuan_video.py:1090-1092) as ONE pass: 16-bit in, fp32 out.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) image_postprocess_kernel(const T* __restrict__ src, float* __restrict__ dst, int64_t n8) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(256) image_postprocess_kernel(const T* __restrict__ src, float* __restrict__ dst, int64_t n8, int64_t n) {
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n8; i += nthr) {  // 8-element vectors (n8 = 0 when a pointer is not 16-byte aligned)
     Vec8<T> q; q.load(src + i * 8);
     float f[8]; q.get(f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fminf(fmaxf(rnd<T>(fmaf(f[j], 0.5f, 0.5f)), 0.f), 1.f);  // x/2 is exact; the sum rounds like the tensor op
+    for (int j = 0; j < 8; ++j) f[j] = post_image<T>(f[j]);  // x/2 is exact; the sum rounds like the tensor op
     Vec8<float> o; o.set(f); o.store(dst + i * 8);
   }
+  for (int64_t i = n8 * 8 + tid; i < n; i += nthr) dst[i] = post_image<T>(to_f<T>(src[i]));  // tail / unaligned: scalar
 }
 
 }  // namespace hyvae
@@ -539,11 +552,19 @@ int hyvae_profile_begin(void) {
 
 double hyvae_profile_executed_flops(void) { return g_prof_exec_flops; }
 
+int hyvae_profile_class_override(int32_t cls) {
+  HYVAE_CHECK_ARG(cls >= -1 && cls < PC_COUNT, "profile class %d out of range", cls);
+  g_prof_class_override = cls;
+  return HYVAE_OK;
+}
+
 int hyvae_profile_end(double* ms, double* work, int64_t* launches, int32_t n_classes) {
   g_prof_on = false;
   HYVAE_CHECK_ARG(ms && work && launches && n_classes >= PC_COUNT, "profile_end needs %d classes", (int)PC_COUNT);
   for (int i = 0; i < n_classes; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }
-  if (!g_prof.empty() && cudaEventSynchronize(g_prof.back().b) != cudaSuccess) return fail(HYVAE_ECUDA, "profile: event sync failed");
+  // records may sit on several streams (tile_streams > 1): wait for every event, not only the last one recorded
+  for (auto& r : g_prof)
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return fail(HYVAE_ECUDA, "profile: event sync failed");
   FILE* dump = nullptr;
   if (const char* path = getenv("HYVAE_PROFILE_DUMP")) dump = fopen(path, "w");
   if (dump) fprintf(dump, "class,tag,work,ms\n");
@@ -724,11 +745,11 @@ int hyvae_softmax_frame_causal(const float* S, void* P, int32_t p_dtype, int32_t
   HYVAE_CHECK_ARG(L <= 48 * 1024, "softmax row of %d floats does not fit the shared-memory staging (max 49152)", L);
   const size_t smem = (size_t)L * sizeof(float);
   HYVAE_DISPATCH_DTYPE(p_dtype, T, {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
       if (cudaFuncSetAttribute(softmax_frame_causal_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024 * 4) != cudaSuccess)
         return fail(HYVAE_ECUDA, "softmax: cannot opt in to 192 KB of shared memory");
-      attr_set = true;
+      attr_once.done();
     }
     softmax_frame_causal_kernel<T><<<(unsigned)((int64_t)B * L), 256, smem, (cudaStream_t)stream>>>(S, (T*)P, L, n_hw, scale);
   });
@@ -760,17 +781,19 @@ int hyvae_interp_t_nearest(const hyvae_vol* x, const hyvae_vol* y, float inv_sca
 }
 
 int hyvae_image_postprocess(const void* src, int32_t src_dtype, float* dst, int64_t n, void* stream) {
-  HYVAE_CHECK_ARG(src && dst && n > 0 && n % 8 == 0, "image_postprocess: need n %% 8 == 0 (n=%lld)", (long long)n);
-  HYVAE_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "pointers must be 16-byte aligned");
+  HYVAE_CHECK_ARG(src && dst && n > 0, "image_postprocess: null pointer or n=%lld", (long long)n);
+  HYVAE_CHECK_ARG(src_dtype == HYVAE_BF16 || src_dtype == HYVAE_F16 || src_dtype == HYVAE_F32, "image_postprocess: bad dtype %d", src_dtype);
+  const bool aligned = ((uintptr_t)src & (src_dtype == HYVAE_F32 ? 31 : 15)) == 0 && ((uintptr_t)dst & 31) == 0;
+  const int64_t n8 = aligned ? n / 8 : 0;
   ProfScope prof(PC_LAYOUT, (double)n * (dtype_size(src_dtype) + 4), stream);
-  HYVAE_DISPATCH_DTYPE(src_dtype, T, (image_postprocess_kernel<T><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const T*)src, dst, n / 8)));
+  HYVAE_DISPATCH_DTYPE(src_dtype, T, (image_postprocess_kernel<T><<<grid_for(aligned ? (n + 7) / 8 : n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)src, dst, n8, n)));
   return check_launch("image_postprocess");
 }
 
 int hyvae_blend_crop_scatter(void* cur, const void* above, const void* left, int32_t dtype, int64_t N,
                              int32_t Yc, int32_t Xc, int32_t Ya, int32_t Xl, int32_t ev, int32_t eh,
                              void* out, int32_t Yo, int32_t Xo, int32_t y0, int32_t x0, int32_t crop_y,
-                             int32_t crop_x, const int64_t* ns, void* stream) {
+                             int32_t crop_x, const int64_t* ns, int32_t post, void* stream) {
   const int64_t cur_ns = ns ? ns[0] : (int64_t)Yc * Xc, above_ns = ns ? ns[1] : (int64_t)Ya * Xc;
   const int64_t left_ns = ns ? ns[2] : (int64_t)Yc * Xl, out_ns = ns ? ns[3] : (int64_t)Yo * Xo;
   HYVAE_CHECK_ARG(cur != nullptr && N > 0 && Yc > 0 && Xc > 0, "bad blend arguments");
@@ -780,9 +803,16 @@ int hyvae_blend_crop_scatter(void* cur, const void* above, const void* left, int
                   "crop window does not fit");
   int64_t total = N * Yc * Xc;
   ProfScope prof(PC_BLEND, (double)total * dtype_size(dtype) + (out ? (double)N * crop_y * crop_x * dtype_size(dtype) : 0.0), stream);
-  HYVAE_DISPATCH_DTYPE(dtype, T, (blend_crop_scatter_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (T*)cur, (const T*)above, (const T*)left, N, Yc, Xc, Ya, Xl, ev, eh, (T*)out, Yo, Xo, y0, x0, crop_y, crop_x,
-      cur_ns, above_ns, left_ns, out_ns)));
+  HYVAE_CHECK_ARG(!post || out != nullptr, "post-processed output requested without an output buffer");
+  if (post) {
+    HYVAE_DISPATCH_DTYPE(dtype, T, (blend_crop_scatter_kernel<T, true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (T*)cur, (const T*)above, (const T*)left, N, Yc, Xc, Ya, Xl, ev, eh, (float*)out, Yo, Xo, y0, x0, crop_y, crop_x,
+        cur_ns, above_ns, left_ns, out_ns)));
+  } else {
+    HYVAE_DISPATCH_DTYPE(dtype, T, (blend_crop_scatter_kernel<T, false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (T*)cur, (const T*)above, (const T*)left, N, Yc, Xc, Ya, Xl, ev, eh, (T*)out, Yo, Xo, y0, x0, crop_y, crop_x,
+        cur_ns, above_ns, left_ns, out_ns)));
+  }
   return check_launch("blend_crop_scatter");
 }
 

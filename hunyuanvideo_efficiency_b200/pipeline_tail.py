@@ -12,7 +12,6 @@ from typing import Optional
 
 import torch
 
-from . import _native as N
 
 
 def decode_latents(vae, latents: torch.Tensor, enable_tiling: bool = True, runner=None, to_cpu: bool = True) -> Optional[torch.Tensor]:
@@ -26,14 +25,16 @@ def decode_latents(vae, latents: torch.Tensor, enable_tiling: bool = True, runne
         raise ValueError(f"Only support latents with shape (b, c, h, w) or (b, c, f, h, w), but got {latents.shape}.")
     cfg = vae.config
     shift = cfg.get("shift_factor", None) if hasattr(cfg, "get") else getattr(cfg, "shift_factor", None)
-    latents = latents / cfg.scaling_factor + shift if shift else latents / cfg.scaling_factor
+    # latents / scaling_factor (+ shift_factor) is folded into post_quant_conv's packed weights, and (x / 2 + 0.5).clamp(0, 1)
+    # + the fp32 cast are the epilogue of the last tile-assembly kernel (AutoencoderKLCausal3D.decode_to_image): the tail
+    # adds no pass over the latents or the video
+    scale, shift = 1.0 / float(cfg.scaling_factor), float(shift) if shift else 0.0
     with torch.no_grad():
         if enable_tiling:
             vae.enable_tiling()
-        image = runner.decode(latents) if runner is not None else vae.decode(latents, return_dict=False)[0]
+        image = (runner if runner is not None else vae).decode_to_image(latents, scale, shift)
     if image is None:
         return None
     if expand_temporal_dim or image.shape[2] == 1:
         image = image.squeeze(2)
-    image = N.image_postprocess(image.contiguous())
     return image.cpu() if to_cpu else image

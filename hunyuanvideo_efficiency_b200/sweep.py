@@ -103,6 +103,29 @@ def enumerate_stride_configs(base: dict) -> List[Tuple[str, dict]]:
     return out
 
 
+def enumerate_stride_pair_configs(base: dict) -> List[Tuple[str, dict]]:
+    """dynamic_enumeration_stride_2.py:82-101: TWO of the encoder down blocks 0, 1, 2 get their temporal stride doubled
+    (block 0: 1 -> 2; blocks 1, 2: x2) x TWO temporal interpolations in the decoder; every pool / interp flag of the base
+    config is cleared first (set_all_false, :30-44).  3 block pairs x C(24, 2) slot pairs = 828 configs for the stock JSON,
+    numbered exp_1.. in (block pair, slot pair) order."""
+    out = []
+    dslots = decoder_slots(base)
+    for a, eb1 in enumerate((0, 1, 2)):
+        for eb2 in (0, 1, 2)[a + 1:]:
+            for j, d1 in enumerate(dslots):
+                for d2 in dslots[j + 1:]:
+                    cfg = copy.deepcopy(base)
+                    for eb in (eb1, eb2):
+                        st = cfg["encoder"]["down_blocks"][eb]["downsample_stride"]
+                        cfg["encoder"]["down_blocks"][eb]["downsample_stride"] = [2 if eb == 0 else st[0] * 2, st[1], st[2]]
+                    _clear(cfg.get("encoder", {}).get("down_blocks", []), ("enable_t_pool_before_block", "enable_t_pool_after_block"))
+                    _clear(cfg.get("decoder", {}).get("up_blocks", []), ("enable_t_interp_before_block", "enable_t_interp_after_block"))
+                    for d in (d1, d2):
+                        cfg["decoder"]["up_blocks"][d[0]]["enable_t_interp_" + d[2] + "_block"][d[1]] = True
+                    out.append((f"exp_{len(out) + 1}", cfg))
+    return out
+
+
 def configs_of_rank(configs: List[Tuple[str, dict]], rank: int, world: int) -> List[Tuple[str, dict]]:
     return [c for i, c in enumerate(configs) if i % world == rank]
 
@@ -180,7 +203,8 @@ def parse_args(argv=None):
     p.add_argument("--tensor-dir", required=True, help="Directory of input .pt clips ((C, T, H, W) fp32 in [-1, 1]).")
     p.add_argument("--metrics-dir", required=True, help="One sub-directory with metrics.txt per experiment is written here.")
     p.add_argument("--base-config", default="t_ops_config.json", help="Base t-ops JSON the enumerators start from.")
-    p.add_argument("--mode", default="pool", choices=["pool", "stride", "dir"], help="Enumerator, or 'dir' to read --config-dir/exp_*.json.")
+    p.add_argument("--mode", default="pool", choices=["pool", "stride", "stride2", "dir"],
+                   help="Enumerator (dynamic_enumeration.py / _stride.py / _stride_2.py), or 'dir' to read --config-dir/exp_*.json.")
     p.add_argument("--config-dir", default=None)
     p.add_argument("--vae-path", default="ckpts/hunyuan-video-t2v-720p/vae")
     p.add_argument("--vae-precision", default="fp16", choices=["fp16", "bf16", "fp32"])
@@ -204,7 +228,7 @@ def main(argv=None):
         configs = [(os.path.splitext(os.path.basename(f))[0], json.load(open(f))) for f in files]
     else:
         base = json.load(open(args.base_config))
-        configs = enumerate_pool_configs(base) if args.mode == "pool" else enumerate_stride_configs(base)
+        configs = {"pool": enumerate_pool_configs, "stride": enumerate_stride_configs, "stride2": enumerate_stride_pair_configs}[args.mode](base)
     if args.max_configs is not None:
         configs = configs[:args.max_configs]
     vae, _, _, _ = load_vae(vae_type="884-16c-hy", vae_precision=args.vae_precision, vae_path=args.vae_path, device=device)

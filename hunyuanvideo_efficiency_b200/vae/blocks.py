@@ -476,10 +476,11 @@ class Attention(nn.Module):
         wo, bo = self.to_out[0].packed(x.dtype)
         for b in range(B):
             xb = Vol(1, 1, 1, L, Cn, x.dtype, x.device, tensor=hn.t[b].reshape(1, 1, 1, L, Cn))
-            q = _gemm_nt(xb, wq, bq, Cn)
-            k = _gemm_nt(xb, wk, bk, Cn)
-            wv_rows = Vol(1, 1, 1, Cn, Cn, x.dtype, x.device, tensor=wv.reshape(1, 1, 1, Cn, Cn))
-            vt = _gemm_nt(wv_rows, xb.t.reshape(L, Cn), None, L)                      # V^T [C][L], bias folded below
+            with N.profile_class("attn_proj"):   # Linear layers of the attention, not nn.Conv3d FLOPs of the reference
+                q = _gemm_nt(xb, wq, bq, Cn)
+                k = _gemm_nt(xb, wk, bk, Cn)
+                wv_rows = Vol(1, 1, 1, Cn, Cn, x.dtype, x.device, tensor=wv.reshape(1, 1, 1, Cn, Cn))
+                vt = _gemm_nt(wv_rows, xb.t.reshape(L, Cn), None, L)                  # V^T [C][L], bias folded below
             o = None
             if self.fused_eligible(x.dtype, L, Cn):
                 try:  # one kernel: S and P stay in TMEM / shared memory (attn_fused.cu)
@@ -488,15 +489,17 @@ class Attention(nn.Module):
                 except N.HyvaeUnsupported:
                     o = None
             if o is None:
-                s = _gemm_nt(q, k.t.reshape(L, Cn), None, L, out_dtype=torch.float32)     # S [L][L] fp32
-                p = N.softmax_frame_causal(s.t.reshape(1, L, L), n_hw, self.scale, x.dtype)
-                pv = Vol(1, 1, 1, L, L, x.dtype, x.device, tensor=p.reshape(1, 1, 1, L, L))
-                o = _gemm_nt(pv, vt.t.reshape(Cn, L), bv, Cn)                             # rows of P sum to 1 => + bv
+                with N.profile_class("attn"):
+                    s = _gemm_nt(q, k.t.reshape(L, Cn), None, L, out_dtype=torch.float32)     # S [L][L] fp32
+                    p = N.softmax_frame_causal(s.t.reshape(1, L, L), n_hw, self.scale, x.dtype)
+                    pv = Vol(1, 1, 1, L, L, x.dtype, x.device, tensor=p.reshape(1, 1, 1, L, L))
+                    o = _gemm_nt(pv, vt.t.reshape(Cn, L), bv, Cn)                             # rows of P sum to 1 => + bv
             res = Vol(1, 1, 1, L, Cn, x.dtype, x.device, tensor=x.t[b].reshape(1, 1, 1, L, Cn)) if self.residual_connection else None
             ob = Vol(1, 1, 1, L, Cn, x.dtype, x.device, tensor=out.t[b].reshape(1, 1, 1, L, Cn))
             # B == 1 (every tiled call): the out-projection's epilogue also emits the GroupNorm statistics that the next
             # resnet's norm1 needs, so no separate statistics pass reads the result back
-            yb = _gemm_nt(o, wo, bo, Cn, residual=res, out=ob, gn_groups=self.emit_gn_groups if B == 1 else 0)
+            with N.profile_class("attn_proj"):
+                yb = _gemm_nt(o, wo, bo, Cn, residual=res, out=ob, gn_groups=self.emit_gn_groups if B == 1 else 0)
             if B == 1 and yb.gn_sums is not None:
                 out.gn_sums, out.gn_groups = yb.gn_sums, yb.gn_groups
         return out

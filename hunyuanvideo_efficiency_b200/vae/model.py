@@ -222,12 +222,25 @@ class _ConvParamsOnly(nn.Module):
         nn.init.uniform_(self.bias, -b, b)
         self._packed = None
 
-    def forward_vol(self, x: Vol) -> Vol:
-        key = (self.weight._version, self.bias._version, self.weight.data_ptr(), x.dtype)
+    def forward_vol(self, x: Vol, affine=None) -> Vol:
+        """affine = (scale, shift): computes conv(x * scale + shift) with the affine map folded into the packed weights and
+        bias (W' = W * scale, b' = b + shift * W.sum(in)), in fp32, rounded once — the pipeline's `latents / scaling_factor
+        (+ shift_factor)` (pipeline_hunyuan_video.py:1060-1069) then costs no pass over the latents."""
+        co, ci = self.weight.shape[0], self.weight.shape[1]
+        if x.C < ci or x.c_valid > ci:
+            raise N.HyvaeError(f"1x1x1 conv: input has {x.c_valid} channels (stored {x.C}), the weight expects {ci}")
+        key = (self.weight._version, self.bias._version, self.weight.data_ptr(), x.dtype, x.C, affine)
         if self._packed is None or self._packed[0] != key:
-            c = self.weight.shape[0]
-            self._packed = (key, self.weight.detach().reshape(1, c, c).to(x.dtype).contiguous(), self.bias.detach().float().contiguous())
-        return N.conv3d_direct(x, self._packed[1], self._packed[2], 1, (1, 1, 1), self.weight.shape[0], round_like_ref=False)
+            w32, b32 = self.weight.detach().float().reshape(co, ci), self.bias.detach().float()
+            if affine is not None:
+                scale, shift = float(affine[0]), float(affine[1])
+                b32 = b32 + shift * w32.sum(1)
+                w32 = w32 * scale
+            if x.C > ci:   # producer padded its channel count (e.g. Cout of a tensor-core conv_out to a multiple of 8): zero columns
+                w32 = torch.cat([w32, torch.zeros(co, x.C - ci, device=w32.device)], 1)
+            self._packed = (key, w32.reshape(1, co, x.C).to(x.dtype).contiguous(), b32.contiguous())
+        y = N.conv3d_direct(x, self._packed[1], self._packed[2], 1, (1, 1, 1), co, round_like_ref=False)
+        return y
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.forward_vol(Vol.from_ncthw(x)).to_ncthw()
@@ -304,6 +317,12 @@ class AutoencoderKLCausal3D(nn.Module):
         self.tile_latent_min_size = int(ss / (2 ** (len(block_out_channels) - 1)))
         self.tile_overlap_factor = 0.25
         self.bf16_compute = "fp16"  # see _act_dtype()
+        # fp16 operands have range 65 504 where the bf16 the model was built in has 3e38: a tile whose result is not finite
+        # is re-run with bf16 operands (see _guard_tiles)
+        self.fp16_range_guard = os.environ.get("HYVAE_FP16_GUARD", "1") == "1"
+        self.range_guard_reruns = 0
+        self._force_bf16 = False
+        self._latent_affine = None   # (scale, shift) folded into post_quant_conv by decode_to_image
         # sub-model calls of different tiles are independent: run them on this many CUDA streams (run_tiles)
         self.tile_streams = int(os.environ.get("HYVAE_TILE_STREAMS", "2"))
 
@@ -372,9 +391,31 @@ class AutoencoderKLCausal3D(nn.Module):
         the reference's default VAE precision (hyvideo/config.py:67-73), so its range is known to suffice.
         `bf16_compute = "bf16"` keeps every operand and intermediate in bf16 like the reference."""
         dt = self.dtype
-        if dt == torch.bfloat16 and os.environ.get("HYVAE_BF16_COMPUTE", self.bf16_compute) == "fp16":
+        if dt == torch.bfloat16 and not self._force_bf16 and os.environ.get("HYVAE_BF16_COMPUTE", self.bf16_compute) == "fp16":
             return torch.float16
         return dt
+
+    def _guard_tiles(self, outs, rerun):
+        """Range guard of the fp16-operand mode of a bf16 model.  An activation beyond fp16's 65 504 becomes inf at the store
+        that rounds it and reaches the tile's output as inf / NaN (the next GroupNorm turns it into NaN), so `all finite` on
+        the outputs detects it: one fp32 sum per tile, ONE host read per batch of tiles.  Flagged tiles are recomputed by
+        `rerun(k)` with every operand in bf16, exactly as `bf16_compute = "bf16"` evaluates them."""
+        if not (self.fp16_range_guard and outs and self.dtype == torch.bfloat16 and self._act_dtype() == torch.float16):
+            return outs
+        flags = torch.stack([o.sum(dtype=torch.float32) for o in outs])
+        bad = (~torch.isfinite(flags)).nonzero().flatten().tolist()
+        if bad:
+            self._force_bf16 = True
+            try:
+                for k in bad:
+                    outs[k] = rerun(k)
+                    self.range_guard_reruns += 1
+            finally:
+                self._force_bf16 = False
+        return outs
+
+    def _guarded(self, fn, x):
+        return self._guard_tiles([fn(x)], lambda k: fn(x))[0]
 
     def _encode_tile(self, x: torch.Tensor) -> torch.Tensor:
         act = self._act_dtype()
@@ -384,7 +425,7 @@ class AutoencoderKLCausal3D(nn.Module):
 
     def _decode_tile(self, z: torch.Tensor) -> torch.Tensor:
         v = Vol.from_ncthw(z, dtype=self._act_dtype())
-        return self.decoder.forward_vol(self.post_quant_conv.forward_vol(v)).to_ncthw(dtype=self.dtype)
+        return self.decoder.forward_vol(self.post_quant_conv.forward_vol(v, affine=self._latent_affine)).to_ncthw(dtype=self.dtype)
 
     # ---- encode / decode (:259-342)
     def encode(self, x: torch.Tensor, return_dict: bool = True):
@@ -394,21 +435,23 @@ class AutoencoderKLCausal3D(nn.Module):
         if self.use_spatial_tiling and (x.shape[-1] > self.tile_sample_min_size or x.shape[-2] > self.tile_sample_min_size):
             return self.spatial_tiled_encode(x, return_dict=return_dict)
         if self.use_slicing and x.shape[0] > 1:
-            moments = torch.cat([self._encode_tile(s) for s in x.split(1)])
+            moments = torch.cat([self._guarded(self._encode_tile, s) for s in x.split(1)])
         else:
-            moments = self._encode_tile(x)
+            moments = self._guarded(self._encode_tile, x)
         posterior = DiagonalGaussianDistribution(moments)
         if not return_dict:
             return (posterior,)
         return AutoencoderKLOutput(latent_dist=posterior, tiles_ci=None)
 
-    def _decode(self, z: torch.Tensor, return_dict: bool = True):
+    def _decode(self, z: torch.Tensor, return_dict: bool = True, _post: bool = False):
         assert len(z.shape) == 5, "The input tensor should have 5 dimensions."
         if self.use_temporal_tiling and z.shape[2] > self.tile_latent_min_tsize:
-            return self.temporal_tiled_decode(z, return_dict=return_dict)
+            return self.temporal_tiled_decode(z, return_dict=return_dict, _post=_post)
         if self.use_spatial_tiling and (z.shape[-1] > self.tile_latent_min_size or z.shape[-2] > self.tile_latent_min_size):
-            return self.spatial_tiled_decode(z, return_dict=return_dict)
-        dec = self._decode_tile(z)
+            return self.spatial_tiled_decode(z, return_dict=return_dict, _post=_post)
+        dec = self._guarded(self._decode_tile, z)
+        if _post:
+            dec = N.image_postprocess(dec)
         if not return_dict:
             return (dec,)
         return DecoderOutput(sample=dec)
@@ -421,6 +464,19 @@ class AutoencoderKLCausal3D(nn.Module):
         if not return_dict:
             return (decoded,)
         return DecoderOutput(sample=decoded)
+
+    def decode_to_image(self, z: torch.Tensor, latent_scale: float = 1.0, latent_shift: float = 0.0) -> torch.Tensor:
+        """The pipeline tail in one call (pipeline_hunyuan_video.py:1060-1092): decode(z * latent_scale + latent_shift)
+        followed by float((x / 2 + 0.5).clamp(0, 1)), returned as an fp32 tensor on the device.  The affine map of the
+        latents is folded into post_quant_conv's packed weights, and the image post-processing is the epilogue of the
+        last tile-assembly kernel (hyvae_blend_crop_scatter, post = 1), so neither costs a pass over the data."""
+        self._latent_affine = None if (latent_scale == 1.0 and latent_shift == 0.0) else (float(latent_scale), float(latent_shift))
+        try:
+            if self.use_slicing and z.shape[0] > 1:
+                return torch.cat([self._decode(s, _post=True).sample for s in z.split(1)])
+            return self._decode(z, _post=True).sample
+        finally:
+            self._latent_affine = None
 
     def tiled_decode(self, z: torch.Tensor, return_dict: bool = True):
         """decode() with spatial + temporal tiling switched on for this call."""
@@ -437,6 +493,11 @@ class AutoencoderKLCausal3D(nn.Module):
         e = min(a.shape[axis], b.shape[axis], extent)
         if e <= 0:
             return b
+        if a.ndim != 5 or b.ndim != 5 or a.dtype != b.dtype or a.device != b.device:
+            raise ValueError("blend_*: a and b must be 5-D tensors of one dtype on one device")
+        ax = axis % 5
+        if any(a.shape[d] != b.shape[d] for d in range(5) if d != ax):   # the reference's tensor ops would raise as well
+            raise ValueError(f"blend_*: shapes {tuple(a.shape)} and {tuple(b.shape)} differ outside the blended axis")
         assert a.is_contiguous() and b.is_contiguous(), "blend_* operate on contiguous tile tensors"
         B, C, T, H, W = b.shape
         if axis == -2:
@@ -457,19 +518,22 @@ class AutoencoderKLCausal3D(nn.Module):
         return self._blend(a, b, blend_extent, -3)
 
     # ---- spatial tiling (:362-469)
-    def _spatial_tiled(self, x: torch.Tensor, fn, tile: int, stride: int, extent: int, limit: int) -> torch.Tensor:
+    def _spatial_tiled(self, x: torch.Tensor, fn, tile: int, stride: int, extent: int, limit: int, post: bool = False) -> torch.Tensor:
         ii, jj = list(range(0, x.shape[-2], stride)), list(range(0, x.shape[-1], stride))
-        outs = run_tiles([(lambda i=i, j=j: fn(x[:, :, :, i:i + tile, j:j + tile])) for i in ii for j in jj],
+        cuts = [(i, j) for i in ii for j in jj]
+        outs = run_tiles([(lambda i=i, j=j: fn(x[:, :, :, i:i + tile, j:j + tile])) for i, j in cuts],
                          self.tile_streams if x.is_cuda else 1)
+        outs = self._guard_tiles(outs, lambda k: fn(x[:, :, :, cuts[k][0]:cuts[k][0] + tile, cuts[k][1]:cuts[k][1] + tile]))
         rows = [outs[r * len(jj):(r + 1) * len(jj)] for r in range(len(ii))]
-        return self._assemble_spatial(rows, extent, limit)
+        return self._assemble_spatial(rows, extent, limit, post)
 
-    def _assemble_spatial(self, rows, extent: int, limit: int) -> torch.Tensor:
-        """Raster-order in-place blend chain + crop + scatter of a grid of tile tensors (one kernel per tile)."""
+    def _assemble_spatial(self, rows, extent: int, limit: int, post: bool = False) -> torch.Tensor:
+        """Raster-order in-place blend chain + crop + scatter of a grid of tile tensors (one kernel per tile).
+        post: the scattered result is the fp32 image float((v / 2 + 0.5).clamp(0, 1)) (decode_to_image)."""
         hs = [min(r[0].shape[-2], limit) for r in rows]
         ws = [min(t.shape[-1], limit) for t in rows[0]]
         B, C, T = rows[0][0].shape[:3]
-        out = torch.empty((B, C, T, sum(hs), sum(ws)), dtype=rows[0][0].dtype, device=rows[0][0].device)
+        out = torch.empty((B, C, T, sum(hs), sum(ws)), dtype=torch.float32 if post else rows[0][0].dtype, device=rows[0][0].device)
         Yo, Xo, n = out.shape[-2], out.shape[-1], B * C * T
         y0 = 0
         for i, row in enumerate(rows):
@@ -485,7 +549,7 @@ class AutoencoderKLCausal3D(nn.Module):
                     left = None
                 N.blend_crop_scatter(t, above, left, n, t.shape[-2], t.shape[-1],
                                      above.shape[-2] if above is not None else 0, left.shape[-1] if left is not None else 0,
-                                     ev, eh, out, Yo, Xo, y0, x0, hs[i], ws[j])
+                                     ev, eh, out, Yo, Xo, y0, x0, hs[i], ws[j], post=post)
                 x0 += ws[j]
             y0 += hs[i]
         return out
@@ -502,34 +566,35 @@ class AutoencoderKLCausal3D(nn.Module):
             return (posterior,)
         return AutoencoderKLOutput(latent_dist=posterior)
 
-    def spatial_tiled_decode(self, z: torch.Tensor, return_dict: bool = True):
+    def spatial_tiled_decode(self, z: torch.Tensor, return_dict: bool = True, _post: bool = False):
         stride = int(self.tile_latent_min_size * (1 - self.tile_overlap_factor))
         extent = int(self.tile_sample_min_size * self.tile_overlap_factor)
         dec = self._spatial_tiled(z, self._decode_tile, self.tile_latent_min_size, stride, extent,
-                                  self.tile_sample_min_size - extent)
+                                  self.tile_sample_min_size - extent, post=_post)
         if not return_dict:
             return (dec,)
         return DecoderOutput(sample=dec)
 
     # ---- temporal tiling (:471-541)
-    def _temporal_tiled(self, x, fn_plain, fn_spatial, tile_t, stride, extent, limit, min_size) -> torch.Tensor:
+    def _temporal_tiled(self, x, fn_plain, fn_spatial, tile_t, stride, extent, limit, min_size, post: bool = False) -> torch.Tensor:
         row = []  # (tensor, first_frame_offset): tiles i>0 drop their first output frame (:491,527)
         for i in range(0, x.shape[2], stride):
             t = x[:, :, i:i + tile_t + 1]
             if self.use_spatial_tiling and (t.shape[-1] > min_size or t.shape[-2] > min_size):
                 t = fn_spatial(t)
             else:
-                t = fn_plain(t)
+                t = self._guarded(fn_plain, t)
             row.append((t, 1 if i > 0 else 0))
-        return self._assemble_temporal(row, extent, limit)
+        return self._assemble_temporal(row, extent, limit, post)
 
-    def _assemble_temporal(self, row, extent: int, limit: int) -> torch.Tensor:
-        """`row` = [(tile tensor, leading frames to drop)]: blend_t chain + crop + concatenate along T."""
+    def _assemble_temporal(self, row, extent: int, limit: int, post: bool = False) -> torch.Tensor:
+        """`row` = [(tile tensor, leading frames to drop)]: blend_t chain + crop + concatenate along T.
+        post: as in _assemble_spatial (this is the last assembly pass of a temporally tiled decode)."""
         lens = [t.shape[2] - off for t, off in row]
         keep = [min(lens[i], limit + 1 if i == 0 else limit) for i in range(len(row))]
         B, C, _, H, W = row[0][0].shape
         hw = H * W
-        out = torch.empty((B, C, sum(keep), H, W), dtype=row[0][0].dtype, device=row[0][0].device)
+        out = torch.empty((B, C, sum(keep), H, W), dtype=torch.float32 if post else row[0][0].dtype, device=row[0][0].device)
         y0 = 0
         for i, (t, off) in enumerate(row):
             cur = t[:, :, off:]
@@ -541,7 +606,7 @@ class AutoencoderKLCausal3D(nn.Module):
             above = pt[:, :, poff:] if (pt is not None and e > 0) else None
             ns = (t.shape[2] * hw, (pt.shape[2] * hw) if pt is not None else 0, 0, out.shape[2] * hw)
             N.blend_crop_scatter(cur, above, None, B * C, lens[i], hw, lens[i - 1] if above is not None else 0, 0,
-                                 e if above is not None else 0, 0, out, out.shape[2], hw, y0, 0, keep[i], hw, n_strides=ns)
+                                 e if above is not None else 0, 0, out, out.shape[2], hw, y0, 0, keep[i], hw, n_strides=ns, post=post)
             y0 += keep[i]
         return out
 
@@ -556,12 +621,12 @@ class AutoencoderKLCausal3D(nn.Module):
             return (posterior,)
         return AutoencoderKLOutput(latent_dist=posterior)
 
-    def temporal_tiled_decode(self, z: torch.Tensor, return_dict: bool = True):
+    def temporal_tiled_decode(self, z: torch.Tensor, return_dict: bool = True, _post: bool = False):
         stride = int(self.tile_latent_min_tsize * (1 - self.tile_overlap_factor))
         extent = int(self.tile_sample_min_tsize * self.tile_overlap_factor)
         dec = self._temporal_tiled(z, self._decode_tile, lambda t: self.spatial_tiled_decode(t, return_dict=True).sample,
                                    self.tile_latent_min_tsize, stride, extent, self.tile_sample_min_tsize - extent,
-                                   self.tile_latent_min_size)
+                                   self.tile_latent_min_size, post=_post)
         if not return_dict:
             return (dec,)
         return DecoderOutput(sample=dec)

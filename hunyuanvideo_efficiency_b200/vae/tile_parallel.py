@@ -107,7 +107,7 @@ class TileParallelVAE:
         return tiles
 
     # ---- one direction ----------------------------------------------------------------------
-    def _run(self, x: torch.Tensor, encode: bool, to_all: bool):
+    def _run(self, x: torch.Tensor, encode: bool, to_all: bool, post: bool = False):
         v = self.vae
         B, _, T, H, W = x.shape
         ov = v.tile_overlap_factor
@@ -126,8 +126,10 @@ class TileParallelVAE:
         specs = tile_grid(T, H, W, temporal=v.use_temporal_tiling, spatial=v.use_spatial_tiling, min_t=min_t, min_s=min_s, overlap=ov)
         owner = lpt_assign([s.cost for s in specs], self.world)
         mine_k = [k for k in range(len(specs)) if owner[k] == self.rank]
-        outs = run_tiles([(lambda s=specs[k]: fn(x[:, :, s.t0:s.t1, s.h0:s.h1, s.w0:s.w1]).contiguous()) for k in mine_k],
-                         getattr(v, "tile_streams", 1) if x.is_cuda else 1)
+        cut = lambda s: fn(x[:, :, s.t0:s.t1, s.h0:s.h1, s.w0:s.w1]).contiguous()
+        outs = run_tiles([(lambda s=specs[k]: cut(s)) for k in mine_k], getattr(v, "tile_streams", 1) if x.is_cuda else 1)
+        if hasattr(v, "_guard_tiles"):   # fp16-operand range guard of a bf16 model (model.py): re-run overflowing tiles in bf16
+            outs = v._guard_tiles(outs, lambda i: cut(specs[mine_k[i]]))
         mine = {}
         for k, t in zip(mine_k, outs):
             assert tuple(t.shape) == oshape(specs[k]), (tuple(t.shape), oshape(specs[k]))
@@ -146,10 +148,19 @@ class TileParallelVAE:
             for k in ks:
                 grid[specs[k].i][specs[k].j] = tiles[k]
             single = len(ks) == 1 and not (v.use_spatial_tiling and (H > min_s or W > min_s))
-            row.append((grid[0][0] if single else self.assemble_spatial(grid, ext_s, lim_s), 1 if tt > 0 else 0))
+            last = n_tt == 1 and not (v.use_temporal_tiling and T > min_t)   # no temporal assembly follows
+            if single:
+                row.append((grid[0][0], 1 if tt > 0 else 0))
+            elif post and last:
+                row.append((self.assemble_spatial(grid, ext_s, lim_s, True), 0))
+            else:
+                row.append((self.assemble_spatial(grid, ext_s, lim_s), 1 if tt > 0 else 0))
         if n_tt == 1 and not (v.use_temporal_tiling and T > min_t):
+            if post and single:
+                from .. import _native as N
+                return N.image_postprocess(row[0][0])
             return row[0][0]
-        return self.assemble_temporal(row, ext_t, lim_t)
+        return self.assemble_temporal(row, ext_t, lim_t, True) if post else self.assemble_temporal(row, ext_t, lim_t)
 
     def encode_moments(self, x: torch.Tensor) -> torch.Tensor:
         """Blended moments of the whole clip, on every rank."""
@@ -158,6 +169,15 @@ class TileParallelVAE:
     def decode(self, z: torch.Tensor) -> Optional[torch.Tensor]:
         """Decoded clip on rank 0 (None elsewhere)."""
         return self._run(z, False, False)
+
+    def decode_to_image(self, z: torch.Tensor, latent_scale: float = 1.0, latent_shift: float = 0.0) -> Optional[torch.Tensor]:
+        """AutoencoderKLCausal3D.decode_to_image with the tiles sharded over the ranks: fp32 image on rank 0."""
+        v = self.vae
+        v._latent_affine = None if (latent_scale == 1.0 and latent_shift == 0.0) else (float(latent_scale), float(latent_shift))
+        try:
+            return self._run(z, False, False, post=True)
+        finally:
+            v._latent_affine = None
 
     def roundtrip(self, x: torch.Tensor) -> Optional[torch.Tensor]:
         """forward(sample_posterior=False): encode -> mode() -> decode (autoencoder_kl_causal_3d.py:543-578)."""

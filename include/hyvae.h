@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HYVAE_VERSION 110 /* 0.1.1: fused attention, metrics, kw-packed conv_in, temporal fold flag */
+#define HYVAE_VERSION 120 /* 0.1.2: Winograd-T convs, GroupNorm finalize folded into the convs, blend post-process epilogue */
 
 typedef enum { HYVAE_OK = 0, HYVAE_EINVAL = -1, HYVAE_ECUDA = -2, HYVAE_EUNSUPPORTED = -3 } hyvae_status;
 typedef enum { HYVAE_BF16 = 0, HYVAE_F32 = 1, HYVAE_F16 = 2 } hyvae_dtype;
@@ -187,24 +187,29 @@ int hyvae_interp_t_nearest(const hyvae_vol* x, const hyvae_vol* y, float inv_sca
  *   out   rows [y0, y0+crop_y) x cols [x0, x0+crop_x) of a dense [N][Yo][Xo] tensor <- cur[:crop_y,:crop_x]
  * Spatial tiles use N=(b,c,t), Y=h, X=w; temporal tiles use N=(b,c), Y=t, X=(h,w).
  * n_strides: NULL for dense tensors, else the element stride between consecutive n of {cur, above, left, out}
- * (lets a caller blend a view that dropped leading rows, e.g. tile[:, :, 1:] at :491,527). */
+ * (lets a caller blend a view that dropped leading rows, e.g. tile[:, :, 1:] at :491,527).
+ * post = 1: `out` is FP32 and receives the pipeline tail's image float(clamp(T(v / 2 + 0.5), 0, 1))
+ * (pipeline_hunyuan_video.py:1090-1092) instead of v: the last assembly pass of a decode emits the final image. */
 int hyvae_blend_crop_scatter(void* cur, const void* above, const void* left, int32_t dtype, int64_t N,
                              int32_t Yc, int32_t Xc, int32_t Ya, int32_t Xl, int32_t ev, int32_t eh,
                              void* out, int32_t Yo, int32_t Xo, int32_t y0, int32_t x0, int32_t crop_y,
-                             int32_t crop_x, const int64_t* n_strides, void* stream);
+                             int32_t crop_x, const int64_t* n_strides, int32_t post, void* stream);
 
 /* ---- pipeline tail ------------------------------------------------------------------------------
  * Replaces `image = (image / 2 + 0.5).clamp(0, 1); image = image.cpu().float()` of
  * pipeline_hunyuan_video.py:1090-1092 (device part): dst[i] = float(clamp(T(src[i] / 2 + 0.5), 0, 1)), one pass.
- * n must be a multiple of 8; src in `src_dtype`, dst fp32. */
+ * Any n and any of the three dtypes; 16-byte (fp32: 32-byte) aligned pointers take the vector path.  src in `src_dtype`, dst fp32. */
 int hyvae_image_postprocess(const void* src, int32_t src_dtype, float* dst, int64_t n, void* stream);
 
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------------
  * profile_begin/end bracket a region; while on, every C-ABI call is timed with two CUDA events on its
  * stream.  profile_end synchronises and returns, per kernel class (0 conv_tc, 1 conv_direct, 2 gn_stats,
- * 3 gn_apply, 4 pad_upsample, 5 softmax, 6 layout, 7 blend, 8 temporal, 9 attn), the summed device milliseconds,
- * the summed ALGORITHMIC work (flops for convs, bytes for the HBM-bound classes) and the launch count. */
-#define HYVAE_PROFILE_CLASSES 9
+ * 3 gn_apply, 4 pad_upsample, 5 softmax, 6 layout, 7 blend, 8 temporal, 9 attn, 10 attn_proj), the summed device
+ * milliseconds, the summed ALGORITHMIC work (flops for convs, bytes for the HBM-bound classes) and the launch count.
+ * profile_class_override(c >= 0) books the conv launches that follow under class c until reset with -1: the attention's
+ * q/k/v/out projections are k=1 launches of the conv kernels but are not nn.Conv3d FLOPs of the reference. */
+#define HYVAE_PROFILE_CLASSES 11
+int hyvae_profile_class_override(int32_t cls);
 int hyvae_profile_begin(void);
 int hyvae_profile_end(double* ms, double* work, int64_t* launches, int32_t n_classes);
 /* Tensor-core flops actually issued by the conv launches since hyvae_profile_begin: equals the algorithmic work except

@@ -25,6 +25,10 @@ import torch
 import torch.nn.functional as F
 
 Tensor = torch.Tensor
+# "explicit": softmax(q k^T * scale + mask) v written out (fp32 checker).  "sdpa": the same through
+# F.scaled_dot_product_attention with the dense additive mask, i.e. the call diffusers' AttnProcessor2_0 makes — used by
+# bench.py's torch_gpu_baseline leg, where the library kernel the reference would run is what is being timed.
+ATTN_IMPL = "explicit"
 EPS = 1e-6  # resnet_eps everywhere on this path (vae.py:88,103; unet_causal_3d_blocks.py:266)
 
 
@@ -66,10 +70,10 @@ def upsample_nearest_causal(x: Tensor, factor) -> Tensor:
     return torch.cat([first, rest], dim=2)
 
 
-def frame_causal_mask(n_frame: int, n_hw: int, dtype=torch.float32) -> Tensor:
+def frame_causal_mask(n_frame: int, n_hw: int, dtype=torch.float32, device=None) -> Tensor:
     """unet_causal_3d_blocks.py:38-46: query i may see every key of frames <= frame(i)."""
-    f = torch.arange(n_frame * n_hw) // n_hw
-    m = torch.zeros(n_frame * n_hw, n_frame * n_hw, dtype=dtype)
+    f = torch.arange(n_frame * n_hw, device=device) // n_hw
+    m = torch.zeros(n_frame * n_hw, n_frame * n_hw, dtype=dtype, device=device)
     m.masked_fill_(f[None, :] > f[:, None], float("-inf"))
     return m
 
@@ -89,7 +93,7 @@ def resnet_block(sd: Dict[str, Tensor], p: str, x: Tensor, groups: int) -> Tenso
 def sdpa_frame_causal(q: Tensor, k: Tensor, v: Tensor, n_frame: int, n_hw: int, scale: float) -> Tensor:
     """The F.scaled_dot_product_attention call inside diffusers' AttnProcessor2_0 (call site unet_causal_3d_blocks.py:661)
     with the additive mask of :38-46, one head: softmax(q k^T * scale + mask) v.  q, k, v: [L][D]."""
-    s = torch.matmul(q, k.transpose(0, 1)) * scale + frame_causal_mask(n_frame, n_hw, q.dtype)
+    s = torch.matmul(q, k.transpose(0, 1)) * scale + frame_causal_mask(n_frame, n_hw, q.dtype, q.device)
     return torch.matmul(torch.softmax(s, dim=-1), v)
 
 
@@ -102,8 +106,12 @@ def attention_block(sd: Dict[str, Tensor], p: str, x: Tensor, groups: int) -> Te
     q = F.linear(hn, sd[p + "to_q.weight"], sd[p + "to_q.bias"])
     k = F.linear(hn, sd[p + "to_k.weight"], sd[p + "to_k.bias"])
     v = F.linear(hn, sd[p + "to_v.weight"], sd[p + "to_v.bias"])
-    s = torch.matmul(q, k.transpose(1, 2)) * (C ** -0.5) + frame_causal_mask(T, H * W, x.dtype)[None]
-    o = torch.matmul(torch.softmax(s, dim=-1), v)
+    mask = frame_causal_mask(T, H * W, x.dtype, x.device)[None]
+    if ATTN_IMPL == "sdpa":  # one head: [B, 1, L, C]; default scale = C ** -0.5
+        o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None], attn_mask=mask[:, None])[:, 0]
+    else:
+        s = torch.matmul(q, k.transpose(1, 2)) * (C ** -0.5) + mask
+        o = torch.matmul(torch.softmax(s, dim=-1), v)
     o = F.linear(o, sd[p + "to_out.0.weight"], sd[p + "to_out.0.bias"]) + res
     return o.reshape(B, T, H, W, C).permute(0, 4, 1, 2, 3).contiguous()
 
@@ -375,7 +383,7 @@ def forward(sd, cfg, x: Tensor, tl: Tiling, t_ops=None, sample_posterior=False, 
     mean, logvar = posterior_mean_logvar(encode_moments(sd, cfg, x, tl, t_ops))
     z = mean
     if sample_posterior:
-        z = mean + torch.exp(0.5 * logvar) * torch.randn(mean.shape, generator=generator, dtype=mean.dtype)
+        z = mean + torch.exp(0.5 * logvar) * torch.randn(mean.shape, generator=generator, dtype=mean.dtype).to(mean.device)
     return decode(sd, cfg, z, tl, t_ops), mean, logvar
 
 

@@ -711,18 +711,75 @@ def test_full_size_tile_properties_bf16():
     assert torch.isfinite(d1.float()).all()
 
 
-def test_pipeline_tail_matches_reference_ops():
-    """pipeline_hunyuan_video.py:1060-1092: latents / scaling_factor -> tiled decode -> (x / 2 + 0.5).clamp(0, 1) -> float."""
+def test_pipeline_tail_matches_oracle():
+    """pipeline_hunyuan_video.py:1060-1092: latents / scaling_factor -> tiled decode -> (x / 2 + 0.5).clamp(0, 1) -> float,
+    against the ORACLE evaluating that chain (fp16 division of the latents as the pipeline does it, fp32 decode of the
+    fp16-rounded parameters, the image ops in fp32).  decode_to_image folds the scaling into post_quant_conv's weights and
+    the image ops into the last assembly kernel's epilogue; both rewrites are also checked against the unfused kernels."""
     from hunyuanvideo_efficiency_b200.pipeline_tail import decode_latents
+    N = _N()
     cfg = dict(W.SMALL_CONFIG, block_out_channels=[64, 128, 256, 256], scaling_factor=0.476986)
     m = _build(cfg, torch.float16)
-    z = W.make_latent((1, 16, 5, 12, 10)).to(_dev(), torch.float16)
-    out = decode_latents(m, z)
-    ref = m.decode(z / cfg["scaling_factor"], return_dict=False)[0]
-    ref = (ref / 2 + 0.5).clamp(0, 1).cpu().float()
-    assert out.dtype == torch.float32 and out.device.type == "cpu" and torch.equal(out, ref)
-    img = decode_latents(m, z[:, :, 0], to_cpu=False)                 # 4-D latents: one frame, temporal dim squeezed
+    z = W.make_latent((1, 16, 5, 12, 10)).half()
+    out = decode_latents(m, z.to(_dev()))
+    assert out.dtype == torch.float32 and out.device.type == "cpu" and out.shape == (1, 3, 17, 96, 80)
+    sd = {k: v.half().float() for k, v in W.make_state_dict(cfg).items()}
+    zin = (z / cfg["scaling_factor"]).float()                         # the pipeline divides in the latents' dtype (:1069)
+    ref = O.decode(sd, cfg, zin, O.Tiling.from_cfg(cfg, True, True))
+    ref = (ref / 2 + 0.5).clamp(0, 1)
+    assert O.rel_err(ref, out) < BF16_TOL and O.psnr(ref, out, data_range=1.0) > PSNR_MIN, (O.rel_err(ref, out), O.psnr(ref, out, 1.0))
+    # the fused epilogue is bit-identical to decode() followed by the stand-alone post-process kernel ...
+    m.enable_tiling()
+    plain = m.decode(z.to(_dev()), return_dict=False)[0]
+    assert torch.equal(m.decode_to_image(z.to(_dev())), N.image_postprocess(plain))
+    assert torch.equal(N.image_postprocess(plain).cpu(), (plain / 2 + 0.5).clamp(0, 1).float().cpu())
+    for t in (plain.float(), plain[..., :5, :3].contiguous(), plain.bfloat16()):   # fp32 input, odd sizes, bf16: same kernel
+        assert torch.equal(N.image_postprocess(t).cpu(), (t / 2 + 0.5).clamp(0, 1).float().cpu())
+    # ... and folding the scale into the weights moves one rounding point only
+    unfolded = N.image_postprocess(m.decode(z.to(_dev()) / cfg["scaling_factor"], return_dict=False)[0]).cpu()
+    assert O.psnr(unfolded, out, data_range=1.0) > 55.0
+    m.disable_tiling()
+    assert torch.equal(m.decode_to_image(z.to(_dev())), N.image_postprocess(m.decode(z.to(_dev()), return_dict=False)[0]))   # untiled path
+    img = decode_latents(m, z[:, :, 0].to(_dev()), to_cpu=False)      # 4-D latents: one frame, temporal dim squeezed
     assert img.shape == (1, 3, 96, 80) and img.is_cuda
+
+
+def test_fp16_range_guard_reruns_overflowing_tiles_in_bf16():
+    """A bf16 model computes with fp16 operands by default (range 65 504).  With conv_in scaled so that its output exceeds
+    that range the reference's bf16 evaluation is still fine; the guard must notice the non-finite tiles and re-run them with
+    bf16 operands, landing where `bf16_compute = "bf16"` lands (and within the pure-bf16 tolerance of the exact evaluation)."""
+    cfg = dict(W.SMALL_CONFIG, block_out_channels=[64, 128, 256, 256])
+    sd = W.make_state_dict(cfg)
+    for k in ("encoder.conv_in.conv.weight", "encoder.conv_in.conv.bias", "decoder.conv_in.conv.weight", "decoder.conv_in.conv.bias"):
+        sd[k] = sd[k] * 1.0e6
+    from hunyuanvideo_efficiency_b200.vae import AutoencoderKLCausal3D
+    m = AutoencoderKLCausal3D.from_config(cfg)
+    m.load_state_dict(sd)
+    m = m.to(torch.bfloat16).to(_dev()).eval().requires_grad_(False)
+    m.enable_spatial_tiling()
+    x = W.make_video((1, 3, 9, 48, 40)).bfloat16()
+    sd_b = {k: v.bfloat16().float() for k, v in sd.items()}
+    tl = O.Tiling.from_cfg(cfg, True, False)
+    ref_mom = O.encode_moments(sd_b, cfg, x.float(), tl)
+    ref_mean, _ = O.posterior_mean_logvar(ref_mom)
+    zin = ref_mean.bfloat16()
+    ref_dec = O.decode(sd_b, cfg, zin.float(), tl)
+    m.fp16_range_guard = False
+    assert not torch.isfinite(m.encode(x.to(_dev())).latent_dist.mode().float()).all()     # fp16 operands alone overflow
+    m.fp16_range_guard = True
+    n0 = m.range_guard_reruns
+    lat = m.encode(x.to(_dev())).latent_dist.mode()
+    dec = m.decode(zin.to(_dev())).sample
+    assert m.range_guard_reruns - n0 == 2 * 4                         # every tile of the 2 x 2 grid, both directions
+    assert torch.isfinite(lat.float()).all() and torch.isfinite(dec.float()).all()
+    m.bf16_compute = "bf16"
+    assert torch.equal(lat, m.encode(x.to(_dev())).latent_dist.mode()) and torch.equal(dec, m.decode(zin.to(_dev())).sample)
+    assert O.rel_err(ref_mean, lat.float().cpu()) < 1.25 * 2.7e-2 and O.rel_err(ref_dec, dec.float().cpu()) < 1.25 * 7.2e-2
+    # a model that stays in range pays one flag read and no re-run
+    m2 = _build(cfg, torch.bfloat16)
+    m2.enable_spatial_tiling()
+    m2.encode(x.to(_dev()))
+    assert m2.range_guard_reruns == 0
 
 
 def test_clip_driver_on_gpu(tmp_path):

@@ -69,6 +69,53 @@ def test_enumerators_follow_the_reference_order_and_counts():
     assert [n for n, _ in S.configs_of_rank(pool[:5], 1, 2)] == ["exp_2", "exp_4"]
 
 
+SSIM_KNOWN_ANSWER = 0.20712946133439245   # see test_ssim_known_answer_from_the_published_definition
+
+
+def test_enumerators_reproduce_the_reference_scripts_output():
+    """tests/golden/enumerators.json holds sha256 digests of the experiment lists the UNMODIFIED dynamic_enumeration.py,
+    dynamic_enumeration_stride.py and dynamic_enumeration_stride_2.py write for the fork's t_ops_config.json
+    (oracle/make_enumerator_golden.py ran them): the restated enumerators must produce the same 384 / 72 / 828 configs."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN
+    g = json.load(open(os.path.join(GOLDEN, "enumerators.json")))
+    dig = lambda cfgs: hashlib.sha256(json.dumps(cfgs, sort_keys=True, separators=(",", ":")).encode()).hexdigest()
+    for mode, fn in (("pool", S.enumerate_pool_configs), ("stride", S.enumerate_stride_configs), ("stride2", S.enumerate_stride_pair_configs)):
+        named = fn(g["base"])
+        cfgs = [c for _, c in named]
+        assert [n for n, _ in named] == [f"exp_{i + 1}" for i in range(g[mode]["count"])]
+        assert cfgs[0] == g[mode]["first"] and cfgs[-1] == g[mode]["last"]
+        assert dig(cfgs) == g[mode]["sha256"], mode
+
+
+def test_ssim_known_answer_from_the_published_definition():
+    """Hand computation of structural_similarity for ONE 7x7 window (a 7x7 single-channel frame pair has exactly one window
+    centre left after the (win_size - 1) // 2 crop), in exact rational arithmetic from the published definition
+    (Wang et al. 2004 with scikit-image's defaults: uniform window, sample covariance NP/(NP-1), K1 = 0.01, K2 = 0.03,
+    data_range = max(img1) - min(img1) as compute_metrics.py:41 passes it).  The literal below was evaluated once from that
+    formula; it pins the constants and normalisations of oracle/metrics_oracle.py.  scikit-image itself is not installed, so
+    DESIGN.md keeps the SSIM row labelled 'parity unpinned' until a skimage-generated fixture can be committed."""
+    from fractions import Fraction as Fr
+    a = np.array([[(7 * y + 3 * x * x) % 256 for x in range(7)] for y in range(7)], dtype=np.uint8)
+    b = np.array([[(5 * y * y + 11 * x + 40) % 256 for x in range(7)] for y in range(7)], dtype=np.uint8)
+    pa, pb = [Fr(int(v)) for v in a.ravel()], [Fr(int(v)) for v in b.ravel()]
+    n = Fr(49)
+    ux, uy = sum(pa) / n, sum(pb) / n
+    cn = n / (n - 1)
+    vx = cn * (sum(v * v for v in pa) / n - ux * ux)
+    vy = cn * (sum(v * v for v in pb) / n - uy * uy)
+    vxy = cn * (sum(p * q for p, q in zip(pa, pb)) / n - ux * uy)
+    R = Fr(int(a.max()) - int(a.min()))
+    c1, c2 = (Fr(1, 100) * R) ** 2, (Fr(3, 100) * R) ** 2
+    exact = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2))
+    got = MO.ssim_frame(a[..., None], b[..., None])
+    assert got == pytest.approx(float(exact), abs=1e-12)
+    assert float(exact) == pytest.approx(SSIM_KNOWN_ANSWER, abs=1e-15)
+    assert MO.ssim_frame_bruteforce(a[..., None], b[..., None]) == pytest.approx(float(exact), abs=1e-12)
+
+
 def test_snapshot_restore_of_t_ops_state(tmp_path):
     from hunyuanvideo_efficiency_b200.synthetic import SMALL_CONFIG
     from hunyuanvideo_efficiency_b200.vae import AutoencoderKLCausal3D, _apply_t_ops_config_to_vae
