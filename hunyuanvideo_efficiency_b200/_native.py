@@ -45,6 +45,8 @@ _SIGNATURES = {
     "hyvae_conv3d_causal_tc_shortcut": [_VP, _vp, _vp, _VP, _vp, _VP, _vp, _i32, _i32, _vp],
     "hyvae_conv3d_upphase_tc": [_VP, _vp, _vp, _VP, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "hyvae_groupnorm_finalize": [_vp, _i32, _i64, _i32, _vp, _vp],
+    "hyvae_groupnorm_apply_wino": [_VP, _vp, _vp, _vp, _i32, _f32, _i32, _VP, _vp],
+    "hyvae_conv3d_causal_wino": [_VP, _i32, _vp, _vp, _VP, _VP, _vp, _i32, _vp],
     "hyvae_groupnorm_stats": [_VP, _i32, _vp, _vp, _i64, _vp],
     "hyvae_groupnorm_apply": [_VP, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _VP, _vp],
     "hyvae_pad_upsample": [_VP, _VP, _i32, _i32, _i32, _vp],
@@ -62,7 +64,7 @@ _SIGNATURES = {
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["hyvae_version", "hyvae_last_error", "hyvae_device_supports_tc", "hyvae_launch_count",
                                        "hyvae_groupnorm_workspace_bytes", "hyvae_profile_begin", "hyvae_profile_end", "hyvae_profile_executed_flops",
-                                       "hyvae_conv3d_tc_gn_rows", "hyvae_frame_metrics_workspace_bytes"])
+                                       "hyvae_conv3d_tc_gn_rows", "hyvae_frame_metrics_workspace_bytes", "hyvae_wino_planes"])
 
 _lib = None
 
@@ -92,6 +94,8 @@ def lib():
         l.hyvae_groupnorm_workspace_bytes.argtypes = [_VP, _i32]
         l.hyvae_profile_executed_flops.restype = C.c_double
         l.hyvae_profile_executed_flops.argtypes = []
+        l.hyvae_wino_planes.restype = C.c_int32
+        l.hyvae_wino_planes.argtypes = [_i32]
         l.hyvae_conv3d_tc_gn_rows.restype = C.c_int64
         l.hyvae_conv3d_tc_gn_rows.argtypes = []
         _lib = l
@@ -158,7 +162,7 @@ def device_supports_tc() -> bool:
 class Vol:
     """Channels-last activation volume [B][T+pt][H+2ph][W+2pw][C] in HBM (see hyvae_vol)."""
 
-    __slots__ = ("t", "B", "T", "H", "W", "C", "pad", "_c", "c_valid", "gn_sums", "gn_groups", "kw_packed")
+    __slots__ = ("t", "B", "T", "H", "W", "C", "pad", "_c", "c_valid", "gn_sums", "gn_groups", "kw_packed", "wino_T")
 
     def __init__(self, B, T, H, W, Cn, dtype, device, pad: Tuple[int, int, int] = (0, 0, 0), tensor=None):
         pt, ph, pw = pad
@@ -174,6 +178,7 @@ class Vol:
         self.c_valid = Cn        # channels that carry data (C may be zero-padded up to a multiple of 8)
         self.gn_sums = None      # [B][groups][2] fp64 GroupNorm statistics emitted by the producing conv, if any
         self.gn_groups = 0
+        self.wino_T = 0          # > 0: this is the Winograd-T PLANE volume of a tensor with that many frames (groupnorm_wino)
         self.kw_packed = False   # channels are (kw, c) of a thin source (from_ncthw(kw_pack=True)): only conv_in reads such a volume
 
     @property
@@ -348,6 +353,44 @@ def groupnorm(x: Vol, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps:
     _check(lib().hyvae_groupnorm_apply(x.ref(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), groups, eps, int(silu),
                                        int(round_like_ref), y.ref(), _stream()), "groupnorm_apply")
     return y
+
+
+def wino_planes(T: int) -> int:
+    """Planes of the Winograd-T operand of a T-frame tensor (hyvae_wino_planes)."""
+    return 0 if T <= 0 else 1 + 4 * ((T - 1) // 2) + (3 if T % 2 == 0 else 0)
+
+
+def groupnorm_wino(x: Vol, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool) -> Vol:
+    """GroupNorm (+SiLU) written as the Winograd-T plane volume of the following stride-1 3x3x3 conv
+    (hyvae_groupnorm_apply_wino): [B][wino_planes(T)][H+2][W+2][C]; statistics as in groupnorm()."""
+    if x.gn_sums is not None and x.gn_groups == groups:
+        sums = x.gn_sums
+    else:
+        sums = torch.empty((x.B, groups, 2), dtype=torch.float64, device=x.device)
+        nbytes = lib().hyvae_groupnorm_workspace_bytes(x.ref(), groups)
+        if nbytes < 0:
+            raise HyvaeError(f"GroupNorm: unsupported channel count C={x.C} (needs C % 8 == 0)")
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+        _check(lib().hyvae_groupnorm_stats(x.ref(), groups, sums.data_ptr(), ws.data_ptr(), nbytes, _stream()), "groupnorm_stats")
+    y = Vol(x.B, wino_planes(x.T), x.H, x.W, x.C, x.dtype, x.device, (0, 1, 1))
+    y.wino_T = x.T
+    _check(lib().hyvae_groupnorm_apply_wino(x.ref(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), groups, eps, int(silu),
+                                            y.ref(), _stream()), "groupnorm_apply_wino")
+    return y
+
+
+def conv3d_wino(planes: Vol, uw: torch.Tensor, bias, cout: int, residual: Optional[Vol] = None, out_pad=(0, 0, 0),
+                gn_groups: int = 0) -> Vol:
+    """Stride-1 3x3x3 causal conv of the tensor whose Winograd-T planes are `planes` (hyvae_conv3d_causal_wino);
+    uw: [45][Cout][Cin] = the five tap groups of _Conv3dParams.wino_packed."""
+    T = planes.wino_T
+    assert T > 0, "conv3d_wino takes the plane volume written by groupnorm_wino"
+    y = Vol(planes.B, T, planes.H, planes.W, cout, planes.dtype, planes.device, tuple(out_pad))
+    with _GnEpilogue(planes, cout, gn_groups, 4) as gn:
+        part, groups = gn.args()
+        _check(lib().hyvae_conv3d_causal_wino(planes.ref(), T, uw.data_ptr(), _ptr(bias), residual.ref() if residual else None, y.ref(),
+                                              part, groups, _stream()), "conv3d_causal_wino")
+        return gn.finalize(y)
 
 
 def halo_fill(y: Vol) -> Vol:

@@ -31,6 +31,24 @@ void halo_geometry(int bn, int mt, bool pair, bool thin, int* twh, int* thh, int
 int launch_halo(int dtype, int bn, int mt, bool pair, bool thin, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
                 const CUtensorMap& tmR, const CUtensorMap& tmX, const CUtensorMap& tmW, const HaloArgs& a, cudaStream_t stream);
 
+// rows per batch item of the GroupNorm partial buffer: one per (CTA, epilogue warp); the Winograd kernel has 8 epilogue warps
+inline int gn_partial_rows() { return num_sms() * 8; }
+
+// conv_wino.cu: stride-1 3x3x3 conv as Winograd F(2,3) along T over a plane volume (see the header of that file)
+struct WinoArgs {
+  const float* bias;
+  int B, T, Ho, Wo, Cin, Cout;
+  int tiles_h, groups_w;   // 16-row x 8-column m-tiles
+  int gpf, upf;            // m-tiles per frame, CTA-pair units per frame (= ceil(gpf / 2))
+  int npairs, ntu;         // output-frame pairs (T - 1) / 2; time units 1 + npairs (+ 1 for an even T)
+  int n_tiles, total;      // 128-channel n-tiles; work items B * ntu * upf * n_tiles
+  int has_res;
+  double* gn_part;         // optional [B][gn_rows][gn_groups][2]
+  int gn_groups, gn_cpg, gn_rows;
+};
+int launch_wino(int dtype, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
+                const WinoArgs& a, cudaStream_t stream);
+
 // conv_stack.cu: stride-1 3x3x3 conv with Cout <= 8 (decoder conv_out), the nine (kh, kw) taps stacked along N.
 // A box {64, 18, 18}; B box {64, 80, 1} over the packed weights viewed as [kt][72][Cin].
 int launch_conv_stack(int dtype, const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloArgs& a, void* y, int64_t ysB, int64_t ysT,

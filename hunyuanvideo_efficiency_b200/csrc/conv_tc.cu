@@ -721,7 +721,7 @@ static void pick_tile(int Ho, int Wo, int sh, int sw, int* TH, int* TW) {
   *TW = best_tw; *TH = 128 / best_tw;
 }
 
-extern "C" int64_t hyvae_conv3d_tc_gn_rows(void) { return (int64_t)num_sms() * 4; }
+extern "C" int64_t hyvae_conv3d_tc_gn_rows(void) { return (int64_t)gn_partial_rows(); }
 
 static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
                          const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,
@@ -853,7 +853,7 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
     h.bias = bias; h.B = y->B; h.To = y->T; h.Ho = y->H; h.Wo = y->W; h.Cin = x->C; h.Cout = y->C;
     h.has_res = residual != nullptr; h.round_like_ref = round_like_ref;
     h.sc_cin = sc_x ? sc_x->C : 0; h.sc_chunks = (h.sc_cin + 63) / 64;
-    h.gn_part = gn_partials; h.gn_groups = gn_groups; h.gn_cpg = 0; h.gn_rows = num_sms() * 4; h.probe = a.probe;
+    h.gn_part = gn_partials; h.gn_groups = gn_groups; h.gn_cpg = 0; h.gn_rows = gn_partial_rows(); h.probe = a.probe;
     h.tfold = (w_has_fold && !thin) ? 1 : 0;
     h.kwpack = kwpack ? 1 : 0;
     HYVAE_CHECK_ARG(!kwpack || thin, "kw-packed input needs the thin halo kernel (Cin stored as 16, 64 < Cout <= 128)");
@@ -954,7 +954,7 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
   a.n_tiles = (y->C + BN - 1) / BN;
   a.m_tiles = (int64_t)y->B * y->T * a.tiles_h * a.tiles_w;
   a.m_tiles_per_b = (int64_t)y->T * a.tiles_h * a.tiles_w;
-  a.gn_part = gn_partials; a.gn_groups = gn_groups; a.gn_cpg = 0; a.gn_rows = num_sms() * 4;
+  a.gn_part = gn_partials; a.gn_groups = gn_groups; a.gn_cpg = 0; a.gn_rows = gn_partial_rows();
   if (gn_partials) {
     HYVAE_CHECK_ARG(gn_groups > 0 && y->C % gn_groups == 0, "gn_groups=%d does not divide Cout=%d", gn_groups, y->C);
     a.gn_cpg = y->C / gn_groups;
@@ -1094,7 +1094,7 @@ extern "C" int hyvae_conv3d_upphase_tc(const hyvae_vol* x, const void* w, const 
   a.m_tiles = (int64_t)y->B * To * a.tiles_h * a.tiles_w;
   a.m_tiles_per_b = (int64_t)To * a.tiles_h * a.tiles_w;
   a.total_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
-  a.gn_part = gn_partials; a.gn_groups = gn_groups; a.gn_cpg = 0; a.gn_rows = num_sms() * 4;
+  a.gn_part = gn_partials; a.gn_groups = gn_groups; a.gn_cpg = 0; a.gn_rows = gn_partial_rows();
   if (gn_partials) {
     HYVAE_CHECK_ARG(gn_groups > 0 && y->C % gn_groups == 0, "gn_groups=%d does not divide Cout=%d", gn_groups, y->C);
     a.gn_cpg = y->C / gn_groups;

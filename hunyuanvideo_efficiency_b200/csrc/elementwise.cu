@@ -293,6 +293,93 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(Vol x, Vol y, const do
   }
 }
 
+// GroupNorm apply (+SiLU) that writes the Winograd-T PLANE volume of the following stride-1 3x3x3 conv (conv_wino.cu):
+//   plane 0 = f(x[0]);  pair p: V0 = d0 - d2, V1 = d1 + d2, V2 = d2 - d1, V3 = d1 - d3 with d = f(x[max(2p-1,0)]), f(x[2p]),
+//   f(x[2p+1]), f(x[2p+2]);  even T: V0, V1, V2 of the last frame;  f = SiLU(GroupNorm(.)) evaluated in fp32, each plane
+//   rounded once.  A thread owns one (padded row, padded column, 8-channel vector) and walks T, so every input voxel is
+//   read once (the two previous frames stay in registers) and 2 planes are written per input frame; the 1-voxel replicate
+//   halo of the planes comes from clamping the source coordinates (replicate padding commutes with the transform).
+template <typename T, bool SILU>
+__global__ void __launch_bounds__(256) gn_apply_wino_kernel(Vol x, Vol y, int Tn, const double* __restrict__ sums, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int groups, float eps, double inv_n) {
+  extern __shared__ float sh[];  // scale[C], shift[C]
+  const int C = x.C, CV = C / 8, b = blockIdx.y;
+  const int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double mean = sums[((int64_t)b * groups + g) * 2] * inv_n;
+    double var = fma(-mean, mean, sums[((int64_t)b * groups + g) * 2 + 1] * inv_n);
+    if (var < 0) var = 0;
+    const float rstd = __frsqrt_rn((float)(var + (double)eps));
+    const float sc = gamma[c] * rstd;
+    sh[c] = sc;
+    sh[C + c] = beta[c] - (float)mean * sc;
+  }
+  __syncthreads();
+  const int Wp = y.Wp(), Hp = y.Hp();
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)Hp * Wp * CV) return;
+  const int cv = (int)(idx % CV);
+  const int wp = (int)((idx / CV) % Wp), hp = (int)(idx / ((int64_t)CV * Wp));
+  const int h = min(max(hp - 1, 0), x.H - 1), w = min(max(wp - 1, 0), x.W - 1);
+  float rsc[8], rsf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { rsc[j] = sh[cv * 8 + j]; rsf[j] = sh[C + cv * 8 + j]; }
+  const T* src = reinterpret_cast<const T*>(x.p) + x.at(b, 0, h, w) + cv * 8;
+  T* dst = reinterpret_cast<T*>(y.p) + (int64_t)b * y.sB + (int64_t)hp * y.sH + (int64_t)wp * y.sW + cv * 8;
+  auto act = [&](const Vec8<T>& q, float* f) {
+    q.get(f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = gn_act<T, SILU, false>(fmaf(f[j], rsc[j], rsf[j]));
+  };
+  auto put = [&](int plane, const float* f) { Vec8<T> o; o.set(f); o.store(dst + (int64_t)plane * y.sT); };
+  float da[8], db[8];  // f(x[max(2p-1, 0)]), f(x[2p])
+  {
+    Vec8<T> q; q.load(src);
+    act(q, db);
+    put(0, db);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) da[j] = db[j];
+  }
+  const int P = (Tn - 1) / 2;
+  Vec8<T> n2, n3;  // software pipeline: the next pair's two frames are in flight while this pair is transformed
+  if (P > 0) { n2.load(src + (int64_t)1 * x.sT); n3.load(src + (int64_t)2 * x.sT); }
+  for (int p = 0; p < P; ++p) {
+    const Vec8<T> q2 = n2, q3 = n3;
+    if (p + 1 < P) { n2.load(src + (int64_t)(2 * p + 3) * x.sT); n3.load(src + (int64_t)(2 * p + 4) * x.sT); }
+    float d2[8], d3[8], v[8];
+    act(q2, d2); act(q3, d3);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = da[j] - d2[j];
+    put(1 + 4 * p, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = db[j] + d2[j];
+    put(2 + 4 * p, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = d2[j] - db[j];
+    put(3 + 4 * p, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = db[j] - d3[j];
+    put(4 + 4 * p, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { da[j] = d2[j]; db[j] = d3[j]; }
+  }
+  if ((Tn & 1) == 0) {  // even T: the last frame alone (three planes)
+    Vec8<T> q; q.load(src + (int64_t)(Tn - 1) * x.sT);
+    float d2[8], v[8];
+    act(q, d2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = da[j] - d2[j];
+    put(1 + 4 * P, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = db[j] + d2[j];
+    put(2 + 4 * P, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = d2[j] - db[j];
+    put(3 + 4 * P, v);
+  }
+}
+
 // Sum per-tile GroupNorm partials (written by the conv epilogue) in a fixed order: grid = (groups, B).
 // part: [B][rows][groups][2] fp64 -> sums: [B][groups][2] fp64.  One block per (group, batch); threads stride
 // over rows, then a fixed-shape tree in shared memory: bit-reproducible.
@@ -690,6 +777,36 @@ int hyvae_groupnorm_apply(const hyvae_vol* x, const double* sums, const float* g
   else { if (round_like_ref) { HYVAE_GN_LAUNCH(false, true); } else { HYVAE_GN_LAUNCH(false, false); } }
 #undef HYVAE_GN_LAUNCH
   return check_launch("groupnorm_apply");
+}
+
+int hyvae_groupnorm_apply_wino(const hyvae_vol* x, const double* sums, const float* gamma, const float* beta, int32_t groups,
+                               float eps, int32_t silu, const hyvae_vol* planes, void* stream) {
+  if (int e = check_vol(x, "x")) return e;
+  if (int e = check_vol(planes, "planes")) return e;
+  HYVAE_CHECK_ARG(sums && gamma && beta, "null parameter");
+  HYVAE_CHECK_ARG(x->dtype == planes->dtype && x->dtype != HYVAE_F32, "Winograd planes are 16-bit, in x's dtype");
+  const int np = x->T <= 0 ? 0 : 1 + 4 * ((x->T - 1) / 2) + ((x->T % 2 == 0) ? 3 : 0);
+  HYVAE_CHECK_ARG(planes->B == x->B && planes->T == np && planes->H == x->H && planes->W == x->W && planes->C == x->C &&
+                  planes->pt == 0 && planes->ph == 1 && planes->pw == 1,
+                  "planes must be [B][%d][H+2][W+2][C] with halo (0,1,1)", np);
+  HYVAE_CHECK_ARG(groups > 0 && x->C % groups == 0 && x->C % 8 == 0 && x->C <= 4096, "bad C=%d / groups=%d", x->C, groups);
+  Vol vx = make_vol(x), vy = make_vol(planes);
+  char tag[56];
+  snprintf(tag, sizeof(tag), "gn C%d %dx%dx%dx%d wino", x->C, x->B, x->T, x->H, x->W);
+  // algorithmic bytes as for hyvae_groupnorm_apply (1 read + 1 write of the tensor); the kernel WRITES ~2x that
+  ProfScope prof(PC_GN_APPLY, 2.0 * x->B * x->T * x->H * x->W * x->C * dtype_size(x->dtype), stream, tag);
+  const int64_t nthreads = (int64_t)vy.Hp() * vy.Wp() * (x->C / 8);
+  dim3 grid((unsigned)((nthreads + 255) / 256), (unsigned)x->B);
+  const size_t smem = sizeof(float) * 2 * x->C;
+  const double inv_n = 1.0 / ((double)x->T * x->H * x->W * (x->C / groups));
+  if (x->dtype == HYVAE_BF16) {
+    if (silu) gn_apply_wino_kernel<__nv_bfloat16, true><<<grid, 256, smem, (cudaStream_t)stream>>>(vx, vy, x->T, sums, gamma, beta, groups, eps, inv_n);
+    else gn_apply_wino_kernel<__nv_bfloat16, false><<<grid, 256, smem, (cudaStream_t)stream>>>(vx, vy, x->T, sums, gamma, beta, groups, eps, inv_n);
+  } else {
+    if (silu) gn_apply_wino_kernel<__half, true><<<grid, 256, smem, (cudaStream_t)stream>>>(vx, vy, x->T, sums, gamma, beta, groups, eps, inv_n);
+    else gn_apply_wino_kernel<__half, false><<<grid, 256, smem, (cudaStream_t)stream>>>(vx, vy, x->T, sums, gamma, beta, groups, eps, inv_n);
+  }
+  return check_launch("groupnorm_apply_wino");
 }
 
 int hyvae_groupnorm_finalize(double* partials, int32_t B, int64_t rows, int32_t groups, double* sums, void* stream) {

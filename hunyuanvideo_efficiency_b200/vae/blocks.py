@@ -105,6 +105,24 @@ class _Conv3dParams(nn.Module):
             _publish(self._packed[1])
         return self._packed[1], self._packed[2]
 
+    def wino_packed(self, dtype):
+        """[5 * 9][Cout][Cin] tap groups of the Winograd-T form of this stride-1 3x3x3 conv (csrc/conv_wino.cu):
+        g0, (g0 + g1 + g2) / 2, (g0 - g1 + g2) / 2, g2 and g0 + g1 + g2 (g_kt = W[:, :, kt]), each [(kh, kw)][Cout][Cin];
+        formed in fp32 and rounded once.  Cached per parameter version."""
+        w = self.weight
+        key = ("wino", w._version, w.data_ptr(), dtype, w.device, None if self.bias is None else self.bias._version)
+        cached = getattr(self, "_wino_packed", None)
+        if cached is None or cached[0] != key:
+            assert self.kernel_size[0] == 3
+            w32 = w.detach().float().permute(2, 3, 4, 0, 1)                      # [kt][kh][kw][Cout][Cin]
+            g0, g1, g2 = w32[0], w32[1], w32[2]
+            u = torch.stack([g0, (g0 + g1 + g2) / 2, (g0 - g1 + g2) / 2, g2, g0 + g1 + g2], 0)
+            pw = u.reshape(45, self.out_channels, self.in_channels).to(dtype).contiguous()
+            pb = None if self.bias is None else self.bias.detach().float().contiguous()
+            self._wino_packed = cached = (key, pw, pb)
+            _publish(pw)
+        return cached[1], cached[2]
+
     def kw_packable(self) -> bool:
         """conv_in-like layer served by the thin halo kernel whose three kw taps fit one 16-channel row (3 * Cin <= 16)."""
         return (self.cin_padded() == 16 and 3 * self.in_channels <= 16 and self.kernel_size[0] == 3
@@ -177,6 +195,15 @@ class CausalConv3d(nn.Module):
         c = self.conv
         return self.halo if tc_eligible(dtype, c.in_channels, c.out_channels, c.stride, c.kernel_size[0]) else (0, 0, 0)
 
+    def wants_wino(self, dtype) -> bool:
+        """True when the GroupNorm that feeds this conv should write the Winograd-T plane volume (csrc/conv_wino.cu): stride-1
+        3x3x3, fp16 operands (like the sub-pixel phases, the transformed taps need fp16's mantissa), Cin % 64 == 0 and
+        Cout % 128 == 0.  HYVAE_WINO=0 switches it off (A/B measurements, parity tests against the plain path)."""
+        c = self.conv
+        return (os.environ.get("HYVAE_WINO", "1") == "1" and dtype == torch.float16 and c.kernel_size[0] == 3
+                and tuple(int(v) for v in c.stride) == (1, 1, 1) and c.in_channels % 64 == 0 and c.out_channels % 128 == 0
+                and c.bias is not None and tc_eligible(dtype, c.in_channels, c.out_channels, (1, 1, 1), 3))
+
     def wants_kw_pack(self, dtype) -> bool:
         """True when the producer (the NCTHW -> volume layout pass) should write the kw-packed operand (conv_in)."""
         c = self.conv
@@ -196,6 +223,12 @@ class CausalConv3d(nn.Module):
         c = self.conv
         k, stride = c.kernel_size[0], tuple(int(s) for s in c.stride)
         rl = False  # one rounding per stored tensor: conv + bias + residual are summed in fp32, then stored
+        if x.wino_T:   # the producer (GroupNorm) wrote the Winograd-T planes: 4 instead of 6 plane-GEMMs per frame pair
+            assert self.wants_wino(x.dtype) and x.C == c.in_channels and up == (1, 1, 1) and out_dtype in (None, x.dtype)
+            w, b = c.wino_packed(x.dtype)
+            y = N.conv3d_wino(x, w, b, c.out_channels, residual, out_pad, gn_groups=self.emit_gn_groups)
+            N.halo_fill(y)
+            return y
         if x.kw_packed:   # conv_in on the operand the layout pass packed for it: 9 (kt, kh) taps of K = 16
             assert self.wants_kw_pack(x.dtype) and x.pad == self.halo and x.C == 16 and residual is None and up == (1, 1, 1)
             w, b = c.packed_kw(x.dtype)
@@ -246,8 +279,11 @@ class _GroupNorm(nn.Module):
             _publish(self._f32[1])
         return self._f32[1], self._f32[2]
 
-    def forward_vol(self, x: Vol, silu: bool, pad=(0, 0, 0)) -> Vol:
+    def forward_vol(self, x: Vol, silu: bool, pad=(0, 0, 0), wino: bool = False) -> Vol:
+        """wino: write the Winograd-T plane volume the consumer conv asked for (CausalConv3d.wants_wino) instead of `pad`."""
         g, b = self._params()
+        if wino:
+            return N.groupnorm_wino(x, g, b, self.num_groups, self.eps, silu)
         return N.groupnorm(x, g, b, self.num_groups, self.eps, silu, pad, False)
 
 
@@ -370,9 +406,11 @@ class ResnetBlockCausal3D(nn.Module):
         """out_pad: halo the block's consumer (a down / upsampler conv) wants on the result; see CausalConv3d.forward_vol."""
         if self.output_scale_factor != 1.0:
             raise NotImplementedError("output_scale_factor != 1")
-        h = self.norm1.forward_vol(x, True, self.conv1.wants_halo(x.dtype))
+        h = self.norm1.forward_vol(x, True, self.conv1.wants_halo(x.dtype), wino=self.conv1.wants_wino(x.dtype))
         h = self.conv1.forward_vol(h)
-        h = self.norm2.forward_vol(h, True, self.conv2.wants_halo(x.dtype))
+        # conv2 with a fused 1x1x1 shortcut stays on the halo / kh-trick kernels (the shortcut rides in their accumulator)
+        w2 = self.conv_shortcut is None and self.conv2.wants_wino(x.dtype)
+        h = self.norm2.forward_vol(h, True, self.conv2.wants_halo(x.dtype), wino=w2)
         if self.conv_shortcut is not None and self._can_fuse_shortcut(h, x):
             return self._conv2_with_shortcut(h, x, out_pad)
         skip = x if self.conv_shortcut is None else self.conv_shortcut.forward_vol(x)

@@ -103,6 +103,24 @@ int hyvae_conv3d_causal_tc_shortcut(const hyvae_vol* x, const void* w, const flo
  * The caller issues 4 (up_t == 1) or 8 calls per conv. */
 int hyvae_conv3d_upphase_tc(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* y, int32_t up_t,
                             int32_t pt, int32_t ph, int32_t pw, double* gn_partials, int32_t gn_groups, void* stream);
+/* ---- stride-1 3x3x3 CausalConv3d as Winograd F(2,3) along T ------------------------------------------
+ * Same op as hyvae_conv3d_causal_tc (k = 3, stride 1; unet_causal_3d_blocks.py:68-75, residual :415) with 1.5x fewer MACs:
+ * two output frames come from four transformed PLANES and four 9-tap GEMMs instead of six (oracle/winograd.py restates the
+ * algebra).  The operand is written by hyvae_groupnorm_apply_wino (every stride-1 3x3x3 conv of a ResnetBlockCausal3D is
+ * fed by GroupNorm + SiLU, :359-363,401-405):
+ *   planes: [B][NP][H+2][W+2][Cin], halo (0,1,1), NP = hyvae_wino_planes(T) = 1 + 4*((T-1)/2) (+3 for an even T):
+ *           plane 0 = f(x[0]); pair p (output frames 2p+1, 2p+2): d0 - d2, d1 + d2, d2 - d1, d1 - d3 with
+ *           d = f(x[max(2p-1,0)]), f(x[2p]), f(x[2p+1]), f(x[2p+2]); an even T ends with the first three of
+ *           (x[T-3], x[T-2], x[T-1]).
+ *   uw:     [5][9][Cout][Cin] tap groups in the planes' dtype: g0, (g0+g1+g2)/2, (g0-g1+g2)/2, g2, g0+g1+g2 (g_kt = W[:,:,kt]),
+ *           each [kh*3+kw][Cout][Cin].
+ *   y, residual, bias, gn_partials: as for hyvae_conv3d_causal_tc (y may carry a halo: only its interior is written).
+ * Cin % 64 == 0 and Cout % 128 == 0, else HYVAE_EUNSUPPORTED (the caller then runs the plain path). */
+int32_t hyvae_wino_planes(int32_t T);
+int hyvae_groupnorm_apply_wino(const hyvae_vol* x, const double* sums, const float* gamma, const float* beta, int32_t groups,
+                               float eps, int32_t silu, const hyvae_vol* planes, void* stream);
+int hyvae_conv3d_causal_wino(const hyvae_vol* planes, int32_t T, const void* uw, const float* bias, const hyvae_vol* residual,
+                             const hyvae_vol* y, double* gn_partials, int32_t gn_groups, void* stream);
 /* rows-per-batch of the gn_partials buffer: gn_partials is [B][rows][gn_groups][2] fp64, ZEROED by the caller; every
  * (CTA, warp) of the conv accumulates into its own row, so several launches may add into one buffer (the phases of
  * an upsampling conv) before hyvae_groupnorm_finalize reduces the rows in a fixed order. */

@@ -473,6 +473,87 @@ def test_tc_first_frame_temporal_fold_matches_unfolded(Cin, Cout, T, H, W, varia
     assert torch.allclose(y0.gn_sums, y1.gn_sums, rtol=2e-3, atol=1.0)
 
 
+def _wino_planes_ref(f):
+    """Planes of conv_wino.cu's operand from f = SiLU(GroupNorm(x)) [B][C][T][H][W] (oracle/winograd.py with the pairs
+    starting at frame 1: plane 0 = f[0]; pair p = frames (2p+1, 2p+2); an even T ends with three planes)."""
+    T = f.shape[2]
+    xp = torch.cat([f[:, :, :1], f[:, :, :1], f], 2)
+    out = [f[:, :, 0]]
+    for p in range((T - 1) // 2):
+        d = [xp[:, :, 2 * p + 1 + i] for i in range(4)]
+        out += [d[0] - d[2], d[1] + d[2], d[2] - d[1], d[1] - d[3]]
+    if T % 2 == 0:
+        d = [xp[:, :, T - 1 + i] for i in range(3)]
+        out += [d[0] - d[2], d[1] + d[2], d[2] - d[1]]
+    return torch.stack(out, 2)
+
+
+@pytest.mark.parametrize("B,Cin,Cout,T,H,W,res,gn", [
+    (1, 64, 128, 1, 16, 16, False, False),     # a single frame: only the folded first-frame GEMM
+    (1, 64, 128, 2, 9, 21, True, False),       # even T: frame 0 + the 3-GEMM tail, ragged tile, odd m-tile count
+    (1, 128, 128, 9, 40, 24, True, True),      # four pairs, residual + GroupNorm statistics of the output
+    (2, 64, 256, 4, 20, 18, False, True),      # batch 2, even T with a pair, two n-tiles
+    (1, 256, 512, 3, 16, 24, True, True),      # four n-tiles, an odd number of m-tiles (half-empty CTA pair)
+    (1, 512, 512, 5, 32, 32, True, True),      # the mid-block geometry
+])
+def test_tc_winograd_t_conv_matches_oracle(B, Cin, Cout, T, H, W, res, gn):
+    """GroupNorm + SiLU written as Winograd-T planes (hyvae_groupnorm_apply_wino) followed by hyvae_conv3d_causal_wino, against
+    the oracle's SiLU(GroupNorm) -> causal_conv3d (+ residual) in fp32 on the same fp16-rounded parameters: <= 2e-3 relative
+    (the direct fp16 kernel is at ~3.6e-4; the transformed operands add one rounding).  Also the plane volume itself."""
+    import torch.nn.functional as F
+    from hunyuanvideo_efficiency_b200.vae.blocks import CausalConv3d, _GroupNorm
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    g = torch.Generator().manual_seed(B * 1000 + Cin + T)
+    x = torch.randn(B, Cin, T, H, W, generator=g).half()
+    conv = CausalConv3d(Cin, Cout, 3).to(_dev())
+    norm = _GroupNorm(32, Cin).to(_dev())
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.1 * torch.randn(Cin, generator=g))
+        norm.bias.copy_(0.1 * torch.randn(Cin, generator=g))
+    conv.emit_gn_groups = 32 if gn else 0
+    assert conv.wants_wino(torch.float16)
+    f = F.silu(O.group_norm(x.float(), norm.weight.detach().cpu(), norm.bias.detach().cpu(), 32))
+    ref = O.causal_conv3d(f, conv.conv.weight.detach().cpu().half().float(), conv.conv.bias.detach().cpu().float())
+    r = torch.randn(B, Cout, T, H, W, generator=g).half() if res else None
+    if res:
+        ref = ref + r.float()
+    pl = norm.forward_vol(_vol(x), True, wino=True)
+    assert pl.wino_T == T and pl.T == N.wino_planes(T) and pl.pad == (0, 1, 1)
+    got = pl.t[:, :, 1:-1, 1:-1, :].permute(0, 4, 1, 2, 3).float().cpu()
+    assert (got - _wino_planes_ref(f)).abs().max() < 4e-3                      # fp16 rounding of values up to ~8, tanh.approx SiLU
+    assert torch.equal(pl.t[:, :, 0], pl.t[:, :, 1]) and torch.equal(pl.t[:, :, :, -1], pl.t[:, :, :, -2])   # replicate halo
+    y = conv.forward_vol(pl, residual=_vol(r) if res else None)
+    out = y.to_ncthw().float().cpu()
+    assert O.rel_err(ref, out) < 2e-3, O.rel_err(ref, out)
+    if gn:
+        o64 = out.double().reshape(B, 32, Cout // 32, -1)
+        sq_ref = (o64 * o64).sum((2, 3))
+        assert ((y.gn_sums.cpu()[..., 1] - sq_ref).abs() / sq_ref).max() < 2e-3
+        assert (y.gn_sums.cpu()[..., 0] - o64.sum((2, 3))).abs().max() < 2e-3 * o64.abs().sum((2, 3)).max()
+    y2 = conv.forward_vol(norm.forward_vol(_vol(x), True, wino=True), residual=_vol(r) if res else None)
+    assert torch.equal(y.t, y2.t)                                              # static schedule: bit-reproducible
+
+
+def test_tc_winograd_t_matches_plain_path_in_a_resnet_block(monkeypatch):
+    """A ResnetBlockCausal3D with and without the Winograd-T convs (HYVAE_WINO=0): same block, same input, results within
+    the fp16 rounding of the transformed operands; out_pad (the halo'd destination a sampler conv asks for) is honoured."""
+    from hunyuanvideo_efficiency_b200.vae.blocks import ResnetBlockCausal3D
+    N = _N()
+    if not N.device_supports_tc():
+        pytest.skip("needs sm_100")
+    blk = ResnetBlockCausal3D(in_channels=128, out_channels=128, temb_channels=None).to(_dev())
+    x = torch.randn(1, 128, 7, 24, 40, generator=torch.Generator().manual_seed(3)).half()
+    n0 = N.launch_count()
+    y = blk.forward_vol(_vol(x), out_pad=(2, 1, 1))
+    assert y.pad == (2, 1, 1) and torch.equal(y.t[:, 0], y.t[:, 2]) and torch.equal(y.t[:, :, 0], y.t[:, :, 1])
+    yw = y.to_ncthw().float().cpu()
+    monkeypatch.setenv("HYVAE_WINO", "0")
+    yp = blk.forward_vol(_vol(x)).to_ncthw().float().cpu()
+    assert N.launch_count() > n0 and O.rel_err(yp, yw) < 1e-3, O.rel_err(yp, yw)
+
+
 def test_tc_gemm_k1_residual_and_fp16():
     N = _N()
     if not N.device_supports_tc():

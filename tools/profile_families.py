@@ -2,7 +2,7 @@
 import csv, collections, re, sys
 path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/profile_dump.csv"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-names = ["conv_tc", "conv_direct", "gn_stats", "gn_apply", "pad_upsample", "softmax", "layout", "blend", "temporal", "attn"]
+names = ["conv_tc", "conv_direct", "gn_stats", "gn_apply", "pad_upsample", "softmax", "layout", "blend", "temporal", "attn", "attn_proj"]
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
 for r in csv.DictReader(open(path)):
     tag, c = r["tag"], int(r["class"])
@@ -10,6 +10,8 @@ for r in csv.DictReader(open(path)):
         m = re.match(r"k\d (\d+)->(\d+)", tag)
         if tag.startswith("up"):
             key = "conv: upsample phases (pair kernel)"
+        elif "wino" in tag:
+            key = f"conv: wino {m.group(1)}->{m.group(2)}"
         elif "halo" in tag:
             key = f"conv: halo {m.group(1)}->{m.group(2)}"
         elif tag.startswith("k1"):
@@ -24,5 +26,5 @@ for r in csv.DictReader(open(path)):
 tot = sum(a[2] for a in agg.values())
 print(f"total device ms per step in profiled kernels: {tot / steps:.1f}")
 for k, (n, w, ms) in sorted(agg.items(), key=lambda kv: -kv[1][2]):
-    unit = "TFLOP/s (algorithmic)" if (k.startswith("conv") or k == "attn") else "TB/s (algorithmic)"
+    unit = "TFLOP/s (algorithmic)" if (k.startswith("conv") or k.startswith("attn")) else "TB/s (algorithmic)"
     print(f"{k:42s} launches/step={n // steps:6d}  ms/step={ms / steps:8.1f}  {100 * ms / tot:5.1f}%  {w / ms / 1e9:8.1f} {unit}")
