@@ -46,7 +46,7 @@ _SIGNATURES = {
     "hyvae_conv3d_upphase_tc": [_VP, _vp, _vp, _VP, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "hyvae_groupnorm_finalize": [_vp, _i32, _i64, _i32, _vp, _vp],
     "hyvae_groupnorm_apply_wino": [_VP, _vp, _vp, _vp, _i32, _f32, _i32, _VP, _vp],
-    "hyvae_conv3d_causal_wino": [_VP, _i32, _vp, _vp, _VP, _VP, _vp, _i32, _vp],
+    "hyvae_conv3d_causal_wino": [_VP, _i32, _vp, _vp, _VP, _VP, _vp, _VP, _vp, _i32, _vp],
     "hyvae_groupnorm_stats": [_VP, _i32, _vp, _vp, _i64, _vp],
     "hyvae_groupnorm_apply": [_VP, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _VP, _vp],
     "hyvae_pad_upsample": [_VP, _VP, _i32, _i32, _i32, _vp],
@@ -380,16 +380,18 @@ def groupnorm_wino(x: Vol, gamma: torch.Tensor, beta: torch.Tensor, groups: int,
 
 
 def conv3d_wino(planes: Vol, uw: torch.Tensor, bias, cout: int, residual: Optional[Vol] = None, out_pad=(0, 0, 0),
-                gn_groups: int = 0) -> Vol:
+                gn_groups: int = 0, sc_x: Optional[Vol] = None, sc_w: Optional[torch.Tensor] = None) -> Vol:
     """Stride-1 3x3x3 causal conv of the tensor whose Winograd-T planes are `planes` (hyvae_conv3d_causal_wino);
-    uw: [45][Cout][Cin] = the five tap groups of _Conv3dParams.wino_packed."""
+    uw: [45][Cout][Cin] = the five tap groups of _Conv3dParams.wino_packed.  sc_x / sc_w ([2][Cout][Csc] = +Ws, -Ws): the
+    resnet block's 1x1x1 conv_shortcut fused into the accumulators (`bias` is then the sum of both convs' biases)."""
     T = planes.wino_T
     assert T > 0, "conv3d_wino takes the plane volume written by groupnorm_wino"
     y = Vol(planes.B, T, planes.H, planes.W, cout, planes.dtype, planes.device, tuple(out_pad))
     with _GnEpilogue(planes, cout, gn_groups, 4) as gn:
         part, groups = gn.args()
-        _check(lib().hyvae_conv3d_causal_wino(planes.ref(), T, uw.data_ptr(), _ptr(bias), residual.ref() if residual else None, y.ref(),
-                                              part, groups, _stream()), "conv3d_causal_wino")
+        _check(lib().hyvae_conv3d_causal_wino(planes.ref(), T, uw.data_ptr(), _ptr(bias), residual.ref() if residual else None,
+                                              sc_x.ref() if sc_x is not None else None, _ptr(sc_w), y.ref(), part, groups, _stream()),
+               "conv3d_causal_wino")
         return gn.finalize(y)
 
 

@@ -43,11 +43,12 @@ struct WinoArgs {
   int npairs, ntu;         // output-frame pairs (T - 1) / 2; time units 1 + npairs (+ 1 for an even T)
   int n_tiles, total;      // 128-channel n-tiles; work items B * ntu * upf * n_tiles
   int has_res;
+  int sc_chunks, sc_cin;   // fused 1x1x1 shortcut conv: 64-channel chunks / channels of its input (0 = none)
   double* gn_part;         // optional [B][gn_rows][gn_groups][2]
   int gn_groups, gn_cpg, gn_rows;
 };
 int launch_wino(int dtype, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
-                const WinoArgs& a, cudaStream_t stream);
+                const CUtensorMap& tmX, const CUtensorMap& tmW, const WinoArgs& a, cudaStream_t stream);
 
 // conv_stack.cu: stride-1 3x3x3 conv with Cout <= 8 (decoder conv_out), the nine (kh, kw) taps stacked along N.
 // A box {64, 18, 18}; B box {64, 80, 1} over the packed weights viewed as [kt][72][Cin].

@@ -149,7 +149,8 @@ __device__ __forceinline__ void wino_epi_half(uint32_t tq /* tmem base + lane qu
 template <typename T>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WINO_THREADS, 1)
 conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const WinoArgs a) {
+                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const WinoArgs a) {
   using Cfg = WinoCfg;
   constexpr int NA = Cfg::NA, NB = Cfg::NB, PITCH = Cfg::PITCH;
   extern __shared__ uint8_t smem_raw[];
@@ -174,6 +175,7 @@ conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY);
     if (a.has_res) tma_prefetch_desc(&tmR);
+    if (a.sc_chunks) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW); }
     for (int s = 0; s < NA; ++s) { mbar_init(afull + 8 * s, 2); mbar_init(aempty + 8 * s, 1); }
     for (int s = 0; s < NB; ++s) { mbar_init(bfull + 8 * s, 2); mbar_init(bempty + 8 * s, 1); }
     for (int s = 0; s < 4; ++s) { mbar_init(accfull + 8 * s, 1); mbar_init(accempty + 8 * s, 256 * 2); }
@@ -188,6 +190,10 @@ conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int kchunks = a.Cin / 64;
+  // Fused 1x1x1 conv_shortcut of the resnet block (unet_causal_3d_blocks.py:338-348,407-415): extra K chunks at the centre
+  // tap, reading the block input's halo patch of the output frame.  y_a = M0 + ... takes + Ws * x[t_a] in accumulator 0;
+  // y_b = M1 - M2 - M3 takes - Ws * x[t_b] in accumulator 3 (tap 1 of tmW holds the negated weights).
+  auto sc_steps = [&](const WinoItem& m, int gi) -> int { return (a.sc_chunks && (gi == 0 || (gi == 3 && m.kind == 1))) ? a.sc_chunks : 0; };
   const uint32_t item0 = blockIdx.x >> 1, istride = gridDim.x >> 1, nitems = (uint32_t)a.total;
 
   if (warp == 0) {
@@ -195,17 +201,21 @@ conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int sa = 0; uint32_t pa = 0;
     for (uint32_t it = item0; it < nitems; it += istride) {
       const WinoItem m = wino_decode(a, it, rank);
-      for (int gi = 0; gi < m.ngemm; ++gi)
-        for (int kc = 0; kc < kchunks; ++kc) {
+      for (int gi = 0; gi < m.ngemm; ++gi) {
+        const int nsc = sc_steps(m, gi), nst = kchunks + nsc;
+        for (int st = 0; st < nst; ++st) {
+          const bool sc = st >= kchunks;   // shortcut input: logical (unpadded) coordinates, the 1-voxel rim of the box is never read
           mbar_wait(aempty + 8 * sa, pa ^ 1);
           if (elect_one()) {
             if (leader) mbar_expect_tx(afull + 8 * sa, 2 * Cfg::A_TX);
-            tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull + 8 * sa, kc * 64, m.w0, m.h0, m.plane0 + gi, m.b);
+            if (sc) tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmX, afull + 8 * sa, (st - kchunks) * 64, m.w0 - 1, m.h0 - 1, gi == 0 ? m.ta : m.tb, m.b);
+            else tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull + 8 * sa, st * 64, m.w0, m.h0, m.plane0 + gi, m.b);
             if (!leader) mbar_arrive_leader(afull + 8 * sa);
           }
           __syncwarp();
           if (++sa == NA) { sa = 0; pa ^= 1; }
         }
+      }
     }
   } else if (warp == 1) {
     // ================= B producer: this CTA's 64 rows of one tap's 128 x 64 weight tile per stage =================
@@ -213,19 +223,25 @@ conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (uint32_t it = item0; it < nitems; it += istride) {
       const WinoItem m = wino_decode(a, it, rank);
       const int n0 = m.nt * WINO_BN + (int)rank * (WINO_BN / 2);
-      for (int gi = 0; gi < m.ngemm; ++gi)
-        for (int kc = 0; kc < kchunks; ++kc)
+      for (int gi = 0; gi < m.ngemm; ++gi) {
+        const int nsc = sc_steps(m, gi), nst = kchunks + nsc;
+        for (int st = 0; st < nst; ++st) {
+          const bool sc = st >= kchunks;
+          const int ntap = sc ? 1 : 9;     // the shortcut has a single tap: + Ws (tap 0) for accumulator 0, - Ws (tap 1) for accumulator 3
 #pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < ntap; ++tap) {
             mbar_wait(bempty + 8 * sb, pb ^ 1);
             if (elect_one()) {
               if (leader) mbar_expect_tx(bfull + 8 * sb, 2 * Cfg::B_BYTES);
-              tma_load_3d_2sm(sB + sb * Cfg::B_BYTES, &tmB, bfull + 8 * sb, kc * 64, n0, (m.wgroup0 + gi) * 9 + tap);
+              if (sc) tma_load_3d_2sm(sB + sb * Cfg::B_BYTES, &tmW, bfull + 8 * sb, (st - kchunks) * 64, n0, gi == 0 ? 0 : 1);
+              else tma_load_3d_2sm(sB + sb * Cfg::B_BYTES, &tmB, bfull + 8 * sb, st * 64, n0, (m.wgroup0 + gi) * 9 + tap);
               if (!leader) mbar_arrive_leader(bfull + 8 * sb);
             }
             __syncwarp();
             if (++sb == NB) { sb = 0; pb ^= 1; }
           }
+        }
+      }
     }
   } else if (warp == 2) {
     if (leader) {
@@ -240,20 +256,26 @@ conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(accempty + 8 * gi, (use[gi] & 1) ^ 1);  // the epilogue has drained this accumulator's previous contents
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(gi * WINO_BN);
-          for (int kc = 0; kc < kchunks; ++kc) {
+          const int nsc = sc_steps(m, gi), nst = kchunks + nsc;
+          for (int kc = 0; kc < nst; ++kc) {
             mbar_wait(afull + 8 * sa, pa);
             const uint32_t a_stage = sA + sa * Cfg::A_BYTES;
+            const bool sc = kc >= kchunks;
+            const int ntap = sc ? 1 : 9;
+            const int rem = sc ? a.sc_cin - (kc - kchunks) * 64 : 64;   // K = 16 slices that hold real channels
+            const int nk = rem >= 64 ? 4 : (rem + 15) / 16;
 #pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < ntap; ++tap) {
               mbar_wait(bfull + 8 * sb, pb);
               tc_fence_after();
               if (elect_one()) {
-                const int kh = tap / 3, kw = tap - 3 * kh;
+                const int tap9 = sc ? 4 : tap;   // shortcut: centre tap (kh, kw) = (1, 1)
+                const int kh = tap9 / 3, kw = tap9 - 3 * kh;
                 const uint64_t adesc = wino_a_desc(a_stage + (uint32_t)((kh * PITCH + kw) * 128), PITCH * 128);
                 const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * Cfg::B_BYTES);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | tap | k) != 0);
+                  if (k < nk) umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | tap | k) != 0);
                 umma_commit_2sm(bempty + 8 * sb);
               }
               __syncwarp();
@@ -379,7 +401,7 @@ conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <typename T>
 static int launch_wino_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
-                         const WinoArgs& a, cudaStream_t stream) {
+                         const CUtensorMap& tmX, const CUtensorMap& tmW, const WinoArgs& a, cudaStream_t stream) {
   static DeviceOnce attr_once;
   if (attr_once.first()) {
     if (cudaFuncSetAttribute(conv_wino_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, WinoCfg::SMEM_BYTES) != cudaSuccess)
@@ -388,14 +410,14 @@ static int launch_wino_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   }
   const int64_t max_pairs = num_sms() / 2;
   const int64_t pairs = a.total < max_pairs ? a.total : max_pairs;
-  conv_wino_kernel<T><<<(unsigned)(2 * pairs), WINO_THREADS, WinoCfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, a);
+  conv_wino_kernel<T><<<(unsigned)(2 * pairs), WINO_THREADS, WinoCfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, tmX, tmW, a);
   return check_launch("conv3d_causal_wino");
 }
 
 int launch_wino(int dtype, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
-                const WinoArgs& a, cudaStream_t stream) {
-  if (dtype == HYVAE_BF16) return launch_wino_t<__nv_bfloat16>(tmA, tmB, tmY, tmR, a, stream);
-  return launch_wino_t<__half>(tmA, tmB, tmY, tmR, a, stream);
+                const CUtensorMap& tmX, const CUtensorMap& tmW, const WinoArgs& a, cudaStream_t stream) {
+  if (dtype == HYVAE_BF16) return launch_wino_t<__nv_bfloat16>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream);
+  return launch_wino_t<__half>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream);
 }
 
 }  // namespace hyvae
@@ -419,7 +441,8 @@ static WinoEncodeFn wino_encode_fn() {
 extern "C" int32_t hyvae_wino_planes(int32_t T) { return T <= 0 ? 0 : 1 + 4 * ((T - 1) / 2) + ((T % 2 == 0) ? 3 : 0); }
 
 extern "C" int hyvae_conv3d_causal_wino(const hyvae_vol* planes, int32_t T, const void* uw, const float* bias, const hyvae_vol* residual,
-                                        const hyvae_vol* y, double* gn_partials, int32_t gn_groups, void* stream) {
+                                        const hyvae_vol* sc_x, const void* sc_w, const hyvae_vol* y, double* gn_partials,
+                                        int32_t gn_groups, void* stream) {
   if (int e = check_vol(planes, "planes")) return e;
   if (int e = check_vol(y, "y")) return e;
   HYVAE_CHECK_ARG(uw != nullptr, "uw is null");
@@ -445,6 +468,14 @@ extern "C" int hyvae_conv3d_causal_wino(const hyvae_vol* planes, int32_t T, cons
   HYVAE_CHECK_ARG(total < (1ll << 31), "too many work items");
   a.total = (int)total;
   a.has_res = residual != nullptr;
+  a.sc_cin = sc_x ? sc_x->C : 0; a.sc_chunks = (a.sc_cin + 63) / 64;
+  if (sc_x != nullptr) {
+    if (int e = check_vol(sc_x, "sc_x")) return e;
+    HYVAE_CHECK_ARG(sc_w != nullptr && residual == nullptr, "fused shortcut: sc_w is null, or a residual was passed as well");
+    HYVAE_CHECK_ARG(sc_x->dtype == y->dtype && sc_x->B == y->B && sc_x->T == y->T && sc_x->H == y->H && sc_x->W == y->W && sc_x->C % 8 == 0,
+                    "shortcut input must have y's extent and dtype and C %% 8 == 0");
+    HYVAE_CHECK_ARG(((uintptr_t)sc_x->data & 15) == 0 && ((uintptr_t)sc_w & 15) == 0, "pointers must be 16-byte aligned");
+  }
   a.gn_part = gn_partials; a.gn_groups = gn_groups; a.gn_cpg = 0; a.gn_rows = gn_partial_rows();
   if (gn_partials) {
     HYVAE_CHECK_ARG(gn_groups > 0 && y->C % gn_groups == 0, "gn_groups=%d does not divide Cout=%d", gn_groups, y->C);
@@ -492,11 +523,30 @@ extern "C" int hyvae_conv3d_causal_wino(const hyvae_vol* planes, int32_t T, cons
   } else {
     tmR = tmY;
   }
+  CUtensorMap tmX = tmA, tmW = tmB;
+  if (sc_x) {
+    Vol vs = make_vol(sc_x);
+    cuuint64_t dims[5] = {(cuuint64_t)sc_x->C, (cuuint64_t)sc_x->W, (cuuint64_t)sc_x->H, (cuuint64_t)sc_x->T, (cuuint64_t)sc_x->B};
+    cuuint64_t strides[4] = {(cuuint64_t)vs.sW * 2, (cuuint64_t)vs.sH * 2, (cuuint64_t)vs.sT * 2, (cuuint64_t)vs.sB * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)WinoCfg::TWH, (cuuint32_t)WinoCfg::THH, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmX, dt, 5, (char*)sc_x->data + vs.at(0, 0, 0, 0) * 2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(shortcut x) failed with %d", (int)r);
+    cuuint64_t wd[3] = {(cuuint64_t)sc_x->C, (cuuint64_t)y->C, 2};   // [+Ws, -Ws]
+    cuuint64_t ws[2] = {(cuuint64_t)sc_x->C * 2, (cuuint64_t)sc_x->C * y->C * 2};
+    cuuint32_t wb[3] = {64, (cuuint32_t)(WINO_BN / 2), 1};
+    cuuint32_t we[3] = {1, 1, 1};
+    r = encode(&tmW, dt, 3, const_cast<void*>(sc_w), wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HYVAE_ECUDA, "cuTensorMapEncodeTiled(shortcut w) failed with %d", (int)r);
+  }
   char tag[56];
-  snprintf(tag, sizeof(tag), "k3 %d->%d %dx%dx%dx%d s111 wino", planes->C, y->C, y->B, y->T, y->H, y->W);
+  snprintf(tag, sizeof(tag), "k3 %d->%d %dx%dx%dx%d s111 wino%s", planes->C, y->C, y->B, y->T, y->H, y->W, sc_x ? "+sc" : "");
   const double vox1 = (double)y->B * y->H * y->W;
-  const double work = 2.0 * vox1 * T * y->C * planes->C * 27.0;                      // what the reference executes
-  const double executed = 2.0 * vox1 * hyvae_wino_planes(T) * y->C * planes->C * 9.0;  // one 9-tap GEMM per plane
+  const double sc_work = sc_x ? 2.0 * vox1 * T * y->C * sc_x->C : 0.0;
+  const double work = 2.0 * vox1 * T * y->C * planes->C * 27.0 + sc_work;                      // what the reference executes
+  const double executed = 2.0 * vox1 * hyvae_wino_planes(T) * y->C * planes->C * 9.0 + sc_work;  // one 9-tap GEMM per plane
   ProfScope prof(PC_CONV_TC, work, stream, tag, executed);
-  return launch_wino(planes->dtype, tmA, tmB, tmY, tmR, a, (cudaStream_t)stream);
+  return launch_wino(planes->dtype, tmA, tmB, tmY, tmR, tmX, tmW, a, (cudaStream_t)stream);
 }

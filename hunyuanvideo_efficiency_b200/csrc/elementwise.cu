@@ -389,11 +389,23 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(double* __restrict__ p
   const int g = blockIdx.x, b = blockIdx.y;
   double* p = part + ((int64_t)b * rows * groups + g) * 2;
   double a = 0.0, q = 0.0;
-  for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) {
-    double2* e = reinterpret_cast<double2*>(p + r * groups * 2);
-    const double2 v = *e;
-    a += v.x; q += v.y;
-    *e = make_double2(0.0, 0.0);  // leave the buffer zeroed for the next conv that accumulates into it
+  // eight independent 16-byte loads in flight per thread (the rows of one group are 512 B apart: a chain of dependent
+  // loads made this tiny kernel ~9 us); the summation order per thread is still row order: bit-reproducible
+  constexpr int U = 8;
+  for (int64_t r0 = threadIdx.x; r0 < rows; r0 += (int64_t)U * blockDim.x) {
+    double2 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + (int64_t)u * blockDim.x;
+      v[u] = r < rows ? *reinterpret_cast<const double2*>(p + r * groups * 2) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + (int64_t)u * blockDim.x;
+      a += v[u].x; q += v[u].y;
+      if (r < rows && (v[u].x != 0.0 || v[u].y != 0.0))   // leave the buffer zeroed for the next conv that accumulates into it
+        *reinterpret_cast<double2*>(p + r * groups * 2) = make_double2(0.0, 0.0);
+    }
   }
   sa[threadIdx.x] = a; sq[threadIdx.x] = q;
   __syncthreads();

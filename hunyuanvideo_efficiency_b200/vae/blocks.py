@@ -408,9 +408,10 @@ class ResnetBlockCausal3D(nn.Module):
             raise NotImplementedError("output_scale_factor != 1")
         h = self.norm1.forward_vol(x, True, self.conv1.wants_halo(x.dtype), wino=self.conv1.wants_wino(x.dtype))
         h = self.conv1.forward_vol(h)
-        # conv2 with a fused 1x1x1 shortcut stays on the halo / kh-trick kernels (the shortcut rides in their accumulator)
-        w2 = self.conv_shortcut is None and self.conv2.wants_wino(x.dtype)
+        w2 = self.conv2.wants_wino(x.dtype) and (self.conv_shortcut is None or self._can_fuse_wino_shortcut(x))
         h = self.norm2.forward_vol(h, True, self.conv2.wants_halo(x.dtype), wino=w2)
+        if w2 and self.conv_shortcut is not None:
+            return self._conv2_wino_with_shortcut(h, x, out_pad)
         if self.conv_shortcut is not None and self._can_fuse_shortcut(h, x):
             return self._conv2_with_shortcut(h, x, out_pad)
         skip = x if self.conv_shortcut is None else self.conv_shortcut.forward_vol(x)
@@ -425,6 +426,24 @@ class ResnetBlockCausal3D(nn.Module):
                 and c2.out_channels % 8 == 0 and cs.in_channels % 8 == 0 and x.C == cs.in_channels and h.pad == self.conv2.halo
                 and h.C == c2.in_channels and c2.bias is not None and cs.bias is not None
                 and tc_eligible(h.dtype, c2.in_channels, c2.out_channels, (1, 1, 1), 3))
+
+    def _can_fuse_wino_shortcut(self, x: Vol) -> bool:
+        """The 1x1x1 conv_shortcut as extra K chunks of the Winograd-T kernel's accumulators 0 and 3 (csrc/conv_wino.cu)."""
+        c2, cs = self.conv2.conv, self.conv_shortcut.conv
+        return (os.environ.get("HYVAE_FUSE_SHORTCUT", "1") == "1" and cs.in_channels % 8 == 0 and x.C == cs.in_channels
+                and c2.bias is not None and cs.bias is not None and cs.kernel_size[0] == 1)
+
+    def _conv2_wino_with_shortcut(self, h: Vol, x: Vol, out_pad=(0, 0, 0)) -> Vol:
+        c2, cs = self.conv2.conv, self.conv_shortcut.conv
+        w2, b2 = c2.wino_packed(h.dtype)
+        ws, bs = cs.packed(h.dtype, pad8=True)
+        key = ("wino", c2.bias._version, cs.bias._version, cs.weight._version, b2.data_ptr(), ws.data_ptr())
+        if getattr(self, "_wino_sc", None) is None or self._wino_sc[0] != key:
+            self._wino_sc = (key, (b2 + bs).contiguous(), torch.cat([ws, -ws], 0).contiguous())   # bias sum; (+Ws, -Ws)
+            _publish(self._wino_sc[2])
+        y = N.conv3d_wino(h, w2, self._wino_sc[1], c2.out_channels, None, tuple(out_pad), gn_groups=self.conv2.emit_gn_groups,
+                          sc_x=x, sc_w=self._wino_sc[2])
+        return N.halo_fill(y)
 
     def _conv2_with_shortcut(self, h: Vol, x: Vol, out_pad=(0, 0, 0)) -> Vol:
         c2, cs = self.conv2.conv, self.conv_shortcut.conv

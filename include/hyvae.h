@@ -115,12 +115,17 @@ int hyvae_conv3d_upphase_tc(const hyvae_vol* x, const void* w, const float* bias
  *   uw:     [5][9][Cout][Cin] tap groups in the planes' dtype: g0, (g0+g1+g2)/2, (g0-g1+g2)/2, g2, g0+g1+g2 (g_kt = W[:,:,kt]),
  *           each [kh*3+kw][Cout][Cin].
  *   y, residual, bias, gn_partials: as for hyvae_conv3d_causal_tc (y may carry a halo: only its interior is written).
+ *   sc_x, sc_w (or NULL, NULL): fused 1x1x1 conv_shortcut of the resnet block (:338-348,407-415) as in
+ *           hyvae_conv3d_causal_tc_shortcut: y = conv(x) + conv1x1x1(sc_x) + bias with bias = conv2.bias + conv_shortcut.bias;
+ *           sc_x is the block input (y's extent, any halo, C % 8 == 0) and sc_w is [2][Cout][Csc] = (+Ws, -Ws): the second
+ *           output frame of a pair is M1 - M2 - M3, so its shortcut term rides, negated, in M3's accumulator.
  * Cin % 64 == 0 and Cout % 128 == 0, else HYVAE_EUNSUPPORTED (the caller then runs the plain path). */
 int32_t hyvae_wino_planes(int32_t T);
 int hyvae_groupnorm_apply_wino(const hyvae_vol* x, const double* sums, const float* gamma, const float* beta, int32_t groups,
                                float eps, int32_t silu, const hyvae_vol* planes, void* stream);
 int hyvae_conv3d_causal_wino(const hyvae_vol* planes, int32_t T, const void* uw, const float* bias, const hyvae_vol* residual,
-                             const hyvae_vol* y, double* gn_partials, int32_t gn_groups, void* stream);
+                             const hyvae_vol* sc_x, const void* sc_w, const hyvae_vol* y, double* gn_partials, int32_t gn_groups,
+                             void* stream);
 /* rows-per-batch of the gn_partials buffer: gn_partials is [B][rows][gn_groups][2] fp64, ZEROED by the caller; every
  * (CTA, warp) of the conv accumulates into its own row, so several launches may add into one buffer (the phases of
  * an upsampling conv) before hyvae_groupnorm_finalize reduces the rows in a fixed order. */

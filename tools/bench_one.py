@@ -25,6 +25,19 @@ if what in CASES:
         r = N.Vol(1, T, H, W, Cout, torch.float16, dev); r.t.normal_()
     for _ in range(4):
         N.conv3d_tc(x, w, b, 3, (1, 1, 1), Cout, residual=r, out=y, gn_groups=32 if Cout >= 64 else 0, variant=variant)
+elif what.startswith("wino"):   # Winograd-T conv (+ the plane-writing GroupNorm apply that feeds it): wino128 / wino256 / wino512 / winogn128
+    from hunyuanvideo_efficiency_b200.vae.blocks import CausalConv3d, _GroupNorm
+    Cn, T, H, W = {"wino128": (128, 17, 256, 256), "winogn128": (128, 17, 256, 256), "wino256": (256, 17, 128, 128), "wino512": (512, 17, 32, 32)}[what]
+    conv = CausalConv3d(Cn, Cn, 3).to(dev); conv.emit_gn_groups = 32
+    norm = _GroupNorm(32, Cn).to(dev)
+    x = N.Vol(1, T, H, W, Cn, torch.float16, dev); x.t.normal_()
+    N.groupnorm(x, *norm._params(), 32, 1e-6, True)   # statistics once (x.gn_sums stays None: use the stats kernel below only once)
+    sums = torch.zeros((1, 32, 2), dtype=torch.float64, device=dev); sums[:, :, 1] = float(T * H * W * (Cn // 32))
+    x.gn_sums, x.gn_groups = sums, 32
+    r = N.Vol(1, T, H, W, Cn, torch.float16, dev); r.t.normal_()
+    for _ in range(4):
+        pl = norm.forward_vol(x, True, wino=True)
+        conv.forward_vol(pl, residual=r)
 elif what == "phase":   # decoder up_block2 upsampler: 256 -> 256, low-res 9 x 128 x 128 -> 17 x 256 x 256
     from hunyuanvideo_efficiency_b200.vae.blocks import UpsampleCausal3D
     m = UpsampleCausal3D(256, use_conv=True, out_channels=256, upsample_factor=(2, 2, 2)).to(dev)
