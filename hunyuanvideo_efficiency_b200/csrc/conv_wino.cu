@@ -37,19 +37,28 @@ namespace hyvae {
 constexpr int WINO_THREADS = 352;
 constexpr int WINO_BN = 128;
 
-struct WinoCfg {
+// Shared-memory plan.  A B stage holds the THREE kw taps of one kh row (one TMA box {64, 64, 3}): the MMA warp then pays one
+// barrier wait, one elect and one commit per 12 MMAs.  With one tap per stage (the first version) its issue loop took ~360
+// clocks per stage against 256 clocks of MMA work and the tensor pipe was active 54 % of the time (ncu,
+// profiles/r02_ncu_conv_wino_128_v1.txt); the direct kernels hide the same loop behind 8 MMAs per stage.
+template <int NA_, int NB_> struct WinoCfgT {
   static constexpr int TWH = 10, THH = 18, PITCH = TWH;
   static constexpr int A_TX = TWH * THH * 128;                      // 23040 bytes per plane stage
   static constexpr int A_BYTES = (A_TX + 1023) / 1024 * 1024;
-  static constexpr int NA = 3;
-  static constexpr int B_BYTES = (WINO_BN / 2) * 128;               // this CTA's half of one tap's weight tile (8 KB)
-  static constexpr int NB = 10;
+  static constexpr int NA = NA_;
+  static constexpr int TB = 3;                                      // taps per B stage
+  static constexpr int B_TAP_BYTES = (WINO_BN / 2) * 128;           // this CTA's half of one tap's weight tile (8 KB)
+  static constexpr int B_BYTES = TB * B_TAP_BYTES;
+  static constexpr int NB = NB_;
   static constexpr int OUT_BYTES = 2 * 2 * 16384;                   // [y_a, y_b][64-channel half][128 rows x 128 B]
   static constexpr int BAR_BYTES = 1024;
   static constexpr int BIAS_BYTES = 8 * 64 * 4;
   static constexpr int SMEM_BYTES = NA * A_BYTES + NB * B_BYTES + OUT_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(8 * (2 * NA + 2 * NB + 8 + 8) + 8 <= BAR_BYTES, "barrier block");
 };
+using WinoCfg = WinoCfgT<3, 3>;      // deep A ring (the planes stream from HBM)
+using WinoCfgB = WinoCfgT<2, 4>;     // deep B ring (HYVAE_WINO_CFG=1; A/B measurements)
 
 __device__ __forceinline__ uint64_t wino_a_desc(uint32_t addr, uint32_t sbo_bytes) {  // see make_halo_desc in conv_halo.cu
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
@@ -146,12 +155,11 @@ __device__ __forceinline__ void wino_epi_half(uint32_t tq /* tmem base + lane qu
     default: wino_epi_half<T, 32, MODE>(__VA_ARGS__); break;                \
   }
 
-template <typename T>
+template <typename T, typename Cfg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WINO_THREADS, 1)
 conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const WinoArgs a) {
-  using Cfg = WinoCfg;
   constexpr int NA = Cfg::NA, NB = Cfg::NB, PITCH = Cfg::PITCH;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -218,35 +226,46 @@ conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ================= B producer: this CTA's 64 rows of one tap's 128 x 64 weight tile per stage =================
+    // ================= B producer: this CTA's 64 rows of the three kw taps of one kh row per stage =================
     int sb = 0; uint32_t pb = 0;
     for (uint32_t it = item0; it < nitems; it += istride) {
       const WinoItem m = wino_decode(a, it, rank);
       const int n0 = m.nt * WINO_BN + (int)rank * (WINO_BN / 2);
       for (int gi = 0; gi < m.ngemm; ++gi) {
-        const int nsc = sc_steps(m, gi), nst = kchunks + nsc;
-        for (int st = 0; st < nst; ++st) {
-          const bool sc = st >= kchunks;
-          const int ntap = sc ? 1 : 9;     // the shortcut has a single tap: + Ws (tap 0) for accumulator 0, - Ws (tap 1) for accumulator 3
+        const int nsc = sc_steps(m, gi);
+        for (int st = 0; st < kchunks; ++st) {
 #pragma unroll 1
-          for (int tap = 0; tap < ntap; ++tap) {
+          for (int kh = 0; kh < 3; ++kh) {
             mbar_wait(bempty + 8 * sb, pb ^ 1);
             if (elect_one()) {
               if (leader) mbar_expect_tx(bfull + 8 * sb, 2 * Cfg::B_BYTES);
-              if (sc) tma_load_3d_2sm(sB + sb * Cfg::B_BYTES, &tmW, bfull + 8 * sb, (st - kchunks) * 64, n0, gi == 0 ? 0 : 1);
-              else tma_load_3d_2sm(sB + sb * Cfg::B_BYTES, &tmB, bfull + 8 * sb, st * 64, n0, (m.wgroup0 + gi) * 9 + tap);
+              tma_load_3d_2sm(sB + sb * Cfg::B_BYTES, &tmB, bfull + 8 * sb, st * 64, n0, (m.wgroup0 + gi) * 9 + kh * 3);
               if (!leader) mbar_arrive_leader(bfull + 8 * sb);
             }
             __syncwarp();
             if (++sb == NB) { sb = 0; pb ^= 1; }
           }
         }
+        for (int c = 0; c < nsc; ++c) {   // the shortcut has a single tap: + Ws (tap 0) for accumulator 0, - Ws (tap 1) for accumulator 3
+          mbar_wait(bempty + 8 * sb, pb ^ 1);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(bfull + 8 * sb, 2 * Cfg::B_TAP_BYTES);
+            tma_load_3d_2sm(sB + sb * Cfg::B_BYTES, &tmW, bfull + 8 * sb, c * 64, n0, gi == 0 ? 0 : 1);
+            if (!leader) mbar_arrive_leader(bfull + 8 * sb);
+          }
+          __syncwarp();
+          if (++sb == NB) { sb = 0; pb ^= 1; }
+        }
       }
     }
   } else if (warp == 2) {
     if (leader) {
       // ================= MMA issuer (leader CTA; warp-uniform loops, one elected lane issues) =================
+      // Per B stage: one wait, then 12 MMAs whose descriptors are the stage bases plus COMPILE-TIME offsets (tap (kh, kw) of
+      // the halo patch = + (kh * PITCH + kw) rows of 128 B; K = 16 slice k = + 32 B; tap kw of the B stage = + 8 KB).
       constexpr uint32_t idesc = make_idesc_m256(WINO_BN, TcFmt<T>::fmt);
+      const uint64_t adesc0 = wino_a_desc(sA, PITCH * 128);
+      const uint64_t bdesc0 = make_kmajor_sw128_desc(sB);
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       uint32_t use[4] = {0, 0, 0, 0};  // how often each accumulator has been handed to the epilogue
       for (uint32_t it = item0; it < nitems; it += istride) {
@@ -256,26 +275,25 @@ conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(accempty + 8 * gi, (use[gi] & 1) ^ 1);  // the epilogue has drained this accumulator's previous contents
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(gi * WINO_BN);
-          const int nsc = sc_steps(m, gi), nst = kchunks + nsc;
-          for (int kc = 0; kc < nst; ++kc) {
-            mbar_wait(afull + 8 * sa, pa);
-            const uint32_t a_stage = sA + sa * Cfg::A_BYTES;
-            const bool sc = kc >= kchunks;
-            const int ntap = sc ? 1 : 9;
-            const int rem = sc ? a.sc_cin - (kc - kchunks) * 64 : 64;   // K = 16 slices that hold real channels
-            const int nk = rem >= 64 ? 4 : (rem + 15) / 16;
+          const int nsc = sc_steps(m, gi);
 #pragma unroll 1
-            for (int tap = 0; tap < ntap; ++tap) {
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(afull + 8 * sa, pa);
+            const uint64_t ad = adesc0 + (uint64_t)((uint32_t)sa * (uint32_t)(Cfg::A_BYTES >> 4));
+            const uint32_t first = kc != 0 ? 1u : 0u;   // the very first MMA of a GEMM overwrites the accumulator
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
               mbar_wait(bfull + 8 * sb, pb);
               tc_fence_after();
               if (elect_one()) {
-                const int tap9 = sc ? 4 : tap;   // shortcut: centre tap (kh, kw) = (1, 1)
-                const int kh = tap9 / 3, kw = tap9 - 3 * kh;
-                const uint64_t adesc = wino_a_desc(a_stage + (uint32_t)((kh * PITCH + kw) * 128), PITCH * 128);
-                const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * Cfg::B_BYTES);
+                const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)sb * (uint32_t)(Cfg::B_BYTES >> 4));
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (k < nk) umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | tap | k) != 0);
+                for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16_2sm(d_tmem, ad + (uint64_t)((kh * PITCH + kw) * 8 + 2 * k), bd + (uint64_t)(kw * (Cfg::B_TAP_BYTES >> 4) + 2 * k),
+                                 idesc, (kh | kw | k) != 0 ? 1u : first);
+                }
                 umma_commit_2sm(bempty + 8 * sb);
               }
               __syncwarp();
@@ -283,6 +301,26 @@ conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if (elect_one()) umma_commit_2sm(aempty + 8 * sa);
             __syncwarp();
+            if (++sa == NA) { sa = 0; pa ^= 1; }
+          }
+#pragma unroll 1
+          for (int c = 0; c < nsc; ++c) {   // fused 1x1x1 shortcut: centre tap (kh, kw) = (1, 1) of the block input's halo patch
+            mbar_wait(afull + 8 * sa, pa);
+            mbar_wait(bfull + 8 * sb, pb);
+            tc_fence_after();
+            const int rem = a.sc_cin - c * 64;              // K = 16 slices that hold real channels
+            const int nk = rem >= 64 ? 4 : (rem + 15) / 16;
+            if (elect_one()) {
+              const uint64_t ad = adesc0 + (uint64_t)((uint32_t)sa * (uint32_t)(Cfg::A_BYTES >> 4) + (uint32_t)((PITCH + 1) * 8));
+              const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)sb * (uint32_t)(Cfg::B_BYTES >> 4));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < nk) umma_f16_2sm(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
+              umma_commit_2sm(bempty + 8 * sb);
+              umma_commit_2sm(aempty + 8 * sa);
+            }
+            __syncwarp();
+            if (++sb == NB) { sb = 0; pb ^= 1; }
             if (++sa == NA) { sa = 0; pa ^= 1; }
           }
           if (elect_one()) umma_commit_2sm(accfull + 8 * gi);
@@ -399,25 +437,30 @@ conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 2) { tc_fence_after(); tmem_dealloc_2sm<512>(tmem_base); }
 }
 
-template <typename T>
+template <typename T, typename Cfg>
 static int launch_wino_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
                          const CUtensorMap& tmX, const CUtensorMap& tmW, const WinoArgs& a, cudaStream_t stream) {
   static DeviceOnce attr_once;
   if (attr_once.first()) {
-    if (cudaFuncSetAttribute(conv_wino_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, WinoCfg::SMEM_BYTES) != cudaSuccess)
-      return fail(HYVAE_ECUDA, "conv_wino: cannot opt in to %d bytes of shared memory", WinoCfg::SMEM_BYTES);
+    if (cudaFuncSetAttribute(conv_wino_kernel<T, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+      return fail(HYVAE_ECUDA, "conv_wino: cannot opt in to %d bytes of shared memory", Cfg::SMEM_BYTES);
     attr_once.done();
   }
   const int64_t max_pairs = num_sms() / 2;
   const int64_t pairs = a.total < max_pairs ? a.total : max_pairs;
-  conv_wino_kernel<T><<<(unsigned)(2 * pairs), WINO_THREADS, WinoCfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, tmX, tmW, a);
+  conv_wino_kernel<T, Cfg><<<(unsigned)(2 * pairs), WINO_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, tmX, tmW, a);
   return check_launch("conv3d_causal_wino");
 }
 
 int launch_wino(int dtype, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
                 const CUtensorMap& tmX, const CUtensorMap& tmW, const WinoArgs& a, cudaStream_t stream) {
-  if (dtype == HYVAE_BF16) return launch_wino_t<__nv_bfloat16>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream);
-  return launch_wino_t<__half>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream);
+  static const bool cfg_b = [] { const char* e = getenv("HYVAE_WINO_CFG"); return e != nullptr && e[0] == '1'; }();
+  if (cfg_b) {
+    if (dtype == HYVAE_BF16) return launch_wino_t<__nv_bfloat16, WinoCfgB>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream);
+    return launch_wino_t<__half, WinoCfgB>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream);
+  }
+  if (dtype == HYVAE_BF16) return launch_wino_t<__nv_bfloat16, WinoCfg>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream);
+  return launch_wino_t<__half, WinoCfg>(tmA, tmB, tmY, tmR, tmX, tmW, a, stream);
 }
 
 }  // namespace hyvae
@@ -497,7 +540,7 @@ extern "C" int hyvae_conv3d_causal_wino(const hyvae_vol* planes, int32_t T, cons
   {
     cuuint64_t dims[3] = {(cuuint64_t)planes->C, (cuuint64_t)y->C, 45};
     cuuint64_t strides[2] = {(cuuint64_t)planes->C * 2, (cuuint64_t)planes->C * y->C * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)(WINO_BN / 2), 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)(WINO_BN / 2), (cuuint32_t)WinoCfg::TB};   // the three kw taps of one kh row
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&tmB, dt, 3, const_cast<void*>(uw), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
