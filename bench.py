@@ -373,7 +373,8 @@ def run_ours(args):
                        "weights": "random-init, HY VAE config [128,256,512,512], 16 latent channels",
                        "l2": "inputs and activations far larger than the 126 MB L2 (713 MB clip); no flush needed",
                        "tile_streams": vae.tile_streams,
-                       "partition": ("clips over ranks" if args.workload == "config3" else "tiles over ranks") if world > 1 else "single GPU"},
+                       "partition": ("clips over ranks" if args.workload == "config3" else "tiles over ranks") if world > 1 else "single GPU",
+                       "tile_exchange": (getattr(runner, "last_exchange", None) if runner is not None else None)},
             "clocks": clocks,
             "gpu_launches": int(launches),
             "e2e": None if args.no_e2e else {"value": frames_per_step / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
@@ -423,6 +424,8 @@ def run_ours(args):
             line["torch_gpu_baseline"] = tb
         print(json.dumps(line), flush=True)
     if world > 1:
+        if runner is not None:
+            runner.close()
         dist.destroy_process_group()
 
 

@@ -611,6 +611,62 @@ __global__ void blend_crop_scatter_kernel(T* __restrict__ cur, const T* __restri
   }
 }
 
+// 16-byte form of the kernel above for 16-bit tiles whose rows, windows and strides are multiples of 8 elements (every tile
+// of the 720p / 544x960 splits): one thread owns 8 consecutive x of one row.  The blend weights are those of blend2 —
+// (float)(1 - y / e) and (float)(y / e) evaluated in double like the reference's Python scalars — tabulated once per block
+// in shared memory instead of two fp64 divisions per element; products and sums round exactly as in blend2.  The scalar
+// kernel took ~60 us per 65 x 256 x 256 tile (2-byte accesses, 64-bit div / mod per element): 10 ms per 720p step, all of it
+// on rank 0 after the gather of a multi-GPU decode.
+constexpr int kBlendMaxExtent = 256;
+template <typename T, bool POST>
+__global__ void __launch_bounds__(256) blend_crop_scatter_vec8_kernel(
+    T* __restrict__ cur, const T* __restrict__ above, const T* __restrict__ left, int64_t N, int Yc, int Xc, int Ya, int Xl, int ev, int eh,
+    typename std::conditional<POST, float, T>::type* __restrict__ out, int Yo, int Xo, int y0, int x0, int crop_y, int crop_x,
+    int64_t cur_ns, int64_t above_ns, int64_t left_ns, int64_t out_ns) {
+  __shared__ float wv[2][kBlendMaxExtent], wh[2][kBlendMaxExtent];
+  for (int i = threadIdx.x; i < ev; i += blockDim.x) { wv[0][i] = (float)(1.0 - (double)i / (double)ev); wv[1][i] = (float)((double)i / (double)ev); }
+  for (int i = threadIdx.x; i < eh; i += blockDim.x) { wh[0][i] = (float)(1.0 - (double)i / (double)eh); wh[1][i] = (float)((double)i / (double)eh); }
+  __syncthreads();
+  const int Xv = Xc >> 3;
+  const int64_t total = N * Yc * Xv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Xv) * 8; const int64_t r = i / Xv;
+    const int y = (int)(r % Yc); const int64_t n = r / Yc;
+    const int64_t ci = n * cur_ns + (int64_t)y * Xc + x;
+    Vec8<T> q; q.load(cur + ci);
+    float v[8]; q.get(v);
+    bool mod = false;
+    if (above != nullptr && y < ev) {
+      Vec8<T> a; a.load(above + n * above_ns + (int64_t)(Ya - ev + y) * Xc + x);
+      float af[8]; a.get(af);
+      const float wa = wv[0][y], wb = wv[1][y];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = rnd<T>(__fadd_rn(rnd<T>(__fmul_rn(af[j], wa)), rnd<T>(__fmul_rn(v[j], wb))));
+      mod = true;
+    }
+    if (left != nullptr && x < eh) {   // eh % 8 == 0: the whole vector lies inside the strip
+      Vec8<T> l; l.load(left + n * left_ns + (int64_t)y * Xl + (Xl - eh + x));
+      float lf[8]; l.get(lf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = rnd<T>(__fadd_rn(rnd<T>(__fmul_rn(lf[j], wh[0][x + j])), rnd<T>(__fmul_rn(v[j], wh[1][x + j]))));
+      mod = true;
+    }
+    if (mod) { q.set(v); q.store(cur + ci); }
+    if (out != nullptr && y < crop_y && x < crop_x) {   // crop_x % 8 == 0
+      const int64_t oi = n * out_ns + (int64_t)(y0 + y) * Xo + (x0 + x);
+      if constexpr (POST) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = post_image<T>(v[j]);
+        Vec8<float> ov; ov.set(o); ov.store(out + oi);
+      } else {
+        if (!mod) q.set(v);
+        q.store(out + oi);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // pipeline tail: image = (image / 2 + 0.5).clamp(0, 1) in the image dtype, then .float()
 // (pipeline_hunyuan_video.py:1090-1092) as ONE pass: 16-bit in, fp32 out.
@@ -933,6 +989,25 @@ int hyvae_blend_crop_scatter(void* cur, const void* above, const void* left, int
   int64_t total = N * Yc * Xc;
   ProfScope prof(PC_BLEND, (double)total * dtype_size(dtype) + (out ? (double)N * crop_y * crop_x * dtype_size(dtype) : 0.0), stream);
   HYVAE_CHECK_ARG(!post || out != nullptr, "post-processed output requested without an output buffer");
+  // 16-byte path: 16-bit tiles with every row length, window and plane stride a multiple of 8 elements and aligned bases
+  auto mult8 = [](int64_t v) { return (v & 7) == 0; };
+  const bool vec8 = dtype != HYVAE_F32 && mult8(Xc) && mult8(cur_ns) && ((uintptr_t)cur & 15) == 0 &&
+                    (above == nullptr || (mult8(above_ns) && ((uintptr_t)above & 15) == 0 && ev <= kBlendMaxExtent)) &&
+                    (left == nullptr || (mult8(Xl) && mult8(eh) && mult8(left_ns) && ((uintptr_t)left & 15) == 0 && eh <= kBlendMaxExtent)) &&
+                    (out == nullptr || (mult8(Xo) && mult8(x0) && mult8(crop_x) && mult8(out_ns) && ((uintptr_t)out & (post ? 31 : 15)) == 0));
+  if (vec8) {
+    const int g = grid_for(total / 8, 256);
+    if (post) {
+      HYVAE_DISPATCH_DTYPE(dtype, T, (blend_crop_scatter_vec8_kernel<T, true><<<g, 256, 0, (cudaStream_t)stream>>>(
+          (T*)cur, (const T*)above, (const T*)left, N, Yc, Xc, Ya, Xl, above ? ev : 0, left ? eh : 0, (float*)out, Yo, Xo, y0, x0, crop_y, crop_x,
+          cur_ns, above_ns, left_ns, out_ns)));
+    } else {
+      HYVAE_DISPATCH_DTYPE(dtype, T, (blend_crop_scatter_vec8_kernel<T, false><<<g, 256, 0, (cudaStream_t)stream>>>(
+          (T*)cur, (const T*)above, (const T*)left, N, Yc, Xc, Ya, Xl, above ? ev : 0, left ? eh : 0, (T*)out, Yo, Xo, y0, x0, crop_y, crop_x,
+          cur_ns, above_ns, left_ns, out_ns)));
+    }
+    return check_launch("blend_crop_scatter");
+  }
   if (post) {
     HYVAE_DISPATCH_DTYPE(dtype, T, (blend_crop_scatter_kernel<T, true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (T*)cur, (const T*)above, (const T*)left, N, Yc, Xc, Ya, Xl, ev, eh, (float*)out, Yo, Xo, y0, x0, crop_y, crop_x,

@@ -5,7 +5,10 @@ a torchrun job (pipeline_hunyuan_video.py:1074-1082); here each rank computes a 
 reference's tile grid and the results are exchanged with ONE collective per direction:
 
   encode: all_gather of the tile moments (1.1 MB each) -> every rank blends the full latent (needed by all)
-  decode: gather of the decoded tiles to rank 0 (<= 1.5 GB over NVLink) -> rank 0 runs the raster-order blend
+  decode: every rank PUSHES each decoded tile into rank 0's tile arena over NVLink as soon as the tile is finished
+          (peer-to-peer copy engine writes into rank 0's memory, mapped through CUDA IPC; no SMs, overlapped with the
+          remaining tiles' compute), then ONE tiny all_reduce orders the pushes before rank 0's raster-order blend.
+          Where peer memory cannot be mapped (CPU / gloo tests, HYVAE_TILE_PUSH=0) the tiles travel in one NCCL gather.
 
 The blend chain is order dependent, so assembly always happens on complete tile grids, in the reference's order.
 The tile functions / assemblers are injectable so the partition + exchange logic is testable on CPU (gloo).
@@ -14,6 +17,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 from typing import Callable, List, Optional, Sequence, Tuple
+
+import os
 
 import torch
 import torch.distributed as dist
@@ -106,6 +111,56 @@ class TileParallelVAE:
                 off += numel[k]
         return tiles
 
+    # ---- peer-memory push (decode direction) --------------------------------------------------
+    def _push_arena(self, shapes: List[Tuple[int, ...]], owner: List[int], dtype, device):
+        """Rank 0's tile arena for this tile set, mapped into every rank: [(views of arena 0), (views of arena 1)] with one
+        view per tile that rank 0 does not own (None for its own), or None when peer memory is not available.
+
+        Two arenas alternate between calls: a rank may start pushing the tiles of call i+1 while rank 0 still blends call i,
+        and it cannot reach call i+2 before rank 0 has passed the ordering all_reduce of call i+1, which rank 0 enqueues
+        after the blends of call i.  The arenas are allocated once per (tile set, dtype) and shared through CUDA IPC
+        (torch.multiprocessing's reduce_tensor: cudaIpcGetMemHandle / cudaIpcOpenMemHandle), so a push is a plain
+        device-to-device copy into peer memory: copy engines over NVLink, no SM and no NCCL kernel."""
+        if os.environ.get("HYVAE_TILE_PUSH", "1") != "1" or device.type != "cuda" or self.world < 2:
+            return None
+        key = (tuple(shapes), tuple(owner), dtype)
+        cache = self.__dict__.setdefault("_arenas", {})
+        if key in cache:
+            return cache[key]
+        numel = [int(torch.Size(s).numel()) for s in shapes]
+        offs, total = [], 0
+        for k, n in enumerate(numel):
+            offs.append(total)
+            if owner[k] != 0:
+                total += (n + 127) // 128 * 128      # keep every tile 256-byte aligned (16-byte vectors in the blend kernel)
+        views, ok = None, 1
+        try:
+            from torch.multiprocessing.reductions import reduce_tensor
+            payload = [None]
+            if self.rank == 0:
+                self._arena_owner = getattr(self, "_arena_owner", [])
+                arenas = [torch.empty(max(total, 1), dtype=dtype, device=device) for _ in range(2)]
+                self._arena_owner.append(arenas)           # rank 0 keeps the allocations alive
+                payload = [[reduce_tensor(a) for a in arenas]]
+            dist.broadcast_object_list(payload, src=0, group=self.group)
+            if self.rank != 0:
+                arenas = [fn(*args) for fn, args in payload[0]]
+            views = [[None if owner[k] == 0 else a[offs[k]:offs[k] + numel[k]].view(shapes[k]) for k in range(len(shapes))] for a in arenas]
+            if self.rank != 0:   # one small write proves the mapping before the hot loop relies on it
+                probe = torch.zeros(1, dtype=dtype, device=device)
+                arenas[0][:1].copy_(probe)
+                torch.cuda.synchronize(device)
+        except Exception as e:  # noqa: BLE001 - any failure (no peer access, IPC refused in this container) selects the gather
+            if os.environ.get("HYVAE_TILE_PUSH_DEBUG"):
+                print(f"[tile_parallel] rank {self.rank}: peer-memory push unavailable: {type(e).__name__}: {e}", flush=True)
+            ok, views = 0, None
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)   # every rank takes the same path
+        if int(flag.item()) == 0:
+            views = None
+        cache[key] = views
+        return views
+
     # ---- one direction ----------------------------------------------------------------------
     def _run(self, x: torch.Tensor, encode: bool, to_all: bool, post: bool = False):
         v = self.vae
@@ -126,16 +181,48 @@ class TileParallelVAE:
         specs = tile_grid(T, H, W, temporal=v.use_temporal_tiling, spatial=v.use_spatial_tiling, min_t=min_t, min_s=min_s, overlap=ov)
         owner = lpt_assign([s.cost for s in specs], self.world)
         mine_k = [k for k in range(len(specs)) if owner[k] == self.rank]
+        shapes = [oshape(s) for s in specs]
         cut = lambda s: fn(x[:, :, s.t0:s.t1, s.h0:s.h1, s.w0:s.w1]).contiguous()
-        outs = run_tiles([(lambda s=specs[k]: cut(s)) for k in mine_k], getattr(v, "tile_streams", 1) if x.is_cuda else 1)
+        out_dtype = getattr(v, "dtype", x.dtype)
+        arena = None if to_all else self._push_arena(shapes, owner, out_dtype, x.device)
+        if arena is not None:
+            self._push_calls = getattr(self, "_push_calls", 0) + 1
+            slots = arena[self._push_calls & 1]
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=x.device)
+            copy_stream = self._copy_stream
+            copy_stream.wait_stream(torch.cuda.current_stream(x.device))
+        if not to_all:
+            self.last_exchange = "push" if arena is not None else "gather"
+
+        def push(k, t):
+            """Peer write of a finished tile into rank 0's arena, on the copy stream, behind the tile's own stream."""
+            if arena is not None and self.rank != 0:
+                copy_stream.wait_stream(torch.cuda.current_stream(x.device))
+                with torch.cuda.stream(copy_stream):
+                    slots[k].copy_(t, non_blocking=True)
+                t.record_stream(copy_stream)
+            return t
+
+        outs = run_tiles([(lambda k=k: push(k, cut(specs[k]))) for k in mine_k], getattr(v, "tile_streams", 1) if x.is_cuda else 1)
         if hasattr(v, "_guard_tiles"):   # fp16-operand range guard of a bf16 model (model.py): re-run overflowing tiles in bf16
-            outs = v._guard_tiles(outs, lambda i: cut(specs[mine_k[i]]))
+            outs = v._guard_tiles(outs, lambda i: push(mine_k[i], cut(specs[mine_k[i]])))
         mine = {}
         for k, t in zip(mine_k, outs):
-            assert tuple(t.shape) == oshape(specs[k]), (tuple(t.shape), oshape(specs[k]))
+            assert tuple(t.shape) == shapes[k], (tuple(t.shape), shapes[k])
             mine[k] = t
-        dtype = next(iter(mine.values())).dtype if mine else getattr(v, "dtype", x.dtype)
-        tiles = self._exchange(mine, [oshape(s) for s in specs], owner, dtype, x.device, to_all)
+        if arena is not None:
+            # ONE ordering collective: stream-ordered behind this rank's pushes; when it completes on rank 0 every peer
+            # write has landed in the arena
+            torch.cuda.current_stream(x.device).wait_stream(copy_stream)
+            done = torch.zeros(1, dtype=torch.int32, device=x.device)
+            dist.all_reduce(done, group=self.group)
+            if self.rank != 0:
+                return None
+            tiles = [mine[k] if owner[k] == 0 else slots[k] for k in range(len(specs))]
+        else:
+            dtype = next(iter(mine.values())).dtype if mine else out_dtype
+            tiles = self._exchange(mine, shapes, owner, dtype, x.device, to_all)
         if tiles is None:
             return None
         # assemble: spatial grids per temporal tile, then the temporal chain
@@ -161,6 +248,16 @@ class TileParallelVAE:
                 return N.image_postprocess(row[0][0])
             return row[0][0]
         return self.assemble_temporal(row, ext_t, lim_t, True) if post else self.assemble_temporal(row, ext_t, lim_t)
+
+    def close(self):
+        """Drop the peer mappings of rank 0's arenas (call on every rank before the process group is destroyed, so that the
+        consumers release the CUDA IPC handles before the producer frees the memory)."""
+        if getattr(self, "_arenas", None):
+            self._arenas.clear()
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            self._arena_owner = []
 
     def encode_moments(self, x: torch.Tensor) -> torch.Tensor:
         """Blended moments of the whole clip, on every rank."""

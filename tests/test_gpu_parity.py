@@ -237,6 +237,53 @@ def test_blend_bit_exact(dtype):
         assert torch.equal(out.cpu(), ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_blend_vec8_path_and_assembly_chain_bit_exact(dtype):
+    """The 16-byte blend kernel (rows / windows / extents that are multiples of 8, as in every production split) and the
+    raster-order assembly built on it, against the oracle's blend loops in the reference's order of operations
+    (autoencoder_kl_causal_3d.py:403-412 spatial, :529-541 temporal)."""
+    from hunyuanvideo_efficiency_b200.vae import AutoencoderKLCausal3D
+    m = AutoencoderKLCausal3D.from_config(W.SMALL_CONFIG)
+    g = torch.Generator().manual_seed(11)
+    a = torch.randn(1, 3, 6, 24, 32, generator=g).to(dtype)
+    for fn, ofn, b_shape, e in ((m.blend_v, O.blend_v, (1, 3, 6, 16, 32), 8), (m.blend_h, O.blend_h, (1, 3, 6, 24, 24), 16),
+                                (m.blend_t, O.blend_t, (1, 3, 9, 24, 32), 4)):
+        b = torch.randn(b_shape, generator=g).to(dtype)
+        ref = ofn(a.clone(), b.clone(), e)
+        out = fn(a.to(_dev()), b.to(_dev()).clone(), e)
+        assert torch.equal(out.cpu(), ref)
+    # 3 x 3 grid of tiles (ragged last row / column), extent 8, limit 24
+    hs, ws = [32, 32, 16], [32, 32, 24]
+    tiles = [[torch.randn(1, 3, 5, h, w, generator=g).to(dtype) for w in ws] for h in hs]
+    ref_rows = []
+    work = [[t.clone() for t in row] for row in tiles]
+    for i, row in enumerate(work):
+        res = []
+        for j, t in enumerate(row):
+            if i > 0:
+                t = O.blend_v(work[i - 1][j], t, 8)
+            if j > 0:
+                t = O.blend_h(row[j - 1], t, 8)
+            res.append(t[:, :, :, :24, :24])
+        ref_rows.append(torch.cat(res, dim=-1))
+    ref = torch.cat(ref_rows, dim=-2)
+    out = m._assemble_spatial([[t.to(_dev()) for t in row] for row in tiles], 8, 24)
+    assert torch.equal(out.cpu(), ref)
+    # temporal chain: three tiles, the later ones drop their first frame, extent 4, limit 12
+    tt = [torch.randn(1, 3, n, 16, 24, generator=g).to(dtype) for n in (17, 17, 9)]
+    row = [tt[0].clone()] + [t[:, :, 1:].clone() for t in tt[1:]]
+    res = []
+    for i, t in enumerate(row):
+        if i > 0:
+            t = O.blend_t(row[i - 1], t, 4)
+            res.append(t[:, :, :12])
+        else:
+            res.append(t[:, :, :13])
+    ref = torch.cat(res, dim=2)
+    out = m._assemble_temporal([(tt[0].to(_dev()), 0)] + [(t.to(_dev()), 1) for t in tt[1:]], 4, 12)
+    assert torch.equal(out.cpu(), ref)
+
+
 # ----------------------------------------------------------------------------------------- tcgen05 conv
 def _rand_case(B, Cin, Cout, T, H, W, seed):
     g = torch.Generator().manual_seed(seed)

@@ -16,12 +16,21 @@ vae = vae.to(torch.bfloat16).to(dev).eval().requires_grad_(False)
 vae.enable_tiling()
 x = W.make_video((1, 3, 29, 72, 88)).to(dev, torch.bfloat16)
 with torch.no_grad():
-    out = TP.TileParallelVAE(vae, rank, world).roundtrip(x)
+    runner = TP.TileParallelVAE(vae, rank, world)
+    ref = vae.decode(vae.encode(x).latent_dist.mode()).sample if rank == 0 else None
+    for it in range(3):      # the peer-memory arenas alternate between calls
+        out = runner.roundtrip(x)
+        if rank == 0:
+            print(f"call {it}: exchange={runner.last_exchange} tile-parallel == single GPU:", torch.equal(out, ref), tuple(out.shape), flush=True)
+            assert torch.equal(out, ref)
+        else:
+            assert out is None
+    os.environ["HYVAE_TILE_PUSH"] = "0"     # the NCCL gather path must give the same bits
+    g = TP.TileParallelVAE(vae, rank, world)
+    out = g.roundtrip(x)
     if rank == 0:
-        ref = vae.decode(vae.encode(x).latent_dist.mode()).sample
-        print("tile-parallel == single GPU:", torch.equal(out, ref), tuple(out.shape), flush=True)
+        print(f"exchange={g.last_exchange} tile-parallel == single GPU:", torch.equal(out, ref), flush=True)
         assert torch.equal(out, ref)
-    else:
-        assert out is None
+    runner.close()
 dist.barrier()
 dist.destroy_process_group()
