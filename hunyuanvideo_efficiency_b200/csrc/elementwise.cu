@@ -299,11 +299,38 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(Vol x, Vol y, const do
 //   rounded once.  A thread owns one (padded row, padded column, 8-channel vector) and walks T, so every input voxel is
 //   read once (the two previous frames stay in registers) and 2 planes are written per input frame; the 1-voxel replicate
 //   halo of the planes comes from clamping the source coordinates (replicate padding commutes with the transform).
+// 4-element (8-byte) vectors of a 16-bit type <-> fp32
+template <typename T> struct Vec4h;
+template <> struct Vec4h<__half> {
+  static __device__ __forceinline__ void get(const uint2& v, float* f) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  }
+  static __device__ __forceinline__ uint2 set(const float* f) {
+    uint2 v; const __half2 a = __floats2half2_rn(f[0], f[1]), b = __floats2half2_rn(f[2], f[3]);
+    v.x = *reinterpret_cast<const uint32_t*>(&a); v.y = *reinterpret_cast<const uint32_t*>(&b); return v;
+  }
+};
+template <> struct Vec4h<__nv_bfloat16> {
+  static __device__ __forceinline__ void get(const uint2& v, float* f) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  }
+  static __device__ __forceinline__ uint2 set(const float* f) {
+    uint2 v; const __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+    v.x = *reinterpret_cast<const uint32_t*>(&a); v.y = *reinterpret_cast<const uint32_t*>(&b); return v;
+  }
+};
+
+// A thread owns FOUR channels of one padded (row, column) and walks T.  The first version (eight channels per thread, one
+// frame pair in flight, 95 registers, 2 blocks per SM) was latency bound: 3.7 warps per scheduler, 75 % of the stall
+// samples waiting on the loads, 4.8 TB/s (profiles/r02_ncu_gn_apply_wino_128_v1.txt).  Now: half the per-thread state
+// (4 blocks per SM) and the loads of the NEXT TWO pairs in flight while two pairs are transformed.
 template <typename T, bool SILU>
-__global__ void __launch_bounds__(256) gn_apply_wino_kernel(Vol x, Vol y, int Tn, const double* __restrict__ sums, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, int groups, float eps, double inv_n) {
+__global__ void __launch_bounds__(256, 4) gn_apply_wino_kernel(Vol x, Vol y, int Tn, const double* __restrict__ sums, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, int groups, float eps, double inv_n) {
   extern __shared__ float sh[];  // scale[C], shift[C]
-  const int C = x.C, CV = C / 8, b = blockIdx.y;
+  const int C = x.C, CQ = C / 4, b = blockIdx.y;
   const int cpg = C / groups;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
@@ -318,64 +345,79 @@ __global__ void __launch_bounds__(256) gn_apply_wino_kernel(Vol x, Vol y, int Tn
   __syncthreads();
   const int Wp = y.Wp(), Hp = y.Hp();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)Hp * Wp * CV) return;
-  const int cv = (int)(idx % CV);
-  const int wp = (int)((idx / CV) % Wp), hp = (int)(idx / ((int64_t)CV * Wp));
+  if (idx >= (int64_t)Hp * Wp * CQ) return;
+  const int cq = (int)(idx % CQ);
+  const int wp = (int)((idx / CQ) % Wp), hp = (int)(idx / ((int64_t)CQ * Wp));
   const int h = min(max(hp - 1, 0), x.H - 1), w = min(max(wp - 1, 0), x.W - 1);
-  float rsc[8], rsf[8];
+  float rsc[4], rsf[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { rsc[j] = sh[cv * 8 + j]; rsf[j] = sh[C + cv * 8 + j]; }
-  const T* src = reinterpret_cast<const T*>(x.p) + x.at(b, 0, h, w) + cv * 8;
-  T* dst = reinterpret_cast<T*>(y.p) + (int64_t)b * y.sB + (int64_t)hp * y.sH + (int64_t)wp * y.sW + cv * 8;
-  auto act = [&](const Vec8<T>& q, float* f) {
-    q.get(f);
+  for (int j = 0; j < 4; ++j) { rsc[j] = sh[cq * 4 + j]; rsf[j] = sh[C + cq * 4 + j]; }
+  const T* src = reinterpret_cast<const T*>(x.p) + x.at(b, 0, h, w) + cq * 4;
+  T* dst = reinterpret_cast<T*>(y.p) + (int64_t)b * y.sB + (int64_t)hp * y.sH + (int64_t)wp * y.sW + cq * 4;
+  const int64_t xsT = x.sT, ysT = y.sT;
+  auto ld = [&](int t) -> uint2 { return __ldg(reinterpret_cast<const uint2*>(src + (int64_t)t * xsT)); };
+  auto act = [&](const uint2& q, float* f) {
+    Vec4h<T>::get(q, f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = gn_act<T, SILU, false>(fmaf(f[j], rsc[j], rsf[j]));
+    for (int j = 0; j < 4; ++j) f[j] = gn_act<T, SILU, false>(fmaf(f[j], rsc[j], rsf[j]));
   };
-  auto put = [&](int plane, const float* f) { Vec8<T> o; o.set(f); o.store(dst + (int64_t)plane * y.sT); };
-  float da[8], db[8];  // f(x[max(2p-1, 0)]), f(x[2p])
+  auto put = [&](int plane, const float* f) { *reinterpret_cast<uint2*>(dst + (int64_t)plane * ysT) = Vec4h<T>::set(f); };
+  float da[4], db[4];  // f(x[max(2p-1, 0)]), f(x[2p])
   {
-    Vec8<T> q; q.load(src);
+    const uint2 q = ld(0);
     act(q, db);
     put(0, db);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) da[j] = db[j];
+    for (int j = 0; j < 4; ++j) da[j] = db[j];
   }
   const int P = (Tn - 1) / 2;
-  Vec8<T> n2, n3;  // software pipeline: the next pair's two frames are in flight while this pair is transformed
-  if (P > 0) { n2.load(src + (int64_t)1 * x.sT); n3.load(src + (int64_t)2 * x.sT); }
-  for (int p = 0; p < P; ++p) {
-    const Vec8<T> q2 = n2, q3 = n3;
-    if (p + 1 < P) { n2.load(src + (int64_t)(2 * p + 3) * x.sT); n3.load(src + (int64_t)(2 * p + 4) * x.sT); }
-    float d2[8], d3[8], v[8];
+  // pair p reads frames 2p + 1 and 2p + 2; a batch is two pairs = frames 2p + 1 .. 2p + 4
+  auto load_batch = [&](int p0, uint2 (&q)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = 2 * p0 + 1 + i;
+      q[i] = t <= 2 * P ? ld(t) : make_uint2(0u, 0u);
+    }
+  };
+  auto pair = [&](int p, const uint2& q2, const uint2& q3) {
+    float d2[4], d3[4], v[4];
     act(q2, d2); act(q3, d3);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = da[j] - d2[j];
+    for (int j = 0; j < 4; ++j) v[j] = da[j] - d2[j];
     put(1 + 4 * p, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = db[j] + d2[j];
+    for (int j = 0; j < 4; ++j) v[j] = db[j] + d2[j];
     put(2 + 4 * p, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = d2[j] - db[j];
+    for (int j = 0; j < 4; ++j) v[j] = d2[j] - db[j];
     put(3 + 4 * p, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = db[j] - d3[j];
+    for (int j = 0; j < 4; ++j) v[j] = db[j] - d3[j];
     put(4 + 4 * p, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { da[j] = d2[j]; db[j] = d3[j]; }
+    for (int j = 0; j < 4; ++j) { da[j] = d2[j]; db[j] = d3[j]; }
+  };
+  uint2 cur[4], nxt[4];
+  if (P > 0) load_batch(0, cur);
+  for (int p = 0; p < P; p += 2) {
+    if (p + 2 < P) load_batch(p + 2, nxt);
+    pair(p, cur[0], cur[1]);
+    if (p + 1 < P) pair(p + 1, cur[2], cur[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
   }
   if ((Tn & 1) == 0) {  // even T: the last frame alone (three planes)
-    Vec8<T> q; q.load(src + (int64_t)(Tn - 1) * x.sT);
-    float d2[8], v[8];
+    const uint2 q = ld(Tn - 1);
+    float d2[4], v[4];
     act(q, d2);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = da[j] - d2[j];
+    for (int j = 0; j < 4; ++j) v[j] = da[j] - d2[j];
     put(1 + 4 * P, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = db[j] + d2[j];
+    for (int j = 0; j < 4; ++j) v[j] = db[j] + d2[j];
     put(2 + 4 * P, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = d2[j] - db[j];
+    for (int j = 0; j < 4; ++j) v[j] = d2[j] - db[j];
     put(3 + 4 * P, v);
   }
 }
@@ -863,7 +905,7 @@ int hyvae_groupnorm_apply_wino(const hyvae_vol* x, const double* sums, const flo
   snprintf(tag, sizeof(tag), "gn C%d %dx%dx%dx%d wino", x->C, x->B, x->T, x->H, x->W);
   // algorithmic bytes as for hyvae_groupnorm_apply (1 read + 1 write of the tensor); the kernel WRITES ~2x that
   ProfScope prof(PC_GN_APPLY, 2.0 * x->B * x->T * x->H * x->W * x->C * dtype_size(x->dtype), stream, tag);
-  const int64_t nthreads = (int64_t)vy.Hp() * vy.Wp() * (x->C / 8);
+  const int64_t nthreads = (int64_t)vy.Hp() * vy.Wp() * (x->C / 4);
   dim3 grid((unsigned)((nthreads + 255) / 256), (unsigned)x->B);
   const size_t smem = sizeof(float) * 2 * x->C;
   const double inv_n = 1.0 / ((double)x->T * x->H * x->W * (x->C / groups));

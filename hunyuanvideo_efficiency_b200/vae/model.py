@@ -24,7 +24,7 @@ from torch import nn
 
 from .. import _native as N
 from .._native import Vol
-from .blocks import CausalConv3d, UNetMidBlockCausal3D, _GroupNorm, get_down_block3d, get_up_block3d
+from .blocks import CausalConv3d, UNetMidBlockCausal3D, _GroupNorm, _publish, get_down_block3d, get_up_block3d
 
 
 # --------------------------------------------------------------------------------------- outputs
@@ -239,6 +239,7 @@ class _ConvParamsOnly(nn.Module):
             if x.C > ci:   # producer padded its channel count (e.g. Cout of a tensor-core conv_out to a multiple of 8): zero columns
                 w32 = torch.cat([w32, torch.zeros(co, x.C - ci, device=w32.device)], 1)
             self._packed = (key, w32.reshape(1, co, x.C).to(x.dtype).contiguous(), b32.contiguous())
+            _publish(self._packed[1])   # read from every tile stream afterwards (run_tiles)
         y = N.conv3d_direct(x, self._packed[1], self._packed[2], 1, (1, 1, 1), co, round_like_ref=False)
         return y
 
@@ -256,18 +257,20 @@ def run_tiles(thunks, n_streams: int = 1):
     current one leaves idle (the 17 x 32 x 32 mid-block layers fill only 136 of 148 SMs' worth of tiles), and let the
     HBM-bound GroupNorm / pad passes of one tile run under the tensor-bound convs of another.  Results do not depend
     on the interleaving: each kernel's tile schedule is static and the GroupNorm partial buffers are per stream.
-    The first thunk runs alone on the caller's stream: it creates the lazily packed weights the others read."""
+    Lazily derived parameter tensors (packed weights, fp32 norm parameters) are created by whichever thunk needs them
+    first and published with a stream synchronisation before any later thunk is enqueued (blocks._publish), so all lanes
+    start at once."""
     thunks = list(thunks)
     if n_streams <= 1 or len(thunks) <= 2 or not torch.cuda.is_available():
         return [f() for f in thunks]
     main = torch.cuda.current_stream()
     dev = torch.cuda.current_device()
     side = _TILE_STREAMS.setdefault((dev, n_streams), [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)])
-    outs = [thunks[0]()]
     for st in side:
         st.wait_stream(main)
     lanes = [main] + side
-    for k, f in enumerate(thunks[1:]):
+    outs = []
+    for k, f in enumerate(thunks):
         st = lanes[k % n_streams]
         with torch.cuda.stream(st):
             o = f()
