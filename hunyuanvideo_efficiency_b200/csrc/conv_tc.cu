@@ -19,6 +19,8 @@
 //   with the n-tile fastest so concurrent CTAs share the A halo in L2.
 #include <cuda.h>
 
+#include <type_traits>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -394,7 +396,43 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (KHT && a.tfold) cls = tile_fold_class(a, mg);
         const int ngroups_t = (KHT && a.tfold) ? (cls + 1) * a.nkw * kchunks : ngroups;
         const int tshift = (KHT && a.tfold) ? 2 - cls : 0;
-        for (int g = 0; g < ngroups_t; ++g) {
+        if constexpr (KHT) {
+          // (kt, kw, channel chunk) groups as nested loops: the flat index with its divisions per group was part of what
+          // kept this warp (one A and nsub B loads per group) from staying ahead of the MMA warp on the short phase convs
+          const int nkt_eff = a.tfold ? cls + 1 : a.nkt;
+          for (int kt = 0; kt < nkt_eff; ++kt) {
+            const int wkt = a.tfold ? tfold_wgroup(cls, kt) : kt;
+            for (int kw = 0; kw < a.nkw; ++kw) {
+              for (int kc = 0; kc < kchunks; ++kc) {
+                mbar_wait(aempty_bar + 8 * sa, pa ^ 1);
+                const bool skip = (a.probe & 1) && afills >= NA;
+                ++afills;
+                if (elect_one()) {
+                  if (leader) { if (skip) mbar_arrive(afull_bar + 8 * sa); else mbar_expect_tx(afull_bar + 8 * sa, 2 * a.a_tx); }
+                  if (!skip) tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull_bar + 8 * sa, kc * 64, m.w0 + a.ow + kw, m.h0 + a.oh, m.t + a.ot + tshift + kt, m.b);
+                  if (!leader) mbar_arrive_leader(afull_bar + 8 * sa);
+                }
+                __syncwarp();
+                if (++sa == NA) { sa = 0; pa ^= 1; }
+#pragma unroll
+                for (int sub = 0; sub < NSUB; ++sub) {
+                  if (sub >= nsub) break;
+                  mbar_wait(bempty_bar + 8 * sb, pb ^ 1);
+                  const bool skipb = (a.probe & 1) && bfills >= SB;
+                  ++bfills;
+                  if (elect_one()) {
+                    if (leader) { if (skipb) mbar_arrive(bfull_bar + 8 * sb); else mbar_expect_tx(bfull_bar + 8 * sb, 2 * Cfg::B_STAGE_BYTES); }
+                    if (!skipb) tma_load_3d_2sm(sB + sb * Cfg::B_STAGE_BYTES, &tmB, bfull_bar + 8 * sb, kc * 64, n0, (wkt * a.nsub + sub) * a.nkw + kw);
+                    if (!leader) mbar_arrive_leader(bfull_bar + 8 * sb);
+                  }
+                  __syncwarp();
+                  if (++sb == SB) { sb = 0; pb ^= 1; }
+                }
+              }
+            }
+          }
+        }
+        for (int g = 0; g < ngroups_t && !KHT; ++g) {
           const int kc = g % kchunks, tg = g / kchunks;
           int kt, kh0, kw;
           if (KHT) { kt = tg / a.nkw; kw = tg % a.nkw; kh0 = 0; }
@@ -473,16 +511,53 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t d_tmem = tmem_base + acc * BN;
         int ngroups_t = ngroups;
         if (KHT && a.tfold) ngroups_t = (tile_fold_class(a, (int64_t)((uint32_t)tile / (uint32_t)a.n_tiles)) + 1) * a.nkw * kchunks;
-        for (int g = 0; g < ngroups_t; ++g) {
-          if (KHT) { mbar_wait(afull_bar + 8 * sa, pa); }
+        if constexpr (KHT) {
+          // Per A stage: one wait, then per kh tap one wait and four MMAs whose descriptors are the stage bases plus
+          // compile-time offsets (tap kh = + kh halo rows of TW voxels; K = 16 slice k = + 32 B).  The tap count per stage
+          // (3, or 2 for a sub-pixel phase) is a template argument of the loop: with the run-time `nsub` the loop took ~185
+          // instructions per stage and the 8 MMAs of a phase stage (1024 clocks) did not hide it (ncu: tensor pipe 62 %).
+          const uint64_t adesc0 = make_kmajor_sw128_desc(sA);
+          const uint64_t bdesc0 = make_kmajor_sw128_desc(sB);
+          const uint32_t row16 = (uint32_t)(a.TW * 128) >> 4;
+          auto run_groups = [&](auto ns_c) {
+            constexpr int NS = decltype(ns_c)::value;
+#pragma unroll 1
+            for (int g = 0; g < ngroups_t; ++g) {
+              mbar_wait(afull_bar + 8 * sa, pa);
+              const uint64_t ad = adesc0 + (uint64_t)((uint32_t)sa * (uint32_t)(Cfg::A_BYTES >> 4));
+              const uint32_t first = g != 0 ? 1u : 0u;
+#pragma unroll
+              for (int sub = 0; sub < NS; ++sub) {
+                mbar_wait(bfull_bar + 8 * sb, pb);
+                tc_fence_after();
+                if (elect_one()) {
+                  const uint64_t as = ad + (uint64_t)((uint32_t)sub * row16);
+                  const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)sb * (uint32_t)(Cfg::B_STAGE_BYTES >> 4));
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16_2sm(d_tmem, as + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (sub | k) != 0 ? 1u : first);
+                  umma_commit_2sm(bempty_bar + 8 * sb);
+                }
+                __syncwarp();
+                if (++sb == SB) { sb = 0; pb ^= 1; }
+              }
+              if (elect_one()) umma_commit_2sm(aempty_bar + 8 * sa);
+              __syncwarp();
+              if (++sa == NA) { sa = 0; pa ^= 1; }
+            }
+          };
+          if (nsub == 3) run_groups(std::integral_constant<int, 3>{});
+          else if (nsub == 2) run_groups(std::integral_constant<int, 2>{});
+          else run_groups(std::integral_constant<int, 1>{});
+        }
+        for (int g = 0; g < ngroups_t && !KHT; ++g) {
 #pragma unroll
           for (int sub = 0; sub < NSUB; ++sub) {
             if (sub >= nsub) break;
             mbar_wait(bfull_bar + 8 * sb, pb);
             tc_fence_after();
             if (elect_one()) {
-              // KHT: tap kh reads the halo stage 8 rows (= 1024 B, one swizzle atom) further down
-              const uint64_t adesc = make_kmajor_sw128_desc(KHT ? sA + sa * Cfg::A_BYTES + sub * a.TW * 128 : sA + sb * Cfg::A_BYTES);
+              const uint64_t adesc = make_kmajor_sw128_desc(sA + sb * Cfg::A_BYTES);
               const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * Cfg::B_STAGE_BYTES);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -491,11 +566,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             __syncwarp();
             if (++sb == SB) { sb = 0; pb ^= 1; }
-          }
-          if (KHT) {
-            if (elect_one()) umma_commit_2sm(aempty_bar + 8 * sa);
-            __syncwarp();
-            if (++sa == NA) { sa = 0; pa ^= 1; }
           }
         }
         if (KHT) {
