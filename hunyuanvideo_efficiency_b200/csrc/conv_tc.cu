@@ -55,6 +55,7 @@ struct TcArgs {
 };
 
 constexpr int TC_THREADS = 192;
+constexpr int TC2_KHT_THREADS = 224;   // kh-trick pair kernel: warp 6 = B (weight) TMA producer, warp 0 loads only the A halo stages
 constexpr int A_STAGE_BYTES = 128 * 64 * 2;
 
 // MT = number of 128-voxel m-tiles a CTA multiplies against one B (weight) tile per stage.  MT = 2 halves
@@ -334,7 +335,7 @@ template <int BN, bool KHT> struct Tc2Cfg {
 };
 
 template <typename T, typename OT, int BN, bool KHT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(KHT ? TC2_KHT_THREADS : TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const TcArgs a) {
@@ -382,9 +383,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int nsub = KHT ? a.nsub : 1;
   const int64_t pair0 = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
-  if (warp == 0) {
+  // ================= TMA producers (both CTAs; warp-uniform loops, one elected lane issues) =================
+  // kh-trick form: warp 0 loads the A halo stages and warp 6 the weight stages (one warp doing both, one A and nsub B loads
+  // per group, did not stay ahead of the MMA warp on the short phase convs); otherwise warp 0 loads both.
+  auto produce = [&](const bool do_a, const bool do_b) {
     {
-      // ================= TMA producer (both CTAs; warp-uniform loops, one elected lane issues) =================
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       int64_t afills = 0, bfills = 0;
       for (int64_t tile = pair0; tile < a.total_tiles; tile += npairs) {
@@ -404,19 +407,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int wkt = a.tfold ? tfold_wgroup(cls, kt) : kt;
             for (int kw = 0; kw < a.nkw; ++kw) {
               for (int kc = 0; kc < kchunks; ++kc) {
-                mbar_wait(aempty_bar + 8 * sa, pa ^ 1);
-                const bool skip = (a.probe & 1) && afills >= NA;
-                ++afills;
-                if (elect_one()) {
-                  if (leader) { if (skip) mbar_arrive(afull_bar + 8 * sa); else mbar_expect_tx(afull_bar + 8 * sa, 2 * a.a_tx); }
-                  if (!skip) tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull_bar + 8 * sa, kc * 64, m.w0 + a.ow + kw, m.h0 + a.oh, m.t + a.ot + tshift + kt, m.b);
-                  if (!leader) mbar_arrive_leader(afull_bar + 8 * sa);
+                if (do_a) {
+                  mbar_wait(aempty_bar + 8 * sa, pa ^ 1);
+                  const bool skip = (a.probe & 1) && afills >= NA;
+                  ++afills;
+                  if (elect_one()) {
+                    if (leader) { if (skip) mbar_arrive(afull_bar + 8 * sa); else mbar_expect_tx(afull_bar + 8 * sa, 2 * a.a_tx); }
+                    if (!skip) tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull_bar + 8 * sa, kc * 64, m.w0 + a.ow + kw, m.h0 + a.oh, m.t + a.ot + tshift + kt, m.b);
+                    if (!leader) mbar_arrive_leader(afull_bar + 8 * sa);
+                  }
+                  __syncwarp();
+                  if (++sa == NA) { sa = 0; pa ^= 1; }
                 }
-                __syncwarp();
-                if (++sa == NA) { sa = 0; pa ^= 1; }
 #pragma unroll
                 for (int sub = 0; sub < NSUB; ++sub) {
-                  if (sub >= nsub) break;
+                  if (sub >= nsub || !do_b) break;
                   mbar_wait(bempty_bar + 8 * sb, pb ^ 1);
                   const bool skipb = (a.probe & 1) && bfills >= SB;
                   ++bfills;
@@ -477,26 +482,35 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           // fused 1x1x1 conv_shortcut: one halo stage of the block input (box origin one row above the tile) and one
           // weight stage per 64-channel chunk
           for (int kc = 0; kc < a.sc_chunks; ++kc) {
-            mbar_wait(aempty_bar + 8 * sa, pa ^ 1);
-            if (elect_one()) {
-              if (leader) mbar_expect_tx(afull_bar + 8 * sa, 2 * a.a_tx);
-              tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmX, afull_bar + 8 * sa, kc * 64, m.w0, m.h0 - 1, m.t, m.b);
-              if (!leader) mbar_arrive_leader(afull_bar + 8 * sa);
+            if (do_a) {
+              mbar_wait(aempty_bar + 8 * sa, pa ^ 1);
+              if (elect_one()) {
+                if (leader) mbar_expect_tx(afull_bar + 8 * sa, 2 * a.a_tx);
+                tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmX, afull_bar + 8 * sa, kc * 64, m.w0, m.h0 - 1, m.t, m.b);
+                if (!leader) mbar_arrive_leader(afull_bar + 8 * sa);
+              }
+              __syncwarp();
+              if (++sa == NA) { sa = 0; pa ^= 1; }
             }
-            __syncwarp();
-            if (++sa == NA) { sa = 0; pa ^= 1; }
-            mbar_wait(bempty_bar + 8 * sb, pb ^ 1);
-            if (elect_one()) {
-              if (leader) mbar_expect_tx(bfull_bar + 8 * sb, 2 * Cfg::B_STAGE_BYTES);
-              tma_load_3d_2sm(sB + sb * Cfg::B_STAGE_BYTES, &tmW, bfull_bar + 8 * sb, kc * 64, n0, 0);
-              if (!leader) mbar_arrive_leader(bfull_bar + 8 * sb);
+            if (do_b) {
+              mbar_wait(bempty_bar + 8 * sb, pb ^ 1);
+              if (elect_one()) {
+                if (leader) mbar_expect_tx(bfull_bar + 8 * sb, 2 * Cfg::B_STAGE_BYTES);
+                tma_load_3d_2sm(sB + sb * Cfg::B_STAGE_BYTES, &tmW, bfull_bar + 8 * sb, kc * 64, n0, 0);
+                if (!leader) mbar_arrive_leader(bfull_bar + 8 * sb);
+              }
+              __syncwarp();
+              if (++sb == SB) { sb = 0; pb ^= 1; }
             }
-            __syncwarp();
-            if (++sb == SB) { sb = 0; pb ^= 1; }
           }
         }
       }
     }
+  };
+  if (warp == 0) {
+    produce(true, !KHT);
+  } else if (KHT && warp == 6) {
+    produce(false, true);
   } else if (warp == 1) {
     if (leader) {
       // ================= MMA issuer (leader CTA only; warp-uniform loops, one elected lane issues) =================
@@ -592,7 +606,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp < 6) {
     // ================= epilogue warps (both CTAs, own TMEM) =================
     const int q = warp & 3;
     int iter = 0;
@@ -771,7 +785,7 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
     if (a.res)
       if (int e = encode_out_map(&tmR, dt, a.res, a.roff, a.Cout, a.Wo, a.Ho, a.To, a.B, a.rsW, a.rsH, a.rsT, a.rsB, a.TW)) return e;
   }
-  conv_tc2_kernel<T, OT, BN, KHT><<<(unsigned)(2 * pairs), TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, tmX ? *tmX : tmA, tmW ? *tmW : tmB, a);
+  conv_tc2_kernel<T, OT, BN, KHT><<<(unsigned)(2 * pairs), KHT ? TC2_KHT_THREADS : TC_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, tmX ? *tmX : tmA, tmW ? *tmW : tmB, a);
   return check_launch("conv3d_causal_tc (2-CTA)");
 }
 
