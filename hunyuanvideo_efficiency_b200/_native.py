@@ -46,7 +46,7 @@ _SIGNATURES = {
     "hyvae_conv3d_upphase_tc": [_VP, _vp, _vp, _VP, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
     "hyvae_groupnorm_finalize": [_vp, _i32, _i64, _i32, _vp, _vp],
     "hyvae_groupnorm_apply_wino": [_VP, _vp, _vp, _vp, _i32, _f32, _i32, _VP, _vp],
-    "hyvae_conv3d_causal_wino": [_VP, _i32, _vp, _vp, _VP, _VP, _vp, _VP, _vp, _i32, _vp],
+    "hyvae_conv3d_causal_wino": [_VP, _i32, _vp, _vp, _VP, _VP, _vp, _VP, _vp, _i32, _vp, _vp],
     "hyvae_groupnorm_stats": [_VP, _i32, _vp, _vp, _i64, _vp],
     "hyvae_groupnorm_apply": [_VP, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _VP, _vp],
     "hyvae_pad_upsample": [_VP, _VP, _i32, _i32, _i32, _vp],
@@ -64,7 +64,7 @@ _SIGNATURES = {
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["hyvae_version", "hyvae_last_error", "hyvae_device_supports_tc", "hyvae_launch_count",
                                        "hyvae_groupnorm_workspace_bytes", "hyvae_profile_begin", "hyvae_profile_end", "hyvae_profile_executed_flops",
-                                       "hyvae_conv3d_tc_gn_rows", "hyvae_frame_metrics_workspace_bytes", "hyvae_wino_planes"])
+                                       "hyvae_conv3d_tc_gn_rows", "hyvae_gn_partials_doubles", "hyvae_frame_metrics_workspace_bytes", "hyvae_wino_planes"])
 
 _lib = None
 
@@ -98,6 +98,8 @@ def lib():
         l.hyvae_wino_planes.argtypes = [_i32]
         l.hyvae_conv3d_tc_gn_rows.restype = C.c_int64
         l.hyvae_conv3d_tc_gn_rows.argtypes = []
+        l.hyvae_gn_partials_doubles.restype = C.c_int64
+        l.hyvae_gn_partials_doubles.argtypes = [_i32, _i32]
         _lib = l
     return _lib
 
@@ -248,19 +250,22 @@ def conv3d_direct(x: Vol, w: torch.Tensor, bias, k: int, stride, cout: int, resi
     return y
 
 
-ABI_VERSION = 120      # HYVAE_VERSION of include/hyvae.h this module binds
+ABI_VERSION = 121      # HYVAE_VERSION of include/hyvae.h this module binds
 VARIANT_KWPACK = 0x200  # hyvae_conv3d_causal_tc: x is a kw-packed thin volume (Vol.from_ncthw(kw_pack=True)), w is [9][Cout][16]
 VARIANT_TFOLD = 0x100  # hyvae_conv3d_causal_tc: `w` carries the 18 folded first-frame tap slices after the 27 (include/hyvae.h)
 _GN_PART = {}
 
 
 def _gn_partials(B: int, rows: int, groups: int, device) -> torch.Tensor:
-    """[B][rows][groups][2] fp64 scratch for the conv epilogue's GroupNorm partial sums.  Zeroed once: every
-    hyvae_groupnorm_finalize leaves it zeroed again, and conv + finalize pairs are stream ordered."""
+    """fp64 scratch for the conv epilogue's GroupNorm partial sums: [B][rows][groups][2] warp rows, then the per-CTA rows and
+    the ticket of the convs that finish the statistics themselves (hyvae_gn_partials_doubles).  Zeroed once: every
+    hyvae_groupnorm_finalize / fused finalize leaves it zeroed again, and conv + finalize pairs are stream ordered."""
     key = (device, torch.cuda.current_stream(device).cuda_stream, B, rows, groups)
     buf = _GN_PART.get(key)
     if buf is None:
-        buf = _GN_PART[key] = torch.zeros((B, rows, groups, 2), dtype=torch.float64, device=device)
+        n = int(lib().hyvae_gn_partials_doubles(B, groups))
+        assert n >= B * rows * groups * 2
+        buf = _GN_PART[key] = torch.zeros((n,), dtype=torch.float64, device=device)
     return buf
 
 
@@ -289,6 +294,12 @@ class _GnEpilogue:
         if exc_type is not None and self.part is not None:
             _GN_PART.pop((self.device, torch.cuda.current_stream(self.device).cuda_stream, self.B, self.rows, self.groups), None)
         return False
+
+    def attach(self, y: Vol):
+        """The conv finished the statistics itself (fused finalize): they travel with y, no launch."""
+        if self.part is not None:
+            y.gn_sums, y.gn_groups = self.sums, self.groups
+        return y
 
     def finalize(self, y: Vol):
         if self.part is not None:
@@ -390,9 +401,10 @@ def conv3d_wino(planes: Vol, uw: torch.Tensor, bias, cout: int, residual: Option
     with _GnEpilogue(planes, cout, gn_groups, 4) as gn:
         part, groups = gn.args()
         _check(lib().hyvae_conv3d_causal_wino(planes.ref(), T, uw.data_ptr(), _ptr(bias), residual.ref() if residual else None,
-                                              sc_x.ref() if sc_x is not None else None, _ptr(sc_w), y.ref(), part, groups, _stream()),
+                                              sc_x.ref() if sc_x is not None else None, _ptr(sc_w), y.ref(), part, groups,
+                                              _ptr(gn.sums) if part is not None else None, _stream()),
                "conv3d_causal_wino")
-        return gn.finalize(y)
+        return gn.attach(y)   # the kernel's last CTA summed the rows: no hyvae_groupnorm_finalize launch
 
 
 def halo_fill(y: Vol) -> Vol:

@@ -33,6 +33,10 @@ int launch_halo(int dtype, int bn, int mt, bool pair, bool thin, const CUtensorM
 
 // rows per batch item of the GroupNorm partial buffer: one per (CTA, epilogue warp); the Winograd kernel has 8 epilogue warps
 inline int gn_partial_rows() { return num_sms() * 8; }
+// Layout of the caller's GroupNorm partial buffer (hyvae_gn_partials_doubles): [B][gn_partial_rows()][groups][2] per-warp rows,
+// then [B][num_sms()][groups][2] per-CTA rows and one 8-byte ticket used by kernels that finish the statistics themselves.
+inline int64_t gn_warp_rows_doubles(int B, int groups) { return (int64_t)B * gn_partial_rows() * groups * 2; }
+inline int64_t gn_cta_rows_doubles(int B, int groups) { return (int64_t)B * num_sms() * groups * 2; }
 
 // conv_wino.cu: stride-1 3x3x3 conv as Winograd F(2,3) along T over a plane volume (see the header of that file)
 struct WinoArgs {
@@ -46,6 +50,10 @@ struct WinoArgs {
   int sc_chunks, sc_cin;   // fused 1x1x1 shortcut conv: 64-channel chunks / channels of its input (0 = none)
   double* gn_part;         // optional [B][gn_rows][gn_groups][2]
   int gn_groups, gn_cpg, gn_rows;
+  double* gn_sums;         // optional [B][gn_groups][2]: the kernel finishes the statistics itself (last CTA sums in fixed order)
+  double* gn_cta;          // [B][gn_cta_rows][gn_groups][2] per-CTA rows (inside the caller's partial buffer)
+  unsigned int* gn_ticket; // arrival counter of the fold (zero between launches)
+  int gn_cta_rows;
 };
 int launch_wino(int dtype, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
                 const CUtensorMap& tmX, const CUtensorMap& tmW, const WinoArgs& a, cudaStream_t stream);

@@ -806,6 +806,9 @@ static void pick_tile(int Ho, int Wo, int sh, int sw, int* TH, int* TW) {
 }
 
 extern "C" int64_t hyvae_conv3d_tc_gn_rows(void) { return (int64_t)gn_partial_rows(); }
+extern "C" int64_t hyvae_gn_partials_doubles(int32_t B, int32_t groups) {
+  return B <= 0 || groups <= 0 ? 0 : gn_warp_rows_doubles(B, groups) + gn_cta_rows_doubles(B, groups) + 2;
+}
 
 static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, const hyvae_vol* residual,
                          const hyvae_vol* y, int32_t k, int32_t st, int32_t sh, int32_t sw,

@@ -435,6 +435,55 @@ conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   cluster_sync_all();  // no CTA of the pair exits (or frees TMEM) while the other may still signal it
   if (warp == 2) { tc_fence_after(); tmem_dealloc_2sm<512>(tmem_base); }
+
+  // ---- GroupNorm statistics finished in the kernel (replaces a hyvae_groupnorm_finalize launch per conv) -----------------
+  // Every CTA adds its eight warp rows (fixed order) into ITS row of the per-CTA buffer and re-zeroes them; the CTA whose
+  // ticket is the last one adds the CTA rows in index order: same bits whatever the arrival order.
+  if (a.gn_sums != nullptr) {
+    volatile int* s_last = reinterpret_cast<volatile int*>(gen_base + (tmem_slot - smem_base) + 8);
+    double* scratch = reinterpret_cast<double*>(gen_base + (sOut - smem_base));   // the staging tiles are idle by now
+    const int G2 = a.gn_groups * 2, nval = a.B * G2;
+    for (int idx = threadIdx.x; idx < nval; idx += blockDim.x) {
+      const int b = idx / G2, v = idx - b * G2;
+      double* p = a.gn_part + ((int64_t)b * a.gn_rows + (int64_t)blockIdx.x * 8) * G2 + v;
+      double r[8];
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) r[w8] = __ldcg(p + (int64_t)w8 * G2);
+      double acc = 0.0;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) { acc += r[w8]; if (r[w8] != 0.0) p[(int64_t)w8 * G2] = 0.0; }
+      a.gn_cta[((int64_t)b * a.gn_cta_rows + blockIdx.x) * G2 + v] = acc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *s_last = (atomicAdd(a.gn_ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (*s_last) {
+      __threadfence();
+      constexpr int PARTS = 5;                      // 5 x 64 = 320 of the 352 threads for the usual [1][32][2]
+      const int nc = (int)gridDim.x, per = (nc + PARTS - 1) / PARTS;
+      for (int base = 0; base < nval; base += 64) {
+        const int v = base + (int)(threadIdx.x & 63), part = (int)(threadIdx.x >> 6);
+        if (part < PARTS && v < nval) {
+          const int b = v / G2, vv = v - b * G2;
+          const double* q = a.gn_cta + ((int64_t)b * a.gn_cta_rows) * G2 + vv;
+          double acc = 0.0;
+          const int c1 = min(nc, (part + 1) * per);
+          for (int c = part * per; c < c1; ++c) acc += __ldcg(q + (int64_t)c * G2);
+          scratch[part * 64 + (threadIdx.x & 63)] = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x < 64 && v < nval) {
+          double acc = 0.0;
+#pragma unroll
+          for (int pp = 0; pp < PARTS; ++pp) acc += scratch[pp * 64 + threadIdx.x];
+          a.gn_sums[v] = acc;
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) *a.gn_ticket = 0u;     // ready for the next launch on this stream
+    }
+  }
 }
 
 template <typename T, typename Cfg>
@@ -485,7 +534,7 @@ extern "C" int32_t hyvae_wino_planes(int32_t T) { return T <= 0 ? 0 : 1 + 4 * ((
 
 extern "C" int hyvae_conv3d_causal_wino(const hyvae_vol* planes, int32_t T, const void* uw, const float* bias, const hyvae_vol* residual,
                                         const hyvae_vol* sc_x, const void* sc_w, const hyvae_vol* y, double* gn_partials,
-                                        int32_t gn_groups, void* stream) {
+                                        int32_t gn_groups, double* gn_sums, void* stream) {
   if (int e = check_vol(planes, "planes")) return e;
   if (int e = check_vol(y, "y")) return e;
   HYVAE_CHECK_ARG(uw != nullptr, "uw is null");
@@ -520,6 +569,13 @@ extern "C" int hyvae_conv3d_causal_wino(const hyvae_vol* planes, int32_t T, cons
     HYVAE_CHECK_ARG(((uintptr_t)sc_x->data & 15) == 0 && ((uintptr_t)sc_w & 15) == 0, "pointers must be 16-byte aligned");
   }
   a.gn_part = gn_partials; a.gn_groups = gn_groups; a.gn_cpg = 0; a.gn_rows = gn_partial_rows();
+  a.gn_sums = nullptr; a.gn_cta = nullptr; a.gn_ticket = nullptr; a.gn_cta_rows = num_sms();
+  if (gn_partials && gn_sums) {   // the buffer has the hyvae_gn_partials_doubles() layout: warp rows | CTA rows | ticket
+    HYVAE_CHECK_ARG(y->B * gn_groups * 2 <= 4096, "fused GroupNorm finalize: B * groups too large");
+    a.gn_sums = gn_sums;
+    a.gn_cta = gn_partials + gn_warp_rows_doubles(y->B, gn_groups);
+    a.gn_ticket = reinterpret_cast<unsigned int*>(a.gn_cta + gn_cta_rows_doubles(y->B, gn_groups));
+  }
   if (gn_partials) {
     HYVAE_CHECK_ARG(gn_groups > 0 && y->C % gn_groups == 0, "gn_groups=%d does not divide Cout=%d", gn_groups, y->C);
     a.gn_cpg = y->C / gn_groups;

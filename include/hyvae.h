@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HYVAE_VERSION 120 /* 0.1.2: Winograd-T convs, GroupNorm finalize folded into the convs, blend post-process epilogue */
+#define HYVAE_VERSION 121 /* 0.1.2: Winograd-T convs, GroupNorm finalize folded into the convs, blend post-process epilogue */
 
 typedef enum { HYVAE_OK = 0, HYVAE_EINVAL = -1, HYVAE_ECUDA = -2, HYVAE_EUNSUPPORTED = -3 } hyvae_status;
 typedef enum { HYVAE_BF16 = 0, HYVAE_F32 = 1, HYVAE_F16 = 2 } hyvae_dtype;
@@ -125,11 +125,16 @@ int hyvae_groupnorm_apply_wino(const hyvae_vol* x, const double* sums, const flo
                                float eps, int32_t silu, const hyvae_vol* planes, void* stream);
 int hyvae_conv3d_causal_wino(const hyvae_vol* planes, int32_t T, const void* uw, const float* bias, const hyvae_vol* residual,
                              const hyvae_vol* sc_x, const void* sc_w, const hyvae_vol* y, double* gn_partials, int32_t gn_groups,
-                             void* stream);
+                             double* gn_sums, void* stream);
 /* rows-per-batch of the gn_partials buffer: gn_partials is [B][rows][gn_groups][2] fp64, ZEROED by the caller; every
  * (CTA, warp) of the conv accumulates into its own row, so several launches may add into one buffer (the phases of
  * an upsampling conv) before hyvae_groupnorm_finalize reduces the rows in a fixed order. */
 int64_t hyvae_conv3d_tc_gn_rows(void);
+/* Size (in doubles) of a gn_partials buffer for B batch items and `groups` groups: the [B][rows][groups][2] warp rows,
+ * followed by per-CTA rows and an arrival ticket.  hyvae_conv3d_causal_wino uses the tail when `gn_sums` ([B][groups][2])
+ * is given: it then finishes the statistics itself (every CTA folds its warp rows, the last CTA to arrive adds the CTA
+ * rows in index order: bit-reproducible) and leaves the whole buffer zeroed, so no hyvae_groupnorm_finalize launch follows. */
+int64_t hyvae_gn_partials_doubles(int32_t B, int32_t groups);
 
 /* ---- GroupNorm (+SiLU) -------------------------------------------------------------------------
  * Replaces nn.GroupNorm(32,C,eps=1e-6) + SiLU, unet_causal_3d_blocks.py:359-363,401-405 and

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in _declared():
         assert hasattr(lib, name), name
     lib.hyvae_version.restype = ctypes.c_int
-    assert lib.hyvae_version() == 120
+    assert lib.hyvae_version() == 121
 
 
 def test_no_cpu_fallback():

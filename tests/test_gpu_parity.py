@@ -677,8 +677,8 @@ def test_resnet_block_fp16_fused_shortcut_vs_reference(cin, cout, T, H, W):
     finally:
         os.environ.pop("HYVAE_FUSE_SHORTCUT")
     assert fused_launches <= unfused_launches              # the k=1 shortcut launch is gone when the tile shape allows
-    if cout <= 128:
-        assert fused_launches == unfused_launches - 1
+    if cout <= 128:   # ... and with it (Winograd-T path: statistics finished inside the conv) the GroupNorm finalize launches
+        assert fused_launches < unfused_launches
     assert O.rel_err(ref, y.float().cpu()) < 3e-3
     assert O.rel_err(y2.float().cpu(), y.float().cpu()) < 2e-3
 
