@@ -60,6 +60,7 @@ _SIGNATURES = {
     "hyvae_image_postprocess": [_vp, _i32, _vp, _i64, _vp],
     "hyvae_blend_crop_scatter": [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32,
                                  _i32, _i32, _i32, _i32, C.POINTER(_i64), _i32, _vp],
+    "hyvae_peer_copy": [_vp, _vp, _i64, _vp],
     "hyvae_profile_class_override": [_i32],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["hyvae_version", "hyvae_last_error", "hyvae_device_supports_tc", "hyvae_launch_count",
@@ -495,6 +496,13 @@ def blend_crop_scatter(cur: torch.Tensor, above, left, N: int, Yc: int, Xc: int,
         raise HyvaeError("blend_crop_scatter: out must have the tile dtype")
     _check(lib().hyvae_blend_crop_scatter(cur.data_ptr(), _ptr(above), _ptr(left), _DT[cur.dtype], N, Yc, Xc, Ya, Xl, ev, eh,
                                           _ptr(out), Yo, Xo, y0, x0, crop_y, crop_x, ns, int(post), _stream()), "blend_crop_scatter")
+
+
+def peer_copy(dst: torch.Tensor, src: torch.Tensor):
+    """dst (possibly peer-GPU memory mapped into this process) <- src on the CURRENT stream of src's device (hyvae_peer_copy)."""
+    assert dst.is_contiguous() and src.is_contiguous() and dst.dtype == src.dtype and dst.numel() == src.numel()
+    _check(lib().hyvae_peer_copy(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size(),
+                                 torch.cuda.current_stream(src.device).cuda_stream), "peer_copy")
 
 
 def image_postprocess(image: torch.Tensor) -> torch.Tensor:

@@ -1017,6 +1017,18 @@ int hyvae_image_postprocess(const void* src, int32_t src_dtype, float* dst, int6
   return check_launch("image_postprocess");
 }
 
+// Device-to-device copy into PEER memory (a tile pushed into rank 0's arena, vae/tile_parallel.py): one cudaMemcpyAsync on the
+// SOURCE device's stream.  Nothing is enqueued on the destination device, whose other processes' contexts would otherwise be
+// time-sliced against its owner's kernels (measured at 8 GPUs: rank 0's convs ran 3 % slower with torch's cross-device
+// copy_, which records and waits events on the destination device).
+int hyvae_peer_copy(void* dst, const void* src, int64_t bytes, void* stream) {
+  HYVAE_CHECK_ARG(dst != nullptr && src != nullptr && bytes >= 0, "bad peer copy arguments");
+  if (bytes == 0) return HYVAE_OK;
+  const cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(HYVAE_ECUDA, "peer copy failed: %s", cudaGetErrorString(e));
+  return HYVAE_OK;
+}
+
 int hyvae_blend_crop_scatter(void* cur, const void* above, const void* left, int32_t dtype, int64_t N,
                              int32_t Yc, int32_t Xc, int32_t Ya, int32_t Xl, int32_t ev, int32_t eh,
                              void* out, int32_t Yo, int32_t Xo, int32_t y0, int32_t x0, int32_t crop_y,

@@ -521,13 +521,18 @@ class AutoencoderKLCausal3D(nn.Module):
         return self._blend(a, b, blend_extent, -3)
 
     # ---- spatial tiling (:362-469)
-    def _spatial_tiled(self, x: torch.Tensor, fn, tile: int, stride: int, extent: int, limit: int, post: bool = False) -> torch.Tensor:
+    @staticmethod
+    def _spatial_cuts(x: torch.Tensor, tile: int, stride: int):
+        """Tile origins of the reference's spatial loops (:387-396,441-450) and the grid's row count."""
         ii, jj = list(range(0, x.shape[-2], stride)), list(range(0, x.shape[-1], stride))
-        cuts = [(i, j) for i in ii for j in jj]
+        return [(i, j) for i in ii for j in jj], len(ii), len(jj)
+
+    def _spatial_tiled(self, x: torch.Tensor, fn, tile: int, stride: int, extent: int, limit: int, post: bool = False) -> torch.Tensor:
+        cuts, ni, nj = self._spatial_cuts(x, tile, stride)
         outs = run_tiles([(lambda i=i, j=j: fn(x[:, :, :, i:i + tile, j:j + tile])) for i, j in cuts],
                          self.tile_streams if x.is_cuda else 1)
         outs = self._guard_tiles(outs, lambda k: fn(x[:, :, :, cuts[k][0]:cuts[k][0] + tile, cuts[k][1]:cuts[k][1] + tile]))
-        rows = [outs[r * len(jj):(r + 1) * len(jj)] for r in range(len(ii))]
+        rows = [outs[r * nj:(r + 1) * nj] for r in range(ni)]
         return self._assemble_spatial(rows, extent, limit, post)
 
     def _assemble_spatial(self, rows, extent: int, limit: int, post: bool = False) -> torch.Tensor:
@@ -579,15 +584,33 @@ class AutoencoderKLCausal3D(nn.Module):
         return DecoderOutput(sample=dec)
 
     # ---- temporal tiling (:471-541)
-    def _temporal_tiled(self, x, fn_plain, fn_spatial, tile_t, stride, extent, limit, min_size, post: bool = False) -> torch.Tensor:
-        row = []  # (tensor, first_frame_offset): tiles i>0 drop their first output frame (:491,527)
-        for i in range(0, x.shape[2], stride):
+    def _temporal_tiled(self, x, fn_plain, spatial, tile_t, stride, extent, limit, min_size, post: bool = False) -> torch.Tensor:
+        """spatial = (tile, stride, extent, limit) of the spatial split applied inside every temporal tile (:487-490,523-526).
+        The sub-model calls of ALL temporal tiles are independent, so they are dealt over the tile streams in one batch
+        (one join per direction instead of one per temporal tile); assembly then follows the reference's order: the
+        spatial grid of each temporal tile, then the temporal chain."""
+        starts = list(range(0, x.shape[2], stride))
+        s_tile, s_stride, s_extent, s_limit = spatial
+        thunks, reruns, layout = [], [], []   # layout: per temporal tile (first thunk index, rows, columns) or (index, 0, 0) when not split
+        for i in starts:
             t = x[:, :, i:i + tile_t + 1]
             if self.use_spatial_tiling and (t.shape[-1] > min_size or t.shape[-2] > min_size):
-                t = fn_spatial(t)
+                cuts, ni, nj = self._spatial_cuts(t, s_tile, s_stride)
+                layout.append((len(thunks), ni, nj))
+                for (a, b) in cuts:
+                    thunks.append(lambda t=t, a=a, b=b: fn_plain(t[:, :, :, a:a + s_tile, b:b + s_tile]))
             else:
-                t = self._guarded(fn_plain, t)
-            row.append((t, 1 if i > 0 else 0))
+                layout.append((len(thunks), 0, 0))
+                thunks.append(lambda t=t: fn_plain(t))
+        outs = run_tiles(thunks, self.tile_streams if x.is_cuda else 1)
+        outs = self._guard_tiles(outs, lambda k: thunks[k]())
+        row = []  # (tensor, first_frame_offset): tiles i>0 drop their first output frame (:491,527)
+        for n, (k0, ni, nj) in enumerate(layout):
+            if ni == 0:
+                t = outs[k0]
+            else:
+                t = self._assemble_spatial([outs[k0 + r * nj:k0 + (r + 1) * nj] for r in range(ni)], s_extent, s_limit)
+            row.append((t, 1 if n > 0 else 0))
         return self._assemble_temporal(row, extent, limit, post)
 
     def _assemble_temporal(self, row, extent: int, limit: int, post: bool = False) -> torch.Tensor:
@@ -616,7 +639,10 @@ class AutoencoderKLCausal3D(nn.Module):
     def temporal_tiled_encode(self, x: torch.Tensor, return_dict: bool = True):
         stride = int(self.tile_sample_min_tsize * (1 - self.tile_overlap_factor))
         extent = int(self.tile_latent_min_tsize * self.tile_overlap_factor)
-        moments = self._temporal_tiled(x, self._encode_tile, lambda t: self.spatial_tiled_encode(t, return_moments=True),
+        s_extent = int(self.tile_latent_min_size * self.tile_overlap_factor)
+        spatial = (self.tile_sample_min_size, int(self.tile_sample_min_size * (1 - self.tile_overlap_factor)), s_extent,
+                   self.tile_latent_min_size - s_extent)                         # as spatial_tiled_encode
+        moments = self._temporal_tiled(x, self._encode_tile, spatial,
                                        self.tile_sample_min_tsize, stride, extent, self.tile_latent_min_tsize - extent,
                                        self.tile_sample_min_size)
         posterior = DiagonalGaussianDistribution(moments)
@@ -627,7 +653,10 @@ class AutoencoderKLCausal3D(nn.Module):
     def temporal_tiled_decode(self, z: torch.Tensor, return_dict: bool = True, _post: bool = False):
         stride = int(self.tile_latent_min_tsize * (1 - self.tile_overlap_factor))
         extent = int(self.tile_sample_min_tsize * self.tile_overlap_factor)
-        dec = self._temporal_tiled(z, self._decode_tile, lambda t: self.spatial_tiled_decode(t, return_dict=True).sample,
+        s_extent = int(self.tile_sample_min_size * self.tile_overlap_factor)
+        spatial = (self.tile_latent_min_size, int(self.tile_latent_min_size * (1 - self.tile_overlap_factor)), s_extent,
+                   self.tile_sample_min_size - s_extent)                         # as spatial_tiled_decode
+        dec = self._temporal_tiled(z, self._decode_tile, spatial,
                                    self.tile_latent_min_tsize, stride, extent, self.tile_sample_min_tsize - extent,
                                    self.tile_latent_min_size, post=_post)
         if not return_dict:

@@ -8,7 +8,9 @@ reference's tile grid and the results are exchanged with ONE collective per dire
   decode: every rank PUSHES each decoded tile into rank 0's tile arena over NVLink as soon as the tile is finished
           (peer-to-peer copy engine writes into rank 0's memory, mapped through CUDA IPC; no SMs, overlapped with the
           remaining tiles' compute), then ONE tiny all_reduce orders the pushes before rank 0's raster-order blend.
-          Where peer memory cannot be mapped (CPU / gloo tests, HYVAE_TILE_PUSH=0) the tiles travel in one NCCL gather.
+          Opt-in (HYVAE_TILE_PUSH=1).  The default is ONE NCCL gather of the tiles to rank 0: at 8 GPUs it measured faster
+          (460 vs 480 ms per step, profiles/r02_bench_8gpu_{gather,push_v1}.json) than the first push version, whose
+          cross-device torch copies enqueued event work on rank 0's GPU from seven other processes.
 
 The blend chain is order dependent, so assembly always happens on complete tile grids, in the reference's order.
 The tile functions / assemblers are injectable so the partition + exchange logic is testable on CPU (gloo).
@@ -23,6 +25,7 @@ import os
 import torch
 import torch.distributed as dist
 
+from .. import _native as N
 from .model import run_tiles
 
 
@@ -121,7 +124,7 @@ class TileParallelVAE:
         after the blends of call i.  The arenas are allocated once per (tile set, dtype) and shared through CUDA IPC
         (torch.multiprocessing's reduce_tensor: cudaIpcGetMemHandle / cudaIpcOpenMemHandle), so a push is a plain
         device-to-device copy into peer memory: copy engines over NVLink, no SM and no NCCL kernel."""
-        if os.environ.get("HYVAE_TILE_PUSH", "1") != "1" or device.type != "cuda" or self.world < 2:
+        if os.environ.get("HYVAE_TILE_PUSH", "0") != "1" or device.type != "cuda" or self.world < 2:
             return None
         key = (tuple(shapes), tuple(owner), dtype)
         cache = self.__dict__.setdefault("_arenas", {})
@@ -200,7 +203,7 @@ class TileParallelVAE:
             if arena is not None and self.rank != 0:
                 copy_stream.wait_stream(torch.cuda.current_stream(x.device))
                 with torch.cuda.stream(copy_stream):
-                    slots[k].copy_(t, non_blocking=True)
+                    N.peer_copy(slots[k], t)     # one cudaMemcpyAsync on THIS device's stream; nothing runs on rank 0's GPU
                 t.record_stream(copy_stream)
             return t
 

@@ -155,6 +155,12 @@ int hyvae_groupnorm_apply(const hyvae_vol* x, const double* sums, const float* g
  * serve every conv enqueued on the same stream. */
 int hyvae_groupnorm_finalize(double* partials, int32_t B, int64_t rows, int32_t groups, double* sums, void* stream);
 
+/* ---- tile exchange of the multi-GPU decode ------------------------------------------------------
+ * Asynchronous device-to-device copy of `bytes` bytes on `stream` (a stream of the SOURCE device) into memory that may
+ * live on a peer GPU (rank 0's tile arena mapped through CUDA IPC): copy engines over NVLink, nothing is enqueued on the
+ * destination device.  Replaces the per-rank torch.cat / replicated decode of pipeline_hunyuan_video.py:1074-1082. */
+int hyvae_peer_copy(void* dst, const void* src, int64_t bytes, void* stream);
+
 /* ---- pad / nearest upsample --------------------------------------------------------------------
  * Replaces F.pad(replicate) :74 and F.interpolate(nearest)+cat of UpsampleCausal3D.forward :152-171:
  * y (T' = 1+up_t*(T-1) if up_t==2, H*up_h, W*up_w, with any halo) <- x.  y->C may exceed x->C (zero channels). */
