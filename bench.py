@@ -36,11 +36,12 @@ FRAMES, HEIGHT, WIDTH = 129, 720, 1280
 CPU_SAMPLE_SHAPE = (1, 3, 17, 256, 256)   # bounded sample the CPU arm times (scaled to the workload by conv FLOPs)
 WORKLOAD = "config4: enable_tiling(); encode(1x3x129x720x1280) -> mode() -> decode(); 84+84 sub-model calls"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the committed `ncu --set full`
-# capture (profiles/r01_ncu_conv_halo_pair_128.txt): conv_halo_kernel<half,128,2,pair>, 128 -> 128 channels, 17x256x256
-# voxels with residual and fused GroupNorm statistics.  Algorithmic bytes of that launch: x 302 MB (with halo) + residual
-# 285 MB + y 285 MB = 872 MB.
-NCU_TRAFFIC = {"bytes": 985.8e6, "note": "one 128->128 17x256x256 launch (ncu --set full, profiles/r01_ncu_conv_halo_pair_128.txt): "
-                                         "722.8 MB read + 263.0 MB written vs 872 MB algorithmic (x with halo + residual + y)"}
+# capture (profiles/r02_ncu_conv_wino_128_v2.txt): conv_wino_kernel<half>, 128 -> 128 channels, 17x256x256 voxels with residual
+# and fused GroupNorm statistics.  Algorithmic bytes of that launch: Winograd-T planes 33 x 258 x 258 x 128 x 2 B = 562 MB +
+# residual 285 MB + y 285 MB = 1133 MB.
+NCU_TRAFFIC = {"bytes": 1116.4e6, "note": "one 128->128 17x256x256 launch of conv_wino_kernel (ncu --set full, "
+                                          "profiles/r02_ncu_conv_wino_128_v2.txt): 849.5 MB read + 266.9 MB written vs 1133 MB algorithmic "
+                                          "(33 Winograd-T planes with halo + residual + y); tensor pipe active 90.6 % of the cycles"}
 
 
 def _peaks():
@@ -367,7 +368,7 @@ def run_ours(args):
         line = {
             "metric": metric, "value": frames_per_step / (ms_per_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-            "dtype": "bf16 model and I/O; fp16 tensor-core operands (bf16 weights convert exactly), fp32 accumulate",
+            "dtype": "bf16 model and I/O; fp16 tensor-core operands (bf16 weights convert exactly; Winograd-T / phase tap sums rounded once to fp16), fp32 accumulate",
             "data": "synthetic",
             "config": {"workload": workload,
                        "weights": "random-init, HY VAE config [128,256,512,512], 16 latent channels",
@@ -379,7 +380,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "e2e": None if args.no_e2e else {"value": frames_per_step / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": host_video.numel() * 4, "d2h_bytes_per_step": int(host_out.numel() * 2)},
-            "roofline": {"kernel": "tcgen05 implicit-GEMM CausalConv3d (conv_halo_kernel, conv_tc2_kernel, conv_tc_kernel, conv_stack_kernel)",
+            "roofline": {"kernel": "tcgen05 implicit-GEMM CausalConv3d (conv_wino_kernel = Winograd F(2,3) along T for the stride-1 3x3x3 layers; "
+                                   "conv_tc2_kernel sub-pixel phases / strided / k=1; conv_halo_kernel conv_in; conv_stack_kernel conv_out)",
                          "bound": "tensor", "achieved": tc_tflops, "peak": peak, "unit": "TFLOP/s", "frac": tc_tflops / peak,
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['_source']}): the kernels run inside a multi-second step under the 1 kW cap",
                          "frac_of_burst_peak": tc_tflops / peaks["bf16_tflops"],
@@ -389,8 +391,9 @@ def run_ours(args):
                                                    "library_counted_tflop_per_step_all_ranks": lib_total.item() / args.steps / 1e12,
                                                    "note": "library counters use stored (zero-padded) channel counts; achieved uses SURVEY 8d's"},
                          "executed_tflops": exec_tflops,
-                         "executed_note": "the post-upsample convs run as sub-pixel phases over the low-res tensor (8/27 or 12/27 of the "
-                                          "reference MACs), so executed < algorithmic and achieved may exceed the cuBLAS-measured peak",
+                         "executed_note": "the stride-1 3x3x3 convs run as Winograd F(2,3) along T (2T-1 instead of 3T plane GEMMs) and the "
+                                          "post-upsample convs as sub-pixel phases over the low-res tensor (8/27 or 12/27 of the reference MACs), "
+                                          "so executed < algorithmic and achieved exceeds the cuBLAS-measured peak",
                          "traffic": NCU_TRAFFIC["bytes"], "traffic_note": NCU_TRAFFIC["note"],
                          "launches_per_step": tc["launches"] / args.steps, "ms_per_step": tc["ms"] / args.steps,
                          "measured": prof_pass, "rank": 0},

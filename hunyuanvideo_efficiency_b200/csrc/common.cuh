@@ -1,6 +1,8 @@
 // Shared helpers for libhyvae.so (sm_100a).  See include/hyvae.h for the ABI.
 #pragma once
 
+#include <cstdlib>
+
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -182,6 +184,15 @@ inline int num_sms() {
     if (n[dev] <= 0) n[dev] = 148;
   }
   return n[dev];
+}
+// SMs the persistent tensor-core conv kernels occupy (grid = conv_sms() CTAs, one per SM).  HYVAE_CONV_SMS < the SM count
+// leaves SMs free on which the HBM-bound passes of ANOTHER tile stream (GroupNorm apply, halo fill) run concurrently with a
+// conv instead of queueing behind it; even, >= 2.
+inline int conv_sms() {
+  static const int want = [] { const char* e = getenv("HYVAE_CONV_SMS"); return e ? atoi(e) : 0; }();
+  const int n = num_sms();
+  if (want < 2 || want >= n) return n;
+  return want & ~1;
 }
 // `static DeviceOnce once; if (once.first()) { cudaFuncSetAttribute(...) ... once.done(); }`
 struct DeviceOnce {

@@ -450,7 +450,7 @@ static int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   if (PAIR) {
-    const int64_t units = (a.total + 1) / 2, max_pairs = num_sms() / 2;
+    const int64_t units = (a.total + 1) / 2, max_pairs = conv_sms() / 2;
     cfg.gridDim = dim3((unsigned)(2 * (units < max_pairs ? units : max_pairs)));
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;

@@ -775,7 +775,7 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
       return fail(HYVAE_ECUDA, "conv_tc2: cannot opt in to %d bytes of shared memory", Cfg::SMEM_BYTES);
     attr_once.done();
   }
-  const int64_t max_pairs = num_sms() / 2;
+  const int64_t max_pairs = conv_sms() / 2;
   const int64_t pairs = a.total_tiles < max_pairs ? a.total_tiles : max_pairs;
   CUtensorMap tmY = tmA, tmR = tmA;  // placeholders unless the staged TMA-store epilogue is compiled in
   if (KHT && sizeof(OT) == 2) {

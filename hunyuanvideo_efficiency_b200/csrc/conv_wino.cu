@@ -495,7 +495,7 @@ static int launch_wino_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
       return fail(HYVAE_ECUDA, "conv_wino: cannot opt in to %d bytes of shared memory", Cfg::SMEM_BYTES);
     attr_once.done();
   }
-  const int64_t max_pairs = num_sms() / 2;
+  const int64_t max_pairs = conv_sms() / 2;
   const int64_t pairs = a.total < max_pairs ? a.total : max_pairs;
   conv_wino_kernel<T, Cfg><<<(unsigned)(2 * pairs), WINO_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmY, tmR, tmX, tmW, a);
   return check_launch("conv3d_causal_wino");
