@@ -57,6 +57,7 @@ _SIGNATURES = {
     "hyvae_frame_metrics_u8": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp],
     "hyvae_avgpool_t": [_VP, _VP, _i32, _i32, _vp],
     "hyvae_interp_t_nearest": [_VP, _VP, _f32, _vp],
+    "hyvae_interp_t": [_VP, _VP, _i32, _f32, _vp],
     "hyvae_image_postprocess": [_vp, _i32, _vp, _i64, _vp],
     "hyvae_blend_crop_scatter": [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32,
                                  _i32, _i32, _i32, _i32, C.POINTER(_i64), _i32, _vp],
@@ -483,6 +484,19 @@ def interp_t_nearest(x: Vol, scale: float) -> Vol:
     import math
     y = x.like(T=int(math.floor(x.T * scale)))
     _check(lib().hyvae_interp_t_nearest(x.ref(), y.ref(), float(1.0 / scale), _stream()), "interp_t_nearest")
+    return y
+
+
+INTERP_MODES = {"nearest": 0, "trilinear": 1, "area": 2, "nearest-exact": 3}
+
+
+def interp_t(x: Vol, scale: float, mode: str) -> Vol:
+    """F.interpolate(x, scale_factor=(scale, 1, 1), mode=mode) for the modes a 5-D tensor accepts (hyvae_interp_t)."""
+    import math
+    if mode not in INTERP_MODES:
+        raise HyvaeError(f"interp_mode {mode!r}: F.interpolate takes {sorted(INTERP_MODES)} for a 5-D tensor")
+    y = x.like(T=int(math.floor(x.T * scale)))
+    _check(lib().hyvae_interp_t(x.ref(), y.ref(), INTERP_MODES[mode], float(1.0 / scale), _stream()), "interp_t")
     return y
 
 

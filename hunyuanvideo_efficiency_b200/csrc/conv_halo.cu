@@ -18,8 +18,10 @@
 //     m-tile slot; each CTA stages its own halo patch and only HALF of the weight tile, so the operand reads of the
 //     tensor core drop from 128 to 96 B/clk/SM and the weight writes from 32 to 16 B/clk/SM — the sum of all
 //     shared-memory traffic (121 B/clk) then fits under the port (it is 168 B/clk for the 1-CTA form).
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue; the producer and
-// MMA loops are warp-uniform with one elected lane issuing.
+// Roles (64 + MT * 128 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), then FOUR epilogue warps PER M-TILE SLOT
+// (warps 2..5 drain slot 0, warps 6..9 slot 1): thin layers (conv_in: 9 MMAs per 128-channel output tile) and the frame-0 / 1 tiles of
+// the temporal fold are bound by the epilogue, which one group of four warps ran at ~4 k clocks per tile.  The producer and MMA loops are
+// warp-uniform with one elected lane issuing.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -30,7 +32,7 @@
 
 namespace hyvae {
 
-constexpr int HALO_THREADS = 192;
+constexpr int HALO_THREADS = 320;   // MT = 2 everywhere: 2 + 4 * MT warps
 
 // THIN (Cin <= 16, e.g. conv_in 3 -> 128 with the input stored as 16 channels): rows are 32 bytes (one K = 16 MMA slice)
 // with SWIZZLE_32B instead of 128-byte rows that would be 7/8 zero fill: a halo stage is 10 KB, so the ring is deep enough
@@ -48,7 +50,7 @@ template <int BN, int MT, bool PAIR, bool THIN = false> struct HaloCfg {
   static constexpr int NH = (BN + 63) / 64;                          // 64-channel halves of the output tile
   static constexpr int OUT_BYTES = MT * NH * 16384;                  // one staging tile per m-tile slot: a tile's TMA store is only
                                                                      // waited for when its slot comes round again, MT tiles later
-  static constexpr int BUDGET = 227 * 1024 - 4096;                   // minus alignment slack, barrier block, per-warp bias copies
+  static constexpr int BUDGET = 227 * 1024 - 6144;                   // minus alignment slack, barrier block, per-warp bias copies (8 warps)
   static constexpr int NA_THIN_RAW = (BUDGET - OUT_BYTES - (B_BYTES + 1023) / 1024 * 1024) / A_BYTES;
   static constexpr int NA = THIN ? (NA_THIN_RAW > 8 ? 8 : NA_THIN_RAW) : 2;
   static constexpr int NB_RAW = (BUDGET - NA * A_BYTES - OUT_BYTES) / B_BYTES;
@@ -56,7 +58,8 @@ template <int BN, int MT, bool PAIR, bool THIN = false> struct HaloCfg {
   static constexpr int B_RING_BYTES = (NB * B_BYTES + 1023) / 1024 * 1024;
   static constexpr int ACC_COLS = MT * BN;
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
-  static constexpr int SMEM_BYTES = NA * A_BYTES + B_RING_BYTES + OUT_BYTES + 4096;
+  static constexpr int SMEM_BYTES = NA * A_BYTES + B_RING_BYTES + OUT_BYTES + 6144;
+  static_assert(MT == 2, "one group of four epilogue warps per m-tile slot: HALO_THREADS assumes MT == 2");
   static_assert(THIN || NB >= 3, "B ring too shallow");
   static_assert(!THIN || NA >= 4, "A ring too shallow");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -102,9 +105,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t afull = bars, aempty = afull + 8 * NA;
   const uint32_t bfull = aempty + 8 * NA, bempty = bfull + 8 * NB;
   const uint32_t tfull = bempty + 8 * NB, tempty = tfull + 16;
-  const uint32_t rfull = tempty + 16;                       // [4 warps]
-  const uint32_t tmem_slot = rfull + 8 * 4;
-  const uint32_t sbias_all = bars + 1024;                   // [4 warps][BN] fp32
+  const uint32_t rfull = tempty + 16;                       // [4 * MT warps]
+  const uint32_t tmem_slot = rfull + 8 * 4 * MT;
+  const uint32_t sbias_all = bars + 1024;                   // [4 * MT warps][BN] fp32
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
 
@@ -119,8 +122,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (a.sc_chunks) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW); }
     for (int s = 0; s < NA; ++s) { mbar_init(afull + 8 * s, NCTA); mbar_init(aempty + 8 * s, 1); }
     for (int s = 0; s < NB; ++s) { mbar_init(bfull + 8 * s, NCTA); mbar_init(bempty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull + 8 * s, 1); mbar_init(tempty + 8 * s, 128 * NCTA); }
-    for (int s = 0; s < 4; ++s) mbar_init(rfull + 8 * s, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + 8 * s, 1); mbar_init(tempty + 8 * s, 128 * MT * NCTA); }
+    for (int s = 0; s < 4 * MT; ++s) mbar_init(rfull + 8 * s, 1);
     fence_barrier_init();
   }
   if constexpr (PAIR) {
@@ -333,14 +336,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ================= epilogue warps (every CTA: its own MT m-tiles, its own TMEM) =================
     const int q = warp & 3;  // TMEM lane quarter = rows 32q .. 32q+31 of every m-tile = tile rows 4q .. 4q+3
+    const int ew = warp - 2, slot = ew >> 2;  // this warp drains m-tile slot `slot` of every work unit
     const int hh = 4 * q + (lane >> 3), ww = lane & 7;
     double gacc[BN / 32];
 #pragma unroll
     for (int j = 0; j < BN / 32; ++j) gacc[j] = 0.0;
     int gb = -1;       // batch item the accumulators belong to
     uint32_t rph = 0;  // phase of this warp's residual barrier
-    const uint32_t rbar = rfull + 8 * q;
-    const uint32_t sbias = sbias_all + q * (BN * 4);
+    const uint32_t rbar = rfull + 8 * ew;
+    const uint32_t sbias = sbias_all + ew * (BN * 4);
     epi_load_bias<BN>(a.bias, 0, a.Cout, sbias, lane);
     const uint32_t stage_q = sOut + q * 4096;  // this warp's 32 rows of a staging tile (slot i: + i * NH * 16384, half hf: + hf * 16384)
     float lacc[64];
@@ -349,14 +353,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto gn_flush = [&]() {
       if (a.gn_part == nullptr || gb < 0) return;
       if (epi_lane_acc(BN, a.gn_cpg)) {
-        epi_flush_lanes<BN>(lacc, a.gn_cpg, 0, a.gn_groups, a.gn_part + ((int64_t)gb * a.gn_rows + blockIdx.x * 4 + q) * a.gn_groups * 2, lane);
+        epi_flush_lanes<BN>(lacc, a.gn_cpg, 0, a.gn_groups, a.gn_part + ((int64_t)gb * a.gn_rows + blockIdx.x * 8 + ew) * a.gn_groups * 2, lane);
         return;
       }
       const int V = 2 * (32 / a.gn_cpg);
       const int per = 32 / V;  // lanes holding the same value
       if (lane % per == 0) {
         const int idx = lane / per;
-        double* row = a.gn_part + ((int64_t)gb * a.gn_rows + blockIdx.x * 4 + q) * a.gn_groups * 2;
+        double* row = a.gn_part + ((int64_t)gb * a.gn_rows + blockIdx.x * 8 + ew) * a.gn_groups * 2;
 #pragma unroll
         for (int j = 0; j < BN / 32; ++j) {
           const int grp = (32 * j) / a.gn_cpg + (idx >> 1);
@@ -375,11 +379,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (live && m.b != gb) { gn_flush(); gb = m.b; }
       // The staging rows of this warp are reused by every m-tile: they are free once the previous TMA stores have read
       // them.  The residual tile of the first m-tile is fetched while the MMAs of this group are still running.
-      // Every m-tile slot commits exactly one bulk group per work unit (an empty one if the tile is skipped), so when
-      // slot i is acquired the group that last read it is the MT-th newest: allow the MT - 1 newer ones to be pending.
+      // A warp owns one m-tile slot: its previous TMA store (one unit ago) is the only bulk group that read the staging rows.
       auto stage_acquire = [&](int i) {
         if (lane == 0) {
-          bulk_wait_read<MT - 1>();
+          bulk_wait_read<0>();
           if (a.has_res) {
             mbar_expect_tx(rbar, NH * 4096);
 #pragma unroll
@@ -389,17 +392,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         __syncwarp();
       };
-      if (live) stage_acquire(0);
+      const int i = slot;
+      const bool mine = live && m.w0 + 8 * i < a.Wo;   // warp-uniform
+      if (mine) stage_acquire(i);
       mbar_wait(tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const bool row_ok = (m.h0 + hh) < a.Ho;
-#pragma unroll 1
-      for (int i = 0; i < MT; ++i) {
-        if (!live || m.w0 + 8 * i >= a.Wo) {  // warp-uniform
-          if (lane == 0) bulk_commit();        // keep one group per slot and unit
-          continue;
-        }
-        if (i > 0) stage_acquire(i);
+      if (mine) {
         const uint32_t stage_w = stage_q + i * NH * 16384;
         const bool valid = row_ok && (m.w0 + 8 * i + ww) < a.Wo;
         if (a.has_res) { mbar_wait(rbar, rph); rph ^= 1u; }

@@ -54,6 +54,7 @@ struct WinoArgs {
   double* gn_cta;          // [B][gn_cta_rows][gn_groups][2] per-CTA rows (inside the caller's partial buffer)
   unsigned int* gn_ticket; // arrival counter of the fold (zero between launches)
   int gn_cta_rows;
+  int probe;               // measurement only (HYVAE_TC_PROBE): bit 0 = no weight loads once the ring is primed, bit 3 = no plane loads either
 };
 int launch_wino(int dtype, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmR,
                 const CUtensorMap& tmX, const CUtensorMap& tmW, const WinoArgs& a, cudaStream_t stream);

@@ -207,6 +207,7 @@ conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ================= A producer: one {64 ch, 10, 18} plane patch per (GEMM, 64-channel chunk) =================
     int sa = 0; uint32_t pa = 0;
+    int afills = 0;
     for (uint32_t it = item0; it < nitems; it += istride) {
       const WinoItem m = wino_decode(a, it, rank);
       for (int gi = 0; gi < m.ngemm; ++gi) {
@@ -214,9 +215,12 @@ conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int st = 0; st < nst; ++st) {
           const bool sc = st >= kchunks;   // shortcut input: logical (unpadded) coordinates, the 1-voxel rim of the box is never read
           mbar_wait(aempty + 8 * sa, pa ^ 1);
+          const bool skipa = (a.probe & 8) && afills >= NA;   // measurement only
+          ++afills;
           if (elect_one()) {
-            if (leader) mbar_expect_tx(afull + 8 * sa, 2 * Cfg::A_TX);
-            if (sc) tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmX, afull + 8 * sa, (st - kchunks) * 64, m.w0 - 1, m.h0 - 1, gi == 0 ? m.ta : m.tb, m.b);
+            if (leader) { if (skipa) mbar_arrive(afull + 8 * sa); else mbar_expect_tx(afull + 8 * sa, 2 * Cfg::A_TX); }
+            if (skipa) {}
+            else if (sc) tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmX, afull + 8 * sa, (st - kchunks) * 64, m.w0 - 1, m.h0 - 1, gi == 0 ? m.ta : m.tb, m.b);
             else tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull + 8 * sa, st * 64, m.w0, m.h0, m.plane0 + gi, m.b);
             if (!leader) mbar_arrive_leader(afull + 8 * sa);
           }
@@ -228,6 +232,7 @@ conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ================= B producer: this CTA's 64 rows of the three kw taps of one kh row per stage =================
     int sb = 0; uint32_t pb = 0;
+    int bfills = 0;
     for (uint32_t it = item0; it < nitems; it += istride) {
       const WinoItem m = wino_decode(a, it, rank);
       const int n0 = m.nt * WINO_BN + (int)rank * (WINO_BN / 2);
@@ -237,9 +242,11 @@ conv_wino_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
           for (int kh = 0; kh < 3; ++kh) {
             mbar_wait(bempty + 8 * sb, pb ^ 1);
+            const bool skipb = (a.probe & 1) && bfills >= NB;   // measurement only
+            ++bfills;
             if (elect_one()) {
-              if (leader) mbar_expect_tx(bfull + 8 * sb, 2 * Cfg::B_BYTES);
-              tma_load_3d_2sm(sB + sb * Cfg::B_BYTES, &tmB, bfull + 8 * sb, st * 64, n0, (m.wgroup0 + gi) * 9 + kh * 3);
+              if (leader) { if (skipb) mbar_arrive(bfull + 8 * sb); else mbar_expect_tx(bfull + 8 * sb, 2 * Cfg::B_BYTES); }
+              if (!skipb) tma_load_3d_2sm(sB + sb * Cfg::B_BYTES, &tmB, bfull + 8 * sb, st * 64, n0, (m.wgroup0 + gi) * 9 + kh * 3);
               if (!leader) mbar_arrive_leader(bfull + 8 * sb);
             }
             __syncwarp();
@@ -570,6 +577,7 @@ extern "C" int hyvae_conv3d_causal_wino(const hyvae_vol* planes, int32_t T, cons
   }
   a.gn_part = gn_partials; a.gn_groups = gn_groups; a.gn_cpg = 0; a.gn_rows = gn_partial_rows();
   a.gn_sums = nullptr; a.gn_cta = nullptr; a.gn_ticket = nullptr; a.gn_cta_rows = num_sms();
+  { const char* pe = getenv("HYVAE_TC_PROBE"); a.probe = pe ? atoi(pe) : 0; }  // measurement only: results are garbage when set
   if (gn_partials && gn_sums) {   // the buffer has the hyvae_gn_partials_doubles() layout: warp rows | CTA rows | ticket
     HYVAE_CHECK_ARG(y->B * gn_groups * 2 <= 4096, "fused GroupNorm finalize: B * groups too large");
     a.gn_sums = gn_sums;

@@ -585,7 +585,11 @@ __global__ void __launch_bounds__(256) softmax_frame_causal_kernel(const float* 
 // ------------------------------------------------------------------------------------------------
 // temporal avg-pool (front-replicated) and nearest temporal interpolation
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MODE>  // MODE 0: avgpool (k, s);  MODE 1: nearest interp (inv_scale)
+// MODE 0: avgpool (k, s);  1: nearest interp (inv_scale);  2: linear interp along T = F.interpolate(mode='trilinear',
+// align_corners=False) with unit H / W scale: src = max((t + 0.5) * inv_scale - 0.5, 0), lerp of frames floor(src), floor(src)+1
+// in fp32;  3: 'area' = adaptive average over [floor(t * Tin / Tout), ceil((t + 1) * Tin / Tout));  4: 'nearest-exact' =
+// frame min(floor((t + 0.5) * inv_scale), Tin - 1)   (ATen's UpSample.h index rules for a given scale_factor)
+template <typename T, int MODE>
 __global__ void temporal_kernel(Vol x, Vol y, int k, int s, float inv_scale) {
   const int C = x.C;
   const int64_t total = (int64_t)y.B * y.T * y.H * y.W * C;
@@ -601,8 +605,21 @@ __global__ void temporal_kernel(Vol x, Vol y, int k, int s, float inv_scale) {
       float acc = 0.f;
       for (int j = 0; j < k; ++j) acc += to_f<T>(xs[x.at(b, max(t * s + j - (k - 1), 0), h, w) + c]);
       o = acc / (float)k;
-    } else {
+    } else if (MODE == 1) {
       int ts = min((int)floorf((float)t * inv_scale), x.T - 1);
+      o = to_f<T>(xs[x.at(b, ts, h, w) + c]);
+    } else if (MODE == 2) {
+      const float src = fmaxf(((float)t + 0.5f) * inv_scale - 0.5f, 0.f);
+      const int t0 = min((int)src, x.T - 1), t1 = min(t0 + 1, x.T - 1);
+      const float l1 = src - (float)t0, l0 = 1.f - l1;
+      o = l0 * to_f<T>(xs[x.at(b, t0, h, w) + c]) + l1 * to_f<T>(xs[x.at(b, t1, h, w) + c]);
+    } else if (MODE == 3) {
+      const int a0 = (int)(((int64_t)t * x.T) / y.T), a1 = (int)((((int64_t)t + 1) * x.T + y.T - 1) / y.T);
+      float acc = 0.f;
+      for (int j = a0; j < a1; ++j) acc += to_f<T>(xs[x.at(b, j, h, w) + c]);
+      o = acc / (float)(a1 - a0);
+    } else {
+      int ts = min((int)floorf(((float)t + 0.5f) * inv_scale), x.T - 1);
       o = to_f<T>(xs[x.at(b, ts, h, w) + c]);
     }
     yd[y.at(b, t, h, w) + c] = from_f<T>(o);
@@ -1005,6 +1022,22 @@ int hyvae_interp_t_nearest(const hyvae_vol* x, const hyvae_vol* y, float inv_sca
   ProfScope prof(PC_TEMPORAL, (double)total * dtype_size(x->dtype) * 2, stream);
   HYVAE_DISPATCH_DTYPE(x->dtype, T, (temporal_kernel<T, 1><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(vx, vy, 0, 0, inv_scale)));
   return check_launch("interp_t_nearest");
+}
+
+int hyvae_interp_t(const hyvae_vol* x, const hyvae_vol* y, int32_t mode, float inv_scale, void* stream) {
+  if (mode == HYVAE_INTERP_NEAREST) return hyvae_interp_t_nearest(x, y, inv_scale, stream);
+  if (int e = check_vol(x, "x")) return e;
+  if (int e = check_vol(y, "y")) return e;
+  HYVAE_CHECK_ARG(y->H == x->H && y->W == x->W && y->C == x->C && y->B == x->B && x->dtype == y->dtype, "interp_t: y shape mismatch");
+  HYVAE_CHECK_ARG(mode == HYVAE_INTERP_LINEAR || mode == HYVAE_INTERP_AREA || mode == HYVAE_INTERP_NEAREST_EXACT, "interp_t: unknown mode %d", mode);
+  Vol vx = make_vol(x), vy = make_vol(y);
+  int64_t total = (int64_t)y->B * y->T * y->H * y->W * y->C;
+  ProfScope prof(PC_TEMPORAL, (double)total * dtype_size(x->dtype) * 2, stream);
+  const int g = grid_for(total, 256);
+  if (mode == HYVAE_INTERP_LINEAR) { HYVAE_DISPATCH_DTYPE(x->dtype, T, (temporal_kernel<T, 2><<<g, 256, 0, (cudaStream_t)stream>>>(vx, vy, 0, 0, inv_scale))); }
+  else if (mode == HYVAE_INTERP_AREA) { HYVAE_DISPATCH_DTYPE(x->dtype, T, (temporal_kernel<T, 3><<<g, 256, 0, (cudaStream_t)stream>>>(vx, vy, 0, 0, inv_scale))); }
+  else { HYVAE_DISPATCH_DTYPE(x->dtype, T, (temporal_kernel<T, 4><<<g, 256, 0, (cudaStream_t)stream>>>(vx, vy, 0, 0, inv_scale))); }
+  return check_launch("interp_t");
 }
 
 int hyvae_image_postprocess(const void* src, int32_t src_dtype, float* dst, int64_t n, void* stream) {

@@ -705,9 +705,13 @@ class UpDecoderBlockCausal3D(nn.Module):
 
     @staticmethod
     def _interp(x: Vol, conf) -> Vol:
-        if conf["mode"] != "nearest":
-            raise NotImplementedError(f"interp_mode {conf['mode']!r}: only 'nearest' has a CUDA kernel")
-        return N.interp_t_nearest(x, conf["scale_factor"]) if x.T > 0 else x
+        if x.T <= 0:
+            return x
+        if conf["mode"] == "nearest":
+            return N.interp_t_nearest(x, conf["scale_factor"])
+        if conf["mode"] not in N.INTERP_MODES:   # F.interpolate raises for 'linear' / 'bilinear' / 'bicubic' on a 5-D tensor as well
+            raise NotImplementedError(f"interp_mode {conf['mode']!r} is not defined for 5-D tensors")
+        return N.interp_t(x, conf["scale_factor"], conf["mode"])
 
     def forward_vol(self, x: Vol) -> Vol:
         for i, resnet in enumerate(self.resnets):

@@ -211,6 +211,11 @@ int hyvae_frame_metrics_u8(const void* a, const void* b, int32_t N, int32_t H, i
  * ATen's nearest source-index rule). */
 int hyvae_avgpool_t(const hyvae_vol* x, const hyvae_vol* y, int32_t k, int32_t s, void* stream);
 int hyvae_interp_t_nearest(const hyvae_vol* x, const hyvae_vol* y, float inv_scale, void* stream);
+/* The other modes F.interpolate accepts for a 5-D tensor (the t-ops JSON passes `interp_mode` through, :889-897,904-910):
+ * 'trilinear' (align_corners=False; with unit H / W scale a linear interpolation of two frames), 'area' (adaptive average)
+ * and 'nearest-exact', with ATen's source-index rules for a given scale_factor.  y.T = floor(x.T * scale). */
+enum { HYVAE_INTERP_NEAREST = 0, HYVAE_INTERP_LINEAR = 1, HYVAE_INTERP_AREA = 2, HYVAE_INTERP_NEAREST_EXACT = 3 };
+int hyvae_interp_t(const hyvae_vol* x, const hyvae_vol* y, int32_t mode, float inv_scale, void* stream);
 
 /* ---- tile blend + crop + scatter ---------------------------------------------------------------
  * Replaces blend_v / blend_h / blend_t (autoencoder_kl_causal_3d.py:344-360), the [:limit] crops and

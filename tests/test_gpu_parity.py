@@ -221,6 +221,9 @@ def test_temporal_pool_and_interp():
         assert torch.allclose(N.avgpool_t(_vol(x), k, s).to_ncthw().cpu(), O.t_avg_pool(x, k, s), atol=1e-6)
     for sc in (2, 3, 1.5):
         assert torch.equal(N.interp_t_nearest(_vol(x), sc).to_ncthw().cpu(), O.t_interp(x, sc, "nearest"))
+        assert torch.equal(N.interp_t(_vol(x), sc, "nearest-exact").to_ncthw().cpu(), O.t_interp(x, sc, "nearest-exact"))
+        for mode in ("trilinear", "area"):   # the other modes F.interpolate takes for a 5-D tensor (unet_causal_3d_blocks.py:889-897)
+            assert torch.allclose(N.interp_t(_vol(x), sc, mode).to_ncthw().cpu(), O.t_interp(x, sc, mode), atol=1e-5), (sc, mode)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -581,6 +584,8 @@ def test_tc_winograd_t_conv_matches_oracle(B, Cin, Cout, T, H, W, res, gn):
         assert (y.gn_sums.cpu()[..., 0] - o64.sum((2, 3))).abs().max() < 2e-3 * o64.abs().sum((2, 3)).max()
     y2 = conv.forward_vol(norm.forward_vol(_vol(x), True, wino=True), residual=_vol(r) if res else None)
     assert torch.equal(y.t, y2.t)                                              # static schedule: bit-reproducible
+    if gn:   # the in-kernel finalize left the partial buffer and its ticket zeroed: the second launch finds the same sums
+        assert torch.equal(y.gn_sums, y2.gn_sums)
 
 
 def test_tc_winograd_t_matches_plain_path_in_a_resnet_block(monkeypatch):
