@@ -226,6 +226,16 @@ def test_temporal_pool_and_interp():
             assert torch.allclose(N.interp_t(_vol(x), sc, mode).to_ncthw().cpu(), O.t_interp(x, sc, mode), atol=1e-5), (sc, mode)
 
 
+def test_peer_copy_is_a_stream_ordered_device_copy():
+    """hyvae_peer_copy (the tile push of vae/tile_parallel.py; on one GPU the 'peer' is the same device)."""
+    N = _N()
+    src = torch.randn(3, 5, 7, device=_dev()).to(torch.bfloat16)
+    dst = torch.zeros_like(src)
+    N.peer_copy(dst, src)
+    torch.cuda.synchronize()
+    assert torch.equal(dst, src)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_blend_bit_exact(dtype):
     from hunyuanvideo_efficiency_b200.vae import AutoencoderKLCausal3D

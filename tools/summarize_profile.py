@@ -1,6 +1,6 @@
 """Aggregate a HYVAE_PROFILE_DUMP csv by (class, tag): total ms, TFLOP/s or GB/s."""
 import csv, sys, collections
-names = ["conv_tc", "conv_direct", "gn_stats", "gn_apply", "pad_upsample", "softmax", "layout", "blend", "temporal", "attn"]
+names = ["conv_tc", "conv_direct", "gn_stats", "gn_apply", "pad_upsample", "softmax", "layout", "blend", "temporal", "attn", "attn_proj"]
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
 for r in csv.DictReader(open(sys.argv[1])):
     a = agg[(int(r["class"]), r["tag"])]
