@@ -247,7 +247,6 @@ class TileParallelVAE:
                 row.append((self.assemble_spatial(grid, ext_s, lim_s), 1 if tt > 0 else 0))
         if n_tt == 1 and not (v.use_temporal_tiling and T > min_t):
             if post and single:
-                from .. import _native as N
                 return N.image_postprocess(row[0][0])
             return row[0][0]
         return self.assemble_temporal(row, ext_t, lim_t, True) if post else self.assemble_temporal(row, ext_t, lim_t)
