@@ -137,25 +137,34 @@ class TileParallelVAE:
             if owner[k] != 0:
                 total += (n + 127) // 128 * 128      # keep every tile 256-byte aligned (16-byte vectors in the blend kernel)
         views, ok = None, 1
-        try:
-            from torch.multiprocessing.reductions import reduce_tensor
-            payload = [None]
-            if self.rank == 0:
-                self._arena_owner = getattr(self, "_arena_owner", [])
+
+        def note(e):
+            if os.environ.get("HYVAE_TILE_PUSH_DEBUG"):
+                print(f"[tile_parallel] rank {self.rank}: peer-memory push unavailable: {type(e).__name__}: {e}", flush=True)
+
+        payload = [None]
+        if self.rank == 0:   # a failure here still reaches the broadcast below (payload None), so no rank waits alone
+            try:
+                from torch.multiprocessing.reductions import reduce_tensor
                 arenas = [torch.empty(max(total, 1), dtype=dtype, device=device) for _ in range(2)]
-                self._arena_owner.append(arenas)           # rank 0 keeps the allocations alive
                 payload = [[reduce_tensor(a) for a in arenas]]
-            dist.broadcast_object_list(payload, src=0, group=self.group)
+                self._arena_owner = getattr(self, "_arena_owner", []) + [arenas]   # rank 0 keeps the allocations alive
+            except Exception as e:  # noqa: BLE001
+                note(e)
+                payload = [None]
+        dist.broadcast_object_list(payload, src=0, group=self.group)
+        try:
+            if payload[0] is None:
+                raise RuntimeError("rank 0 could not export its arena")
             if self.rank != 0:
                 arenas = [fn(*args) for fn, args in payload[0]]
             views = [[None if owner[k] == 0 else a[offs[k]:offs[k] + numel[k]].view(shapes[k]) for k in range(len(shapes))] for a in arenas]
-            if self.rank != 0:   # one small write proves the mapping before the hot loop relies on it
+            if self.rank != 0:   # one small write proves the mapping (and lets torch enable peer access) before the hot loop relies on it
                 probe = torch.zeros(1, dtype=dtype, device=device)
                 arenas[0][:1].copy_(probe)
                 torch.cuda.synchronize(device)
         except Exception as e:  # noqa: BLE001 - any failure (no peer access, IPC refused in this container) selects the gather
-            if os.environ.get("HYVAE_TILE_PUSH_DEBUG"):
-                print(f"[tile_parallel] rank {self.rank}: peer-memory push unavailable: {type(e).__name__}: {e}", flush=True)
+            note(e)
             ok, views = 0, None
         flag = torch.tensor([ok], dtype=torch.int32, device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)   # every rank takes the same path
