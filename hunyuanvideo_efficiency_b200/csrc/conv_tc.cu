@@ -50,6 +50,7 @@ struct TcArgs {
   // the sub-pixel decomposition of nearest-upsample + conv (hyvae_conv3d_upphase_tc) has 2 (or 3) x 2 x 2 taps and a
   // box origin shifted by the phase.  Weight tap index = (kt * nsub + kh) * nkw + kw.
   int nkt, nkw, nsub, ot, oh, ow, a_tx;
+  int halo2d;             // kh-trick pair kernel, sub-pixel phases: ONE {64 ch, TW + nkw - 1, TH + nsub - 1} halo stage per (kt, chunk) feeds all (kh, kw) taps
   int sc_chunks, sc_cin;  // kh-trick pair kernel: fused 1x1x1 shortcut conv (64-channel chunks / channels of its input)
   int tfold;              // kh-trick pair kernel, standard 3x3x3 taps: weights carry the folded first-frame taps (tfold_class)
 };
@@ -403,7 +404,38 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           // (kt, kw, channel chunk) groups as nested loops: the flat index with its divisions per group was part of what
           // kept this warp (one A and nsub B loads per group) from staying ahead of the MMA warp on the short phase convs
           const int nkt_eff = a.tfold ? cls + 1 : a.nkt;
-          for (int kt = 0; kt < nkt_eff; ++kt) {
+          if (a.halo2d) {
+            // 2-D halo stage (sub-pixel phases): one A load per (kt, chunk), then the nkw * nsub weight taps it feeds
+            for (int kt = 0; kt < a.nkt; ++kt) {
+              for (int kc = 0; kc < kchunks; ++kc) {
+                if (do_a) {
+                  mbar_wait(aempty_bar + 8 * sa, pa ^ 1);
+                  if (elect_one()) {
+                    if (leader) mbar_expect_tx(afull_bar + 8 * sa, 2 * a.a_tx);
+                    tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull_bar + 8 * sa, kc * 64, m.w0 + a.ow, m.h0 + a.oh, m.t + a.ot + kt, m.b);
+                    if (!leader) mbar_arrive_leader(afull_bar + 8 * sa);
+                  }
+                  __syncwarp();
+                  if (++sa == NA) { sa = 0; pa ^= 1; }
+                }
+                if (do_b) {
+                  for (int kw = 0; kw < a.nkw; ++kw) {
+                    for (int sub = 0; sub < nsub; ++sub) {
+                      mbar_wait(bempty_bar + 8 * sb, pb ^ 1);
+                      if (elect_one()) {
+                        if (leader) mbar_expect_tx(bfull_bar + 8 * sb, 2 * Cfg::B_STAGE_BYTES);
+                        tma_load_3d_2sm(sB + sb * Cfg::B_STAGE_BYTES, &tmB, bfull_bar + 8 * sb, kc * 64, n0, (kt * a.nsub + sub) * a.nkw + kw);
+                        if (!leader) mbar_arrive_leader(bfull_bar + 8 * sb);
+                      }
+                      __syncwarp();
+                      if (++sb == SB) { sb = 0; pb ^= 1; }
+                    }
+                  }
+                }
+              }
+            }
+          }
+          for (int kt = 0; kt < nkt_eff && !a.halo2d; ++kt) {
             const int wkt = a.tfold ? tfold_wgroup(cls, kt) : kt;
             for (int kw = 0; kw < a.nkw; ++kw) {
               for (int kc = 0; kc < kchunks; ++kc) {
@@ -560,7 +592,41 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (++sa == NA) { sa = 0; pa ^= 1; }
             }
           };
-          if (nsub == 3) run_groups(std::integral_constant<int, 3>{});
+          if (a.halo2d) {
+            // sub-pixel phase with a 2-D halo stage: 2 x 2 (kh, kw) taps per stage; tap (kh, kw) = + (kh * PITCH + kw) rows of
+            // 128 B with the 8-row-group stride PITCH * 128 B (PITCH = TW + 1 columns; the swizzle follows absolute address bits)
+            const uint32_t pitch = (uint32_t)(a.TW + a.nkw - 1);
+            const uint64_t hdesc0 = (uint64_t)((sA >> 4) & 0x3FFF) | ((uint64_t)(((pitch * 128u) >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+            const int nstage = a.nkt * kchunks;
+#pragma unroll 1
+            for (int g = 0; g < nstage; ++g) {
+              mbar_wait(afull_bar + 8 * sa, pa);
+              const uint64_t ad = hdesc0 + (uint64_t)((uint32_t)sa * (uint32_t)(Cfg::A_BYTES >> 4));
+              const uint32_t first = g != 0 ? 1u : 0u;
+#pragma unroll
+              for (int kw = 0; kw < 2; ++kw) {
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                  mbar_wait(bfull_bar + 8 * sb, pb);
+                  tc_fence_after();
+                  if (elect_one()) {
+                    const uint64_t as = ad + (uint64_t)(((uint32_t)sub * pitch + (uint32_t)kw) * 8u);
+                    const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)sb * (uint32_t)(Cfg::B_STAGE_BYTES >> 4));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_f16_2sm(d_tmem, as + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kw | sub | k) != 0 ? 1u : first);
+                    umma_commit_2sm(bempty_bar + 8 * sb);
+                  }
+                  __syncwarp();
+                  if (++sb == SB) { sb = 0; pb ^= 1; }
+                }
+              }
+              if (elect_one()) umma_commit_2sm(aempty_bar + 8 * sa);
+              __syncwarp();
+              if (++sa == NA) { sa = 0; pa ^= 1; }
+            }
+          }
+          else if (nsub == 3) run_groups(std::integral_constant<int, 3>{});
           else if (nsub == 2) run_groups(std::integral_constant<int, 2>{});
           else run_groups(std::integral_constant<int, 1>{});
         }
@@ -868,7 +934,7 @@ static int conv_tc_entry(const hyvae_vol* x, const void* w, const float* bias, c
   a.B = y->B; a.To = y->T; a.Ho = y->H; a.Wo = y->W; a.Cin = x->C; a.Cout = y->C;
   a.k = k; a.st = st; a.sh = sh; a.sw = sw; a.round_like_ref = round_like_ref;
   { const char* pe = getenv("HYVAE_TC_PROBE"); a.probe = pe ? atoi(pe) : 0; }  // measurement only: results are garbage when set
-  a.nkt = a.nkw = a.nsub = 3; a.ot = a.oh = a.ow = 0; a.a_tx = 18 * 1024;
+  a.nkt = a.nkw = a.nsub = 3; a.ot = a.oh = a.ow = 0; a.a_tx = 18 * 1024; a.halo2d = 0;
   a.sc_chunks = a.sc_cin = 0;
   // variant bit 8: `w` holds 45 tap slices, the 27 of the conv followed by the 18 folded first-frame taps (tfold_class);
   // used by the halo and kh-trick kernels for stride-1 3x3x3 convs, ignored (first 27 slices) by every other kernel
@@ -1171,7 +1237,10 @@ extern "C" int hyvae_conv3d_upphase_tc(const hyvae_vol* x, const void* w, const 
   a.B = y->B; a.To = To; a.Ho = x->H; a.Wo = x->W; a.Cin = x->C; a.Cout = y->C;
   a.k = 3; a.st = a.sh = a.sw = 1; a.round_like_ref = 0;
   { const char* pe = getenv("HYVAE_TC_PROBE"); a.probe = pe ? atoi(pe) : 0; }
-  a.nkt = nkt; a.nkw = 2; a.nsub = 2; a.ot = (up_t == 2 && pt == 1) ? 1 : 0; a.oh = ph; a.ow = pw; a.a_tx = 17 * 1024;
+  a.nkt = nkt; a.nkw = 2; a.nsub = 2; a.ot = (up_t == 2 && pt == 1) ? 1 : 0; a.oh = ph; a.ow = pw;
+  // 2-D halo stage {64 ch, 9, 17}: the two kw taps read the same stage one column apart (HYVAE_PHASE_HALO2D=0: one {64, 8, 17} stage per kw)
+  { const char* e = getenv("HYVAE_PHASE_HALO2D"); a.halo2d = (e && e[0] == '0') ? 0 : 1; }
+  a.a_tx = (a.halo2d ? 9 : 8) * 17 * 128;
   a.sc_chunks = a.sc_cin = 0;
   a.tfold = 0;
   a.TH = 16; a.TW = 8;
@@ -1192,7 +1261,7 @@ extern "C" int hyvae_conv3d_upphase_tc(const hyvae_vol* x, const void* w, const 
   {
     cuuint64_t dims[5] = {(cuuint64_t)x->C, (cuuint64_t)vx.Wp(), (cuuint64_t)vx.Hp(), (cuuint64_t)vx.Tp(), (cuuint64_t)x->B};
     cuuint64_t strides[4] = {(cuuint64_t)vx.sW * 2, (cuuint64_t)vx.sH * 2, (cuuint64_t)vx.sT * 2, (cuuint64_t)vx.sB * 2};
-    cuuint32_t box[5] = {64, 8, 17, 1, 1};
+    cuuint32_t box[5] = {64, (cuuint32_t)(a.halo2d ? 9 : 8), 17, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = encode(&tmA, dt, 5, x->data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
