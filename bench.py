@@ -391,6 +391,9 @@ def run_ours(args):
                                                    "library_counted_tflop_per_step_all_ranks": lib_total.item() / args.steps / 1e12,
                                                    "note": "library counters use stored (zero-padded) channel counts; achieved uses SURVEY 8d's"},
                          "executed_tflops": exec_tflops,
+                         "executed_frac_of_sustained_peak": exec_tflops / peak, "executed_frac_of_burst_peak": exec_tflops / peaks["bf16_tflops"],
+                         "tensor_pipe_active_ncu": {"conv_wino_kernel 128->128": 0.906, "conv_wino_kernel 256->256": 0.936,
+                                                    "source": "profiles/r02_ncu_conv_wino_{128,256}_v2.txt (sm__pipe_tensor_cycles_active, one launch each)"},
                          "executed_note": "the stride-1 3x3x3 convs run as Winograd F(2,3) along T (2T-1 instead of 3T plane GEMMs) and the "
                                           "post-upsample convs as sub-pixel phases over the low-res tensor (8/27 or 12/27 of the reference MACs), "
                                           "so executed < algorithmic and achieved exceeds the cuBLAS-measured peak",
