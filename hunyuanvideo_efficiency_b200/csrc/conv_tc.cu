@@ -469,46 +469,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         }
-        for (int g = 0; g < ngroups_t && !KHT; ++g) {
+        for (int g = 0; g < ngroups_t && !KHT; ++g) {   // per-tap form: one stage = the A tile and the weight tile of one (tap, chunk)
           const int kc = g % kchunks, tg = g / kchunks;
-          int kt, kh0, kw;
-          if (KHT) { kt = tg / a.nkw; kw = tg % a.nkw; kh0 = 0; }
-          else { kt = tg / (a.k * a.k); kh0 = (tg / a.k) % a.k; kw = tg % a.k; }
-          const int wkt = (KHT && a.tfold) ? tfold_wgroup(cls, kt) : kt;
-          if (KHT) {
-            mbar_wait(aempty_bar + 8 * sa, pa ^ 1);
-            const bool skip = (a.probe & 1) && afills >= NA;
-            ++afills;
-            if (elect_one()) {
-              if (leader) { if (skip) mbar_arrive(afull_bar + 8 * sa); else mbar_expect_tx(afull_bar + 8 * sa, 2 * a.a_tx); }
-              if (!skip) tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull_bar + 8 * sa, kc * 64, m.w0 + a.ow + kw, m.h0 + a.oh, m.t + a.ot + tshift + kt, m.b);
-              if (!leader) mbar_arrive_leader(afull_bar + 8 * sa);
+          const int kt = tg / (a.k * a.k), kh = (tg / a.k) % a.k, kw = tg % a.k;
+          mbar_wait(bempty_bar + 8 * sb, pb ^ 1);
+          const bool skipb = (a.probe & 1) && bfills >= SB;
+          ++bfills;
+          if (elect_one()) {
+            if (leader) {
+              if (skipb) mbar_arrive(bfull_bar + 8 * sb);
+              else mbar_expect_tx(bfull_bar + 8 * sb, 2 * (Cfg::B_STAGE_BYTES + Cfg::A_BYTES));
             }
-            __syncwarp();
-            if (++sa == NA) { sa = 0; pa ^= 1; }
-          }
-#pragma unroll
-          for (int sub = 0; sub < NSUB; ++sub) {
-            if (sub >= nsub) break;
-            const int kh = kh0 + sub;
-            mbar_wait(bempty_bar + 8 * sb, pb ^ 1);
-            const bool skipb = (a.probe & 1) && bfills >= SB;
-            ++bfills;
-            if (elect_one()) {
-              if (leader) {
-                if (skipb) mbar_arrive(bfull_bar + 8 * sb);
-                else mbar_expect_tx(bfull_bar + 8 * sb, 2 * (Cfg::B_STAGE_BYTES + (KHT ? 0 : Cfg::A_BYTES)));
-              }
-              if (!KHT && !skipb)
-                tma_load_5d_2sm(sA + sb * Cfg::A_BYTES, &tmA, bfull_bar + 8 * sb, kc * 64,
-                                m.w0 * a.sw + kw, m.h0 * a.sh + kh, m.t * a.st + kt, m.b);
-              if (!skipb) tma_load_3d_2sm(sB + sb * Cfg::B_STAGE_BYTES, &tmB, bfull_bar + 8 * sb, kc * 64, n0,
-                                          KHT ? (wkt * a.nsub + kh) * a.nkw + kw : (kt * a.k + kh) * a.k + kw);
-              if (!leader) mbar_arrive_leader(bfull_bar + 8 * sb);
+            if (!skipb) {
+              tma_load_5d_2sm(sA + sb * Cfg::A_BYTES, &tmA, bfull_bar + 8 * sb, kc * 64, m.w0 * a.sw + kw, m.h0 * a.sh + kh, m.t * a.st + kt, m.b);
+              tma_load_3d_2sm(sB + sb * Cfg::B_STAGE_BYTES, &tmB, bfull_bar + 8 * sb, kc * 64, n0, (kt * a.k + kh) * a.k + kw);
             }
-            __syncwarp();
-            if (++sb == SB) { sb = 0; pb ^= 1; }
+            if (!leader) mbar_arrive_leader(bfull_bar + 8 * sb);
           }
+          __syncwarp();
+          if (++sb == SB) { sb = 0; pb ^= 1; }
         }
         if (KHT) {
           // fused 1x1x1 conv_shortcut: one halo stage of the block input (box origin one row above the tile) and one
@@ -630,23 +609,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           else if (nsub == 2) run_groups(std::integral_constant<int, 2>{});
           else run_groups(std::integral_constant<int, 1>{});
         }
-        for (int g = 0; g < ngroups_t && !KHT; ++g) {
+        for (int g = 0; g < ngroups_t && !KHT; ++g) {   // per-tap form: A and B of a (tap, chunk) share the stage index
+          mbar_wait(bfull_bar + 8 * sb, pb);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t adesc = make_kmajor_sw128_desc(sA + sb * Cfg::A_BYTES);
+            const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * Cfg::B_STAGE_BYTES);
 #pragma unroll
-          for (int sub = 0; sub < NSUB; ++sub) {
-            if (sub >= nsub) break;
-            mbar_wait(bfull_bar + 8 * sb, pb);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t adesc = make_kmajor_sw128_desc(sA + sb * Cfg::A_BYTES);
-              const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb * Cfg::B_STAGE_BYTES);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (g | sub | k) != 0);
-              umma_commit_2sm(bempty_bar + 8 * sb);
-            }
-            __syncwarp();
-            if (++sb == SB) { sb = 0; pb ^= 1; }
+            for (int k = 0; k < 4; ++k)
+              umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (g | k) != 0);
+            umma_commit_2sm(bempty_bar + 8 * sb);
           }
+          __syncwarp();
+          if (++sb == SB) { sb = 0; pb ^= 1; }
         }
         if (KHT) {
           for (int kc = 0; kc < a.sc_chunks; ++kc) {  // fused shortcut: the tile rows start one row into the stage
