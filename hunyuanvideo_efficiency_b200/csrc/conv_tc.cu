@@ -317,22 +317,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // SWIZZLE_128B atom, so the A operand of tap kh is the same stage at byte offset kh*1024 — still atom aligned.  One
 // A load then feeds the three kh taps (3 B stages): A traffic from L2 drops 2.7x, which is what the Cout=128 layers
 // (half the MACs per A byte) need to leave the L2-bandwidth bound.  A and B run in separate TMA rings.
-template <int BN, bool KHT> struct Tc2Cfg {
+template <int BN, bool KHT, bool STAGED = KHT> struct Tc2Cfg {
   static constexpr int NSUB = KHT ? 3 : 1;                            // B stages (taps) consumed per A stage
   static constexpr int A_BYTES = KHT ? 20 * 1024 : A_STAGE_BYTES;     // KHT halo stage: 18 rows x 8 or 10 rows x 16 voxels
   static constexpr int B_STAGE_BYTES = (BN / 2) * 64 * 2;             // this CTA's half of the weight tile
   static constexpr int SA = KHT ? 3 : 0;                              // A ring depth (KHT); non-KHT shares the B ring index
-  // KHT kernels with a 16-bit output run the epilogue through shared memory and TMA stores (see conv_halo.cu): one
-  // 128-row x 64-channel SWIZZLE_128B staging block per 64-channel half of the tile
+  // Kernels with a 16-bit output (STAGED) run the epilogue through shared memory and TMA stores (see conv_halo.cu): one
+  // 128-row x 64-channel SWIZZLE_128B staging block per 64-channel half of the tile.  The per-tap form got it in round 2:
+  // with scattered 16-byte global stores a k = 1 GEMM (attention projections: 8 K-steps per tile) spent 50 k of its 64 k
+  // cycles in the epilogue (ncu, [17408 x 512] x [512 x 512]: 34 us for 6 us of MMA work).
   static constexpr int NH = (BN + 63) / 64;
-  static constexpr int OUT_BYTES = KHT ? NH * 16384 : 0;
-  static constexpr int BUDGET = (KHT ? 225 * 1024 - 4 * BN * 4 : 200 * 1024) - OUT_BYTES;
+  static constexpr int OUT_BYTES = STAGED ? NH * 16384 : 0;
+  static constexpr int BIAS_BYTES = STAGED ? 4 * BN * 4 : 0;
+  static constexpr int BUDGET = (KHT ? 225 * 1024 : 204 * 1024) - BIAS_BYTES - OUT_BYTES;
   static constexpr int SB_RAW = KHT ? (BUDGET - SA * A_BYTES) / B_STAGE_BYTES : BUDGET / (A_BYTES + B_STAGE_BYTES);
   static constexpr int SB = SB_RAW > 12 ? 12 : SB_RAW;
   static constexpr int NA = KHT ? SA : SB;                            // number of A buffers
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = NA * A_BYTES + SB * B_STAGE_BYTES + OUT_BYTES + 1024 + 1024 + (KHT ? 4 * BN * 4 : 0);
+  static constexpr int SMEM_BYTES = NA * A_BYTES + SB * B_STAGE_BYTES + OUT_BYTES + 1024 + 1024 + BIAS_BYTES;
   static_assert(SB >= 4, "B ring too shallow");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 template <typename T, typename OT, int BN, bool KHT>
@@ -340,9 +344,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(KHT ? TC2_KHT_THREAD
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const TcArgs a) {
-  using Cfg = Tc2Cfg<BN, KHT>;
+  constexpr bool TMA_EPI = sizeof(OT) == 2;  // staged TMA-store epilogue (16-bit output)
+  using Cfg = Tc2Cfg<BN, KHT, TMA_EPI>;
   constexpr int SB = Cfg::SB, NA = Cfg::NA, NSUB = Cfg::NSUB;
-  constexpr bool TMA_EPI = KHT && sizeof(OT) == 2;  // staged TMA-store epilogue (16-bit output, 16 x 8 tiles)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -657,6 +661,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // flushed when the (batch item, n-tile) changes.  Same scheme as conv_halo.cu.
       constexpr int NH = Cfg::NH;
       const int hq = (32 * q) / a.TW;                                  // first tile row of this warp's 32 voxels
+      const int wq = a.TW > 32 ? (32 * q) % a.TW : 0;                  // ... and their first column (tiles wider than 32 voxels)
       const int hh = (32 * q + lane) / a.TW, ww = (32 * q + lane) % a.TW;
       const uint32_t rbar = rfull_bar + 8 * q;
       const uint32_t stage_w = sOut + q * 4096;
@@ -707,7 +712,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               mbar_expect_tx(rbar, NH * 4096);
 #pragma unroll
               for (int hf = 0; hf < NH; ++hf)
-                tma_load_5d(stage_w + hf * 16384, &tmR, rbar, n0 + hf * 64, m.w0, m.h0 + hq, m.t, m.b);
+                tma_load_5d(stage_w + hf * 16384, &tmR, rbar, n0 + hf * 64, m.w0 + wq, m.h0 + hq, m.t, m.b);
             }
           }
           __syncwarp();
@@ -727,7 +732,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int hf = 0; hf < NH; ++hf)
               if (n0 + hf * 64 < a.Cout)
-                tma_store_5d(&tmY, stage_w + hf * 16384, n0 + hf * 64, m.w0, m.h0 + hq, m.t, m.b);
+                tma_store_5d(&tmY, stage_w + hf * 16384, n0 + hf * 64, m.w0 + wq, m.h0 + hq, m.t, m.b);
             bulk_commit();
           }
         }
@@ -799,7 +804,8 @@ static int encode_out_map(CUtensorMap* tm, CUtensorMapDataType dt, const void* b
   EncodeTiledFn encode = get_encode_fn();
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t strides[4] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sT * 2, (cuuint64_t)sB * 2};
-  cuuint32_t box[5] = {64, (cuuint32_t)TW, (cuuint32_t)(32 / TW), 1, 1};  // one warp's 32 voxels of a TH x TW tile
+  const int bw = TW > 32 ? 32 : TW;
+  cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)(32 / bw), 1, 1};  // one warp's 32 voxels of a TH x TW tile
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = encode(tm, dt, 5, (char*)const_cast<void*>(base) + off * 2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -809,7 +815,7 @@ static int encode_out_map(CUtensorMap* tm, CUtensorMapDataType dt, const void* b
 template <typename T, typename OT, int BN, bool KHT>
 static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream,
                       const CUtensorMap* tmX = nullptr, const CUtensorMap* tmW = nullptr) {
-  using Cfg = Tc2Cfg<BN, KHT>;
+  using Cfg = Tc2Cfg<BN, KHT, sizeof(OT) == 2>;
   static DeviceOnce attr_once;
   if (attr_once.first()) {
     if (cudaFuncSetAttribute(conv_tc2_kernel<T, OT, BN, KHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
@@ -819,7 +825,7 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcAr
   const int64_t max_pairs = conv_sms() / 2;
   const int64_t pairs = a.total_tiles < max_pairs ? a.total_tiles : max_pairs;
   CUtensorMap tmY = tmA, tmR = tmA;  // placeholders unless the staged TMA-store epilogue is compiled in
-  if (KHT && sizeof(OT) == 2) {
+  if (sizeof(OT) == 2) {
     const CUtensorMapDataType dt = TcFmt<T>::fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     if (int e = encode_out_map(&tmY, dt, a.y, a.yoff, a.Cout, a.Wo, a.Ho, a.To, a.B, a.ysW, a.ysH, a.ysT, a.ysB, a.TW)) return e;
     tmR = tmY;

@@ -51,6 +51,12 @@ elif what == "conv512s":  # mid-block conv at the canonical tile: 512 -> 512, 17
     r = N.Vol(1, 17, 32, 32, 512, torch.float16, dev); r.t.normal_()
     for _ in range(6):
         N.conv3d_tc(x, w, b, 3, (1, 1, 1), 512, residual=r, gn_groups=32)
+elif what == "gemm512":   # attention projection: [17408 x 512] x [512 x 512]^T as a k = 1 launch of the pair kernel
+    x = N.Vol(1, 1, 1, 17408, 512, torch.float16, dev); x.t.normal_()
+    w = (torch.randn(512, 512, device=dev) / 512 ** 0.5).half()
+    b = torch.randn(512, device=dev)
+    for _ in range(6):
+        N.conv3d_tc(x, w, b, 1, (1, 1, 1), 512)
 elif what == "attn":     # fused mid-block attention at the canonical tile: L = 17 x 32 x 32, D = 512
     L, D = 17408, 512
     q = torch.randn(L, D, device=dev).half(); k = torch.randn(L, D, device=dev).half()
