@@ -414,9 +414,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               for (int kc = 0; kc < kchunks; ++kc) {
                 if (do_a) {
                   mbar_wait(aempty_bar + 8 * sa, pa ^ 1);
+                  const bool skip = (a.probe & 1) && afills >= NA;
+                  ++afills;
                   if (elect_one()) {
-                    if (leader) mbar_expect_tx(afull_bar + 8 * sa, 2 * a.a_tx);
-                    tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull_bar + 8 * sa, kc * 64, m.w0 + a.ow, m.h0 + a.oh, m.t + a.ot + kt, m.b);
+                    if (leader) { if (skip) mbar_arrive(afull_bar + 8 * sa); else mbar_expect_tx(afull_bar + 8 * sa, 2 * a.a_tx); }
+                    if (!skip) tma_load_5d_2sm(sA + sa * Cfg::A_BYTES, &tmA, afull_bar + 8 * sa, kc * 64, m.w0 + a.ow, m.h0 + a.oh, m.t + a.ot + kt, m.b);
                     if (!leader) mbar_arrive_leader(afull_bar + 8 * sa);
                   }
                   __syncwarp();
@@ -426,9 +428,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                   for (int kw = 0; kw < a.nkw; ++kw) {
                     for (int sub = 0; sub < nsub; ++sub) {
                       mbar_wait(bempty_bar + 8 * sb, pb ^ 1);
+                      const bool skipb = (a.probe & 1) && bfills >= SB;
+                      ++bfills;
                       if (elect_one()) {
-                        if (leader) mbar_expect_tx(bfull_bar + 8 * sb, 2 * Cfg::B_STAGE_BYTES);
-                        tma_load_3d_2sm(sB + sb * Cfg::B_STAGE_BYTES, &tmB, bfull_bar + 8 * sb, kc * 64, n0, (kt * a.nsub + sub) * a.nkw + kw);
+                        if (leader) { if (skipb) mbar_arrive(bfull_bar + 8 * sb); else mbar_expect_tx(bfull_bar + 8 * sb, 2 * Cfg::B_STAGE_BYTES); }
+                        if (!skipb) tma_load_3d_2sm(sB + sb * Cfg::B_STAGE_BYTES, &tmB, bfull_bar + 8 * sb, kc * 64, n0, (kt * a.nsub + sub) * a.nkw + kw);
                         if (!leader) mbar_arrive_leader(bfull_bar + 8 * sb);
                       }
                       __syncwarp();
