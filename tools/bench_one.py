@@ -51,6 +51,12 @@ elif what == "conv512s":  # mid-block conv at the canonical tile: 512 -> 512, 17
     r = N.Vol(1, 17, 32, 32, 512, torch.float16, dev); r.t.normal_()
     for _ in range(6):
         N.conv3d_tc(x, w, b, 3, (1, 1, 1), 512, residual=r, gn_groups=32)
+elif what == "strided128":   # encoder down_block 0 downsampler: 128 -> 128, stride (1, 2, 2), 17 x 256 x 256 -> 17 x 128 x 128
+    x = N.Vol(1, 17, 256, 256, 128, torch.float16, dev, (2, 1, 1)); x.t.normal_()
+    w = (torch.randn(27, 128, 128, device=dev) / (27 * 128) ** 0.5).half()
+    b = torch.randn(128, device=dev)
+    for _ in range(5):
+        N.conv3d_tc(x, w, b, 3, (1, 2, 2), 128, gn_groups=32)
 elif what == "gemm512":   # attention projection: [17408 x 512] x [512 x 512]^T as a k = 1 launch of the pair kernel
     x = N.Vol(1, 1, 1, 17408, 512, torch.float16, dev); x.t.normal_()
     w = (torch.randn(512, 512, device=dev) / 512 ** 0.5).half()
